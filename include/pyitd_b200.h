@@ -1,0 +1,128 @@
+/*
+ * pyitd_b200.h -- C ABI of the B200-native ITD sifting loop (libpyitd_b200.so).
+ *
+ * The reference (falseywinchnet/PyITD) has no FFI layer: its boundary for this path is one Python
+ * class and two numba functions in /root/reference/ITD.py.  Each entry point below names the
+ * reference interface it replaces; INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add to route ITD.itd through this library.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void* (NULL = default
+ *     stream); every `_device` call is asynchronous on that stream, every `_host` call returns
+ *     after the result is in the caller's host buffers;
+ *   - signals are rows of a C-contiguous (n_signals, n_samples) matrix;
+ *   - outputs are C-contiguous (n_signals, rows, n_samples) with rows = max_iteration + 2
+ *     (the reference hard-codes 22 rows, ITD.py:384-385; ITD_numba.py:102-103 intends
+ *     max_iteration + 1 rotations + 1 trend row);
+ *   - every function returns 0 on success or a negative PYITD_E_* code; per-signal algorithmic
+ *     conditions (the exceptions the reference raises) are reported in `status[signal]`.
+ */
+#ifndef PYITD_B200_H
+#define PYITD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PYITD_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PYITD_API __attribute__((visibility("default")))
+#else
+#define PYITD_API
+#endif
+
+/* precision variants */
+#define PYITD_F64        0   /* float64 in/out, float64 carry + arithmetic: the reference's dtype   */
+#define PYITD_F32_MIXED  1   /* float32 in/out, float64 carry + arithmetic == float32(reference)    */
+#define PYITD_F32        2   /* float32 in/out/carry/arithmetic (pure fp32)          */
+
+/* per-signal status bits (status[signal]) */
+#define PYITD_ST_OK        0
+#define PYITD_ST_ZERO_DX   1  /* X[k+1] == X[k] in a segment: reference raises ZeroDivisionError, ITD.py:116 */
+#define PYITD_ST_NONFINITE 2  /* NaN/Inf in the input: the reference's NaN path (ITD.py:46-51,64-68) is unsupported */
+#define PYITD_ST_TOO_SHORT 4  /* fewer than 3 samples: undefined in the reference, ITD.py:42-43 */
+
+/* stop kinds (stop_kind[signal]) */
+#define PYITD_STOP_NONE  0
+#define PYITD_STOP_KNOTS 1    /* baseline has < min_extrema extrema, ITD.py:404-416 */
+#define PYITD_STOP_ITER  2    /* counter > max_iteration ("Out of time!"), ITD.py:418-426 */
+
+/* call-level error codes */
+#define PYITD_E_INVALID  (-1) /* bad argument */
+#define PYITD_E_CUDA     (-2) /* CUDA runtime error, see pyitd_last_error() */
+#define PYITD_E_NOMEM    (-3) /* workspace allocation failed */
+#define PYITD_E_NODEVICE (-4) /* no usable sm_100 device */
+
+/* option flags for pyitd_plan_create */
+#define PYITD_OPT_BASELINES  1  /* also produce the per-level baselines (ITD.get_baselines, ITD.py:436) */
+#define PYITD_OPT_ZERO_TAIL  2  /* zero-fill rows >= n_rows[signal] (the reference's zeros((22,N)) look) */
+
+typedef struct pyitd_plan pyitd_plan;
+
+PYITD_API int         pyitd_abi_version(void);
+PYITD_API const char *pyitd_last_error(void);      /* thread-local text of the last failure */
+PYITD_API int         pyitd_device_count(void);
+
+/*
+ * A plan owns the device workspace for one problem shape (like an FFT plan): the ping-pong carry
+ * buffers that keep every signal resident in HBM between levels, the compacted knot tables and
+ * the look-back descriptors.  Replaces the per-call numpy.zeros((22, N)) pair of ITD.py:384-387.
+ */
+PYITD_API int  pyitd_plan_create(pyitd_plan **plan, int device, int64_t n_signals, int64_t n_samples,
+                       int dtype, int max_iteration, int min_extrema, int options);
+PYITD_API void pyitd_plan_destroy(pyitd_plan *plan);
+PYITD_API int     pyitd_plan_rows(const pyitd_plan *plan);             /* max_iteration + 2 */
+PYITD_API int64_t pyitd_plan_workspace_bytes(const pyitd_plan *plan);
+PYITD_API int     pyitd_plan_launches(const pyitd_plan *plan);         /* kernel launches of the last call */
+
+/*
+ * Replaces ITD.itd(data, max_iteration) (ITD.py:351-433) for a batch of independent signals.
+ *   x           [n_signals, n_samples]            dtype per plan (device memory)
+ *   rotations   [n_signals, rows, n_samples]      rows [0, n_rows[s]) = proper rotations, last = trend
+ *   baselines   [n_signals, rows, n_samples]      NULL unless PYITD_OPT_BASELINES; valid rows:
+ *                                                 n_rows-1 on the knot stop (ITD.py:414), n_rows on the
+ *                                                 iteration stop with a zero last row (ITD.py:424)
+ *   n_rows      [n_signals] int32
+ *   knot_counts [n_signals, rows] int32           extrema of each new baseline = what ITD.py:403 prints
+ *   input_knots [n_signals] int32 (may be NULL)   interior knots of the input itself
+ *   stop_kind   [n_signals] int32 (may be NULL)
+ *   status      [n_signals] int32
+ * No host synchronisation happens inside; the stop test runs on the device.
+ */
+PYITD_API int pyitd_decompose_device(pyitd_plan *plan, const void *x, void *rotations, void *baselines,
+                           int32_t *n_rows, int32_t *knot_counts, int32_t *input_knots,
+                           int32_t *stop_kind, int32_t *status, void *stream);
+
+/* Same call with HOST buffers: copies x in, runs, copies every output back, synchronises.  This is
+ * the entry a non-CUDA host (the reference's numpy caller) binds. */
+PYITD_API int pyitd_decompose_host(pyitd_plan *plan, const void *x, void *rotations, void *baselines,
+                         int32_t *n_rows, int32_t *knot_counts, int32_t *input_knots,
+                         int32_t *stop_kind, int32_t *status);
+
+/*
+ * Replaces itd_baseline_extract(data) -> (rotation, baseline) (ITD.py:79-121): one sifting level.
+ *   rotation, baseline [n_signals, n_samples]; knot_count [n_signals] = interior knots of x.
+ */
+PYITD_API int pyitd_extract_level_device(pyitd_plan *plan, const void *x, void *rotation, void *baseline,
+                               int32_t *knot_count, int32_t *status, void *stream);
+
+/*
+ * Replaces detect_peaks (ITD.py:33-76) and the knot merge around it (ITD.py:87-88, :97).
+ *   kinds      PYITD_KNOTS_VALLEYS = detect_peaks(x), PYITD_KNOTS_PEAKS = detect_peaks(-x),
+ *              PYITD_KNOTS_BOTH = sort(unique(hstack(both))) = the knot set of one level
+ *   knots      [n_signals, knot_capacity] int32, ascending, first knot_count[s] entries valid
+ *   knot_count [n_signals] int32 (the true count even when it exceeds knot_capacity)
+ */
+#define PYITD_KNOTS_VALLEYS 1
+#define PYITD_KNOTS_PEAKS   2
+#define PYITD_KNOTS_BOTH    3
+PYITD_API int pyitd_find_knots_device(pyitd_plan *plan, const void *x, int kinds, int32_t *knots,
+                            int64_t knot_capacity, int32_t *knot_count, int32_t *status, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYITD_B200_H */

@@ -1,0 +1,13 @@
+"""pyitd_b200 -- B200-native Intrinsic Time-scale Decomposition behind PyITD's ``ITD`` interface.
+
+``from pyitd_b200 import ITD`` is the drop-in for ``from ITD import ITD`` of the reference
+(/root/reference/ITD.py); ``decompose`` is the batched entry point.  All compute goes through the
+C ABI of ``libpyitd_b200.so`` (hand-written sm_100a kernels); there is no CPU fallback.
+"""
+from ._capi import PyITDLibraryError, Plan  # noqa: F401
+from .itd import (ITD, ITDResult, clear_plan_cache, decompose, detect_peaks, extract_level,  # noqa: F401
+                  find_knots, itd_baseline_extract)
+
+__all__ = ["ITD", "ITDResult", "decompose", "detect_peaks", "itd_baseline_extract", "extract_level",
+           "find_knots", "Plan", "PyITDLibraryError", "clear_plan_cache"]
+__version__ = "0.1.0"
