@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ITD sifting loop (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one full decomposition (all levels) of one batch of synthetic channels:
+BASELINE.json configs[1] -- 4 096 x 65 536-sample fp64 EEG-like channels, knot-count stopping -- per
+GPU.  Channels are independent, so N GPUs run N shards with no collective (weak scaling);
+`value` = channels x samples over all ranks / max-over-ranks device time.
+
+Keys beyond the base contract:
+  roofline      achieved HBM GB/s of the level kernel by ALGORITHMIC bytes (3 x 8 B per sample per
+                executed level) / its CUDA-event time, against the measured
+                copy peak in MEASURED_PEAKS.json;
+  e2e           the same metric through the C ABI with HOST buffers (pyitd_decompose_host: H2D of the
+                inputs and D2H of every output row inside the timed region);
+  cpu_baseline  the oracle's C port on this box's host cores over a bounded sample of the same
+                workload (a reported baseline, not the target).
+`--impl reference` times that CPU port alone (the reference is Python+numba and cannot travel to the
+GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_SAMPLES = 65536
+CHANNELS_PER_GPU = 4096
+MAX_ITERATION = 11
+SEED = 1234
+METRIC = "input samples/s fully decomposed (all levels)"
+UNIT = "samples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--channels", type=int, default=CHANNELS_PER_GPU, help="channels per GPU")
+    ap.add_argument("--samples", type=int, default=N_SAMPLES)
+    ap.add_argument("--e2e-channels", type=int, default=1024, help="channels per e2e step (host buffers)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": "configs[1]: batched 4096 x 65536-sample synthetic EEG-like channels, fp64, "
+                    "knot-count stopping (max_iteration=11), per GPU",
+        "channels_per_gpu": args.channels, "n_samples": args.samples, "max_iteration": MAX_ITERATION,
+        "generator": "pyitd_b200.synth.eeg_like(seed=1234+rank)", "parallelism": f"channel-shard x{n_gpus}, no collective",
+        "l2": "inputs (2 GiB) and outputs (26 GiB) per step are larger than the 126 MB L2; no explicit flush",
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU port timing (cpu_baseline leg and --impl reference)
+# ---------------------------------------------------------------------------------------------
+def cpu_port_throughput(n_samples: int, budget_s: float = 12.0, max_channels: int = 4096):
+    """Times oracle/itd_oracle.c (pthreads, one channel per thread) on a bounded sample of the
+    workload.  Returns (samples_per_s, threads, n_channels, seconds)."""
+    import torch
+
+    from oracle import itd_oracle
+    from pyitd_b200 import synth
+
+    threads = itd_oracle.c_max_threads()
+    itd_oracle.c_decompose_batch(synth.eeg_like(threads, n_samples, seed=SEED).numpy(), MAX_ITERATION)  # warm
+    chunk = max(threads * 4, 32)
+    done, spent = 0, 0.0
+    while spent < budget_s and done < max_channels:
+        x = synth.eeg_like(chunk, n_samples, seed=SEED + 1 + done, first_channel=done,
+                           total_channels=CHANNELS_PER_GPU).numpy()
+        t0 = time.perf_counter()
+        _, _, _, status, _ = itd_oracle.c_decompose_batch(x, MAX_ITERATION)
+        spent += time.perf_counter() - t0
+        done += chunk
+        assert int(status.max()) == 0
+    del torch
+    return done * n_samples / spent, threads, done, spent
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # one "step" = one bounded sample; K steps + W warm-ups stay within a few minutes
+    per_step_budget = max(1.0, min(10.0, 120.0 / max(args.steps + args.warmup, 1)))
+    vals = []
+    threads = n_ch = 0
+    for i in range(args.warmup + args.steps):
+        v, threads, n_ch, secs = cpu_port_throughput(args.samples, budget_s=per_step_budget, max_channels=1024)
+        if i >= args.warmup:
+            vals.append((v, secs, n_ch))
+    tot_samples = sum(n * args.samples for _, _, n in vals)
+    tot_secs = sum(s for _, s, _ in vals)
+    value = tot_samples / tot_secs
+    sample = f"{vals[0][2]} channels x {args.samples} samples per step (same generator as the GPU arm), {threads} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_secs / max(len(vals), 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "oracle/itd_oracle.c (bit-exact C port of ITD.py, pthreads over channels): the reference is "
+                "Python+numba and is not shipped to the GPU box",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.path = tempfile.mktemp(prefix="pyitd_clocks_", suffix=".csv")
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        # "under load" = the upper half of the samples (the sampler also sees the idle edges)
+        load = sm[len(sm) // 2:]
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import pyitd_b200
+    from pyitd_b200 import _capi, synth
+    from pyitd_b200.itd import get_plan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU port")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    S, N = args.channels, args.samples
+    x = synth.eeg_like(S, N, seed=SEED + rank, device=dev)
+    plan = get_plan(local_rank, S, N, _capi.F64, MAX_ITERATION, 2, 0)
+    rows = plan.rows
+    rot = torch.empty((S, rows, N), dtype=torch.float64, device=dev)
+    n_rows = torch.empty(S, dtype=torch.int32, device=dev)
+    counts = torch.empty((S, rows), dtype=torch.int32, device=dev)
+    iknots = torch.empty(S, dtype=torch.int32, device=dev)
+    kind = torch.empty(S, dtype=torch.int32, device=dev)
+    status = torch.empty(S, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        plan.decompose_device(x.data_ptr(), rot.data_ptr(), None, n_rows.data_ptr(), counts.data_ptr(),
+                              iknots.data_ptr(), kind.data_ptr(), status.data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    assert int(status.abs().max()) == 0, "synthetic workload hit an error status"
+    launches_per_step = plan.launches
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream ----------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * S * N / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (level_kernel), per-launch CUDA events ------------------
+    plan.enable_timing(True)
+    lvl_ms = None
+    reps = 3
+    for _ in range(reps):
+        step()
+        tms = plan.launch_times_ms()
+        lvl_ms = tms if lvl_ms is None else [a + b for a, b in zip(lvl_ms, tms)]
+    plan.enable_timing(False)
+    lvl_ms = [v / reps for v in lvl_ms]
+    nr = n_rows.long()
+    active = [int((nr >= e + 1).sum()) for e in range(rows)]        # signals that execute extraction e
+    level_bytes = [a * N * 24 for a in active]                      # read X + write R + write B, fp64
+    # launch 0 is the knot scan, launches 1..rows are extractions 0..rows-1, the last is the fix-up
+    lv_times = lvl_ms[1:1 + rows]
+    n_lv = sum(1 for a in active if a > 0)
+    alg_bytes = sum(level_bytes)
+    lv_time_ms = sum(tm for tm, a in zip(lv_times, active) if a > 0)
+    achieved = alg_bytes / (lv_time_ms * 1e-3) / 1e9
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "level_kernel_traffic.json"))).get("traffic_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {
+        "bound": "hbm", "kernel": "pyitd::level_kernel<double,double,double>",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
+        "algorithmic_bytes_per_launch": alg_bytes / max(n_lv, 1),
+        "avg_launch_ms": lv_time_ms / max(n_lv, 1), "level_launches": n_lv,
+        "per_level": [{"e": e, "active_signals": a, "ms": round(tm, 4),
+                       "GBps": (round(b / (tm * 1e-3) / 1e9, 1) if a > 0 and tm > 0 else None)}
+                      for e, (a, tm, b) in enumerate(zip(active, lv_times, level_bytes))],
+        "knot_scan_ms": lvl_ms[0], "sample_levels_per_s": world * int(nr.sum()) * N / (ms_per_step * 1e-3),
+    }
+
+    # ---- e2e: host buffers through the C ABI (pyitd_decompose_host) -------------------------------
+    e2e = None
+    if not args.no_e2e:
+        Se = min(args.e2e_channels, S)
+        hplan = get_plan(local_rank, Se, N, _capi.F64, MAX_ITERATION, 2, 0) if Se != S else plan
+        hx = x[:Se].cpu().pin_memory()
+        hrot = torch.empty((Se, rows, N), dtype=torch.float64).pin_memory()
+        hn = torch.empty(Se, dtype=torch.int32).pin_memory()
+        hc = torch.empty((Se, rows), dtype=torch.int32).pin_memory()
+        hs = torch.empty(Se, dtype=torch.int32).pin_memory()
+
+        def host_step():
+            hplan.decompose_host(hx.data_ptr(), hrot.data_ptr(), None, hn.data_ptr(), hc.data_ptr(), None, None,
+                                 hs.data_ptr())
+
+        for _ in range(2):
+            host_step()
+        barrier()
+        k_e2e = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            host_step()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        h2d = hx.numel() * 8
+        d2h = hrot.numel() * 8 + (hn.numel() + hc.numel() + hs.numel()) * 4
+        e2e = {"value": world * Se * N * k_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "channels_per_step": Se, "steps": k_e2e,
+               "api": "pyitd_decompose_host (C ABI, pinned host buffers, all rotation rows copied back)"}
+
+    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, threads, n_ch, secs = cpu_port_throughput(N)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{n_ch} channels x {N} samples of the same generator in {secs:.1f} s "
+                         f"(oracle/itd_oracle.c, one channel per pthread)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clocks, "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "rows_per_channel_mean": float(nr.double().mean()),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

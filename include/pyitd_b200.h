@@ -78,6 +78,12 @@ PYITD_API int     pyitd_plan_rows(const pyitd_plan *plan);             /* max_it
 PYITD_API int64_t pyitd_plan_workspace_bytes(const pyitd_plan *plan);
 PYITD_API int     pyitd_plan_launches(const pyitd_plan *plan);         /* kernel launches of the last call */
 
+/* Measurement aid: with timing enabled every kernel launch of pyitd_decompose_device is bracketed by
+ * CUDA events on the launching stream; pyitd_plan_launch_times waits for the last one and returns the
+ * number of launches, writing their durations in ms (launch 0 = knot scan, 1.. = one per level). */
+PYITD_API int     pyitd_plan_enable_timing(pyitd_plan *plan, int enable);
+PYITD_API int     pyitd_plan_launch_times(pyitd_plan *plan, float *ms, int capacity);
+
 /*
  * Replaces ITD.itd(data, max_iteration) (ITD.py:351-433) for a batch of independent signals.
  *   x           [n_signals, n_samples]            dtype per plan (device memory)

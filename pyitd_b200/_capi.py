@@ -70,6 +70,10 @@ def lib() -> ctypes.CDLL:
     L.pyitd_plan_workspace_bytes.argtypes = [vp]
     L.pyitd_plan_launches.restype = ci
     L.pyitd_plan_launches.argtypes = [vp]
+    L.pyitd_plan_enable_timing.restype = ci
+    L.pyitd_plan_enable_timing.argtypes = [vp, ci]
+    L.pyitd_plan_launch_times.restype = ci
+    L.pyitd_plan_launch_times.argtypes = [vp, vp, ci]
     L.pyitd_decompose_device.restype = ci
     L.pyitd_decompose_device.argtypes = [vp] * 10
     L.pyitd_decompose_host.restype = ci
@@ -119,6 +123,16 @@ class Plan:
     @property
     def launches(self) -> int:
         return int(self._L.pyitd_plan_launches(self.handle))
+
+    def enable_timing(self, on: bool = True) -> None:
+        check(self._L.pyitd_plan_enable_timing(self.handle, int(on)), "pyitd_plan_enable_timing")
+
+    def launch_times_ms(self) -> list[float]:
+        buf = (ctypes.c_float * (self.rows + 8))()
+        n = self._L.pyitd_plan_launch_times(self.handle, buf, len(buf))
+        if n < 0:
+            check(n, "pyitd_plan_launch_times")
+        return [float(buf[i]) for i in range(n)]
 
     def close(self) -> None:
         if self._h:

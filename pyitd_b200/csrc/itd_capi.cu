@@ -49,6 +49,10 @@ struct pyitd_plan {
     int *stop_e = nullptr, *stop_kind = nullptr, *input_knots = nullptr;
     unsigned tag = 0;
     int launches = 0;
+    // optional per-launch CUDA-event timing (bench.py's roofline leg)
+    bool timing = false;
+    cudaEvent_t *events = nullptr;
+    int n_events = 0, events_used = 0;
     // lazily allocated device mirrors for the _host entry point
     void *h_x = nullptr, *h_rot = nullptr, *h_bas = nullptr;
     int *h_ints = nullptr;    // n_rows | knot_counts | input_knots | stop_kind | status
@@ -234,6 +238,10 @@ extern "C" void pyitd_plan_destroy(pyitd_plan *pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);
     if (pl->h_stream) cudaStreamDestroy(pl->h_stream);
+    if (pl->events) {
+        for (int i = 0; i < pl->n_events; ++i) cudaEventDestroy(pl->events[i]);
+        delete[] pl->events;
+    }
     cudaFree(pl->h_x);
     cudaFree(pl->h_rot);
     cudaFree(pl->h_bas);
@@ -256,6 +264,13 @@ static int next_tag(pyitd_plan *pl, cudaStream_t st, unsigned *tag) {
     return 0;
 }
 
+// event i is recorded before launch i, event i+1 after it, on the launching stream
+static int mark(pyitd_plan *pl, cudaStream_t st) {
+    if (!pl->timing) return 0;
+    if (pl->events_used < pl->n_events) CU(cudaEventRecord(pl->events[pl->events_used++], st));
+    return 0;
+}
+
 static int run_scan(pyitd_plan *pl, const void *x, int *status, int *input_knots, cudaStream_t st, int kinds = 3) {
     ScanParams sp;
     sp.x = x;
@@ -267,9 +282,10 @@ static int run_scan(pyitd_plan *pl, const void *x, int *status, int *input_knots
     sp.n = pl->n;
     sp.tiles = pl->tiles;
     sp.kinds = kinds;
+    if (int rc = mark(pl, st)) return rc;
     CU(launch_scan(pl, sp, st));
     pl->launches++;
-    return 0;
+    return mark(pl, st);
 }
 
 extern "C" int pyitd_decompose_device(pyitd_plan *pl, const void *x, void *rotations, void *baselines,
@@ -283,6 +299,7 @@ extern "C" int pyitd_decompose_device(pyitd_plan *pl, const void *x, void *rotat
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(pl->device));
     pl->launches = 0;
+    pl->events_used = 0;
     int *sk = stop_kind ? stop_kind : pl->stop_kind;
     const size_t b_sig = (size_t)pl->S * sizeof(int);
     CU(cudaMemsetAsync(pl->stop_e, 0x7f, b_sig, st));
@@ -321,8 +338,34 @@ extern "C" int pyitd_decompose_device(pyitd_plan *pl, const void *x, void *rotat
         lp.opts = pl->opts;
         CU(launch_level(pl, lp, e == 0, st));
         pl->launches++;
+        if (int rc = mark(pl, st)) return rc;
     }
     return 0;
+}
+
+extern "C" int pyitd_plan_enable_timing(pyitd_plan *pl, int enable) {
+    if (!pl) return fail(PYITD_E_INVALID, "null plan");
+    CU(cudaSetDevice(pl->device));
+    if (enable && !pl->events) {
+        pl->n_events = pl->emax + 5;
+        pl->events = new (std::nothrow) cudaEvent_t[pl->n_events];
+        if (!pl->events) return fail(PYITD_E_NOMEM, "host allocation failed");
+        for (int i = 0; i < pl->n_events; ++i) CU(cudaEventCreate(&pl->events[i]));
+    }
+    pl->timing = enable != 0;
+    pl->events_used = 0;
+    return 0;
+}
+
+extern "C" int pyitd_plan_launch_times(pyitd_plan *pl, float *ms, int capacity) {
+    if (!pl || !ms) return fail(PYITD_E_INVALID, "null argument");
+    if (!pl->timing || pl->events_used < 2) return 0;
+    CU(cudaSetDevice(pl->device));
+    CU(cudaEventSynchronize(pl->events[pl->events_used - 1]));
+    int n = pl->events_used - 1;
+    if (n > capacity) n = capacity;
+    for (int i = 0; i < n; ++i) CU(cudaEventElapsedTime(&ms[i], pl->events[i], pl->events[i + 1]));
+    return n;
 }
 
 extern "C" int pyitd_extract_level_device(pyitd_plan *pl, const void *x, void *rotation, void *baseline,
