@@ -12,6 +12,7 @@
 #include <string>
 
 #include "itd_kernels.cuh"
+#include "itd_stream.cuh"
 
 using namespace pyitd;
 
@@ -39,6 +40,7 @@ struct pyitd_plan {
     int emax = 12, rows = 13;
     int tile_cfg = 1;         // index into the (THREADS, ITEMS) table
     int tile = 1024, tiles = 0;
+    bool stream = false;      // one-CTA-per-signal TMA-pipelined level kernel (itd_stream.cuh)
     size_t carry_elem = 8, io_elem = 8;
     // workspace
     void *ws = nullptr;
@@ -111,6 +113,20 @@ static cudaError_t launch_level_cfg(int cfg, const LevelParams &p, long long cta
     }
 }
 
+// one CTA per signal, 8 consumer warps x 4 samples/lane = 1024-sample tiles, 3-stage TMA ring
+constexpr int kStreamWarps = 8, kStreamItems = 4, kStreamStages = 3;
+constexpr int kStreamTile = kStreamWarps * 32 * kStreamItems;
+
+template <typename InT, typename CarryT, typename OutT>
+static cudaError_t launch_stream_t(const LevelParams &p, long long ctas, cudaStream_t st) {
+    auto k = level_stream_kernel<InT, CarryT, OutT, kStreamWarps, kStreamItems, kStreamStages>;
+    constexpr size_t smem = sizeof(StreamSmem<InT, CarryT, kStreamWarps, kStreamItems, kStreamStages>);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<(unsigned)ctas, (kStreamWarps + 1) * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
 static cudaError_t launch_scan(const pyitd_plan *pl, const ScanParams &p, cudaStream_t st) {
     const long long ctas = pl->S * pl->tiles;
     switch (pl->dtype) {
@@ -121,6 +137,15 @@ static cudaError_t launch_scan(const pyitd_plan *pl, const ScanParams &p, cudaSt
 }
 // first = the launch reads the caller's input (io type) instead of a carry buffer
 static cudaError_t launch_level(const pyitd_plan *pl, const LevelParams &p, bool first, cudaStream_t st) {
+    if (pl->stream && (reinterpret_cast<uintptr_t>(p.in) & 15) == 0) {
+        switch (pl->dtype) {
+            case PYITD_F64: return launch_stream_t<double, double, double>(p, pl->S, st);
+            case PYITD_F32_MIXED:
+                return first ? launch_stream_t<float, double, float>(p, pl->S, st)
+                             : launch_stream_t<double, double, float>(p, pl->S, st);
+            default: return launch_stream_t<float, float, float>(p, pl->S, st);
+        }
+    }
     const long long ctas = pl->S * pl->tiles;
     switch (pl->dtype) {
         case PYITD_F64: return launch_level_cfg<double, double, double>(pl->tile_cfg, p, ctas, st);
@@ -186,6 +211,16 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
         int v = atoi(env);
         if (v >= 0 && v < kNumTileCfgs) cfg = v;
     }
+    // path choice: many signals -> one pipelined CTA per signal; few long signals -> multi-CTA
+    // look-back tiles.  The streaming kernel needs 16-byte aligned rows for its TMA bulk copies.
+    const long long stream_tiles = (n_samples + kStreamTile - 1) / kStreamTile;
+    bool stream = (n_samples % 4 == 0) && stream_tiles <= 2048 && n_signals >= 256;
+    if (const char *env = getenv("PYITD_FORCE_PATH")) {
+        if (!strcmp(env, "stream")) stream = (n_samples % 4 == 0) && stream_tiles <= 2048;
+        if (!strcmp(env, "lookback")) stream = false;
+    }
+    if (stream) cfg = 1;                       // both kernels must agree on the 1024-sample tile
+    pl->stream = stream;
     pl->tile_cfg = cfg;
     pl->tile = kTileCfgs[cfg].threads * kTileCfgs[cfg].items;
     pl->tiles = (int)((n_samples + pl->tile - 1) / pl->tile);
@@ -195,13 +230,18 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
     }
 
     const size_t SN = (size_t)pl->S * (size_t)pl->n;
+    const long long kstride = (((long long)pl->n + 3) & ~3ll) + 4;
+    const long long mstride = ((((long long)pl->n + 31) / 32) + 3) & ~3ll;
+    const size_t SK = (size_t)pl->S * (size_t)kstride;
     const size_t b_carry = align_up(SN * pl->carry_elem);
-    const size_t b_tau = align_up(SN * sizeof(int));
+    const size_t b_xk = align_up(SK * pl->carry_elem);
+    const size_t b_tau = align_up(SK * sizeof(int));
+    const size_t b_mask = align_up((size_t)pl->S * (size_t)mstride * sizeof(unsigned));
     const size_t b_tbase = align_up((size_t)pl->S * (pl->tiles + 1) * sizeof(int));
     const size_t b_sig = align_up((size_t)pl->S * sizeof(int));
     const size_t b_endl = align_up((size_t)pl->S * 2 * pl->carry_elem);
     const size_t b_desc = align_up((size_t)pl->S * pl->tiles * sizeof(unsigned long long));
-    size_t total = 2 * b_carry + 2 * (b_tau + b_carry + b_tbase + b_sig + b_endl) + b_desc + 3 * b_sig;
+    size_t total = 2 * b_carry + 2 * (b_tau + b_xk + b_tbase + b_sig + b_endl + b_mask) + b_desc + 3 * b_sig;
     pl->ws_bytes = total;
     cudaError_t ce = cudaMalloc(&pl->ws, total);
     if (ce != cudaSuccess) {
@@ -215,7 +255,10 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
     pl->carry[1] = take(b_carry);
     for (int i = 0; i < 2; ++i) {
         pl->table[i].tau = (int *)take(b_tau);
-        pl->table[i].xk = take(b_carry);
+        pl->table[i].xk = take(b_xk);
+        pl->table[i].mask = (unsigned *)take(b_mask);
+        pl->table[i].kstride = kstride;
+        pl->table[i].mstride = mstride;
         pl->table[i].tbase = (int *)take(b_tbase);
         pl->table[i].kcount = (int *)take(b_sig);
         pl->table[i].endl = take(b_endl);
@@ -424,9 +467,9 @@ extern "C" int pyitd_find_knots_device(pyitd_plan *pl, const void *x, int kinds,
     for (long long s0 = 0; s0 < pl->S; s0 += 65535) {
         const long long ns = (pl->S - s0 < 65535) ? pl->S - s0 : 65535;
         dim3 grid((unsigned)per, (unsigned)ns);
-        export_knots_kernel<<<grid, 256, 0, st>>>(pl->table[0].tau + s0 * pl->n, pl->table[0].kcount + s0,
-                                                  pl->n, knots + s0 * knot_capacity, knot_capacity,
-                                                  knot_count + s0);
+        export_knots_kernel<<<grid, 256, 0, st>>>(pl->table[0].tau + s0 * pl->table[0].kstride,
+                                                  pl->table[0].kcount + s0, pl->table[0].kstride,
+                                                  knots + s0 * knot_capacity, knot_capacity, knot_count + s0);
         CU(cudaGetLastError());
         pl->launches++;
     }

@@ -177,11 +177,14 @@ __device__ __forceinline__ int tile_scan(const unsigned (&bal)[ITEMS], int *s_wc
 // parameter blocks (plain pointers; element types are fixed by the template arguments)
 // ---------------------------------------------------------------------------------------------
 struct KnotTable {
-    int *tau;        // [S, N]   tau_0 = 0, interior knots, tau_{K+1} = N-1
-    void *xk;        // [S, N]   X_k = x[tau_k]           (carry type)
+    int *tau;        // [S, kstride]  tau_0 = 0, interior knots, tau_{K+1} = N-1
+    void *xk;        // [S, kstride]  X_k = x[tau_k]           (carry type)
     int *tbase;      // [S, tiles+1] interior knots before each tile; [tiles] = K
     int *kcount;     // [S]      K
     void *endl;      // [S, 2]   L_0 and L_{K+1} (ITD.py:101-102) (carry type)
+    unsigned *mask;  // [S, mstride] knot flags, bit (t & 31) of word (t >> 5)
+    long long kstride;   // entries per signal in tau/xk: N rounded up to 4, + 4 (16-byte aligned rows)
+    long long mstride;   // words per signal in mask: ceil(N/32) rounded up to 4
 };
 
 struct ScanParams {
@@ -261,10 +264,12 @@ __global__ void __launch_bounds__(THREADS) knot_scan_kernel(const ScanParams p) 
     const int base = tile_scan<THREADS, ITEMS>(bal, s_wcnt, s_wpre, s_misc,
                                                p.desc + (long long)sig * p.tiles, tile, p.tag, total);
 
-    int *tau = p.out.tau + (long long)sig * n;
-    CarryT *xk = reinterpret_cast<CarryT *>(p.out.xk) + (long long)sig * n;
+    int *tau = p.out.tau + (long long)sig * p.out.kstride;
+    CarryT *xk = reinterpret_cast<CarryT *>(p.out.xk) + (long long)sig * p.out.kstride;
+    unsigned *gmask = p.out.mask + (long long)sig * p.out.mstride + tile * (T / 32);
 #pragma unroll
     for (int r = 0; r < ITEMS; ++r) {
+        if (lane == 0 && t0 + r * THREADS + warp * 32 < n) gmask[r * (THREADS / 32) + warp] = bal[r];
         if ((bal[r] >> lane) & 1u) {
             const int rank = base + s_wpre[r * (THREADS / 32) + warp] + __popc(bal[r] & ((1u << lane) - 1u));
             tau[1 + rank] = t0 + r * THREADS + tid;
@@ -373,8 +378,8 @@ __global__ void __launch_bounds__(THREADS) level_kernel(const LevelParams p) {
     const int hi = min(kb + cnt + 3, K + 1);
     const int m = hi - lo + 1;                  // <= cnt + 5 <= KC
     {
-        const int *gtau = p.cur.tau + (long long)sig * n + lo;
-        const CarryT *gxk = reinterpret_cast<const CarryT *>(p.cur.xk) + (long long)sig * n + lo;
+        const int *gtau = p.cur.tau + (long long)sig * p.cur.kstride + lo;
+        const CarryT *gxk = reinterpret_cast<const CarryT *>(p.cur.xk) + (long long)sig * p.cur.kstride + lo;
         for (int j = tid; j < m; j += THREADS) {
             ktau[j] = gtau[j];
             kX[j] = gxk[j];
@@ -505,10 +510,12 @@ __global__ void __launch_bounds__(THREADS) level_kernel(const LevelParams p) {
     int total;
     const int base = tile_scan<THREADS, ITEMS>(bal, s_wcnt, s_wpre, s_misc,
                                                p.desc + (long long)sig * p.tiles, tile, p.tag, total);
-    int *tau = p.next.tau + (long long)sig * n;
-    CarryT *xk = reinterpret_cast<CarryT *>(p.next.xk) + (long long)sig * n;
+    int *tau = p.next.tau + (long long)sig * p.next.kstride;
+    CarryT *xk = reinterpret_cast<CarryT *>(p.next.xk) + (long long)sig * p.next.kstride;
+    unsigned *gmask = p.next.mask + (long long)sig * p.next.mstride + tile * (T / 32);
 #pragma unroll
     for (int r = 0; r < ITEMS; ++r) {
+        if (lane == 0 && t0 + r * THREADS + warp * 32 < n) gmask[r * WARPS + warp] = bal[r];
         if ((bal[r] >> lane) & 1u) {
             const int rank = base + s_wpre[r * WARPS + warp] + __popc(bal[r] & ((1u << lane) - 1u));
             tau[1 + rank] = t0 + r * THREADS + tid;
@@ -547,13 +554,13 @@ __global__ void __launch_bounds__(THREADS) level_kernel(const LevelParams p) {
 }
 
 // copies the interior knots of the current table into a user buffer (find_knots entry point)
-__global__ void export_knots_kernel(const int *tau, const int *kcount, int n, int *out,
+__global__ void export_knots_kernel(const int *tau, const int *kcount, long long kstride, int *out,
                                     long long capacity, int *count_out) {
     const int sig = blockIdx.y;
     const int K = kcount[sig];
     if (blockIdx.x == 0 && threadIdx.x == 0) count_out[sig] = K;
     const long long lim = (K < capacity) ? K : capacity;
-    const int *src = tau + (long long)sig * n + 1;
+    const int *src = tau + (long long)sig * kstride + 1;
     int *dst = out + (long long)sig * capacity;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < lim;
          i += (long long)gridDim.x * blockDim.x)

@@ -167,6 +167,33 @@ def test_tile_boundaries_all_configs(cfg, monkeypatch):
         pyitd_b200.clear_plan_cache()
 
 
+@pytest.mark.parametrize("path", ["stream", "lookback"])
+def test_both_level_kernels_agree_with_oracle(path, monkeypatch):
+    """The one-CTA-per-signal TMA-pipelined kernel and the multi-CTA look-back kernel are forced in
+    turn over sizes around the 1024-sample tile and the 128-sample warp span."""
+    monkeypatch.setenv("PYITD_FORCE_PATH", path)
+    pyitd_b200.clear_plan_cache()
+    rng = np.random.default_rng(300)
+    try:
+        for n in (4, 8, 32, 36, 124, 128, 132, 1020, 1024, 1028, 2044, 2048, 2052, 3076, 5120, 8192, 10004):
+            check_against_oracle(_mixed_batch(rng, 9, n), max_iteration=11)
+        for mi in (0, 1, 4):
+            check_against_oracle(_mixed_batch(rng, 9, 6000), max_iteration=mi)
+        x32 = _mixed_batch(rng, 6, 4096).astype(np.float32)
+        for dt in ("f32_mixed", "f32"):
+            res = pyitd_b200.decompose(gpu(x32), max_iteration=7, dtype=dt)
+            for s in range(6):
+                src = x32[s].astype(np.float64) if dt == "f32_mixed" else x32[s]
+                try:
+                    want = o.c_decompose(src, 7)
+                except o.OracleError:
+                    assert int(res.status[s]) != 0
+                    continue
+                assert res.rows_of(s).cpu().numpy().tobytes() == want.rotations.astype(np.float32).tobytes(), (dt, s)
+    finally:
+        pyitd_b200.clear_plan_cache()
+
+
 @pytest.mark.parametrize("max_iteration", [0, 1, 3, 7, 20])
 def test_iteration_cap(max_iteration):
     rng = np.random.default_rng(11)
