@@ -117,10 +117,27 @@ static cudaError_t launch_level_cfg(int cfg, const LevelParams &p, long long cta
 constexpr int kStreamWarps = 8, kStreamItems = 4, kStreamStages = 3;
 constexpr int kStreamTile = kStreamWarps * 32 * kStreamItems;
 
+template <typename InT, typename CarryT, typename OutT, bool LAST, bool BAS>
+static cudaError_t launch_stream_v(const LevelParams &p, long long ctas, cudaStream_t st) {
+    auto k = level_stream_kernel<InT, CarryT, OutT, kStreamWarps, kStreamItems, kStreamStages, LAST, BAS>;
+    constexpr size_t smem = sizeof(StreamSmem<InT, CarryT, kStreamWarps, kStreamItems, kStreamStages, true>);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<(unsigned)ctas, (kStreamWarps + 1) * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
 template <typename InT, typename CarryT, typename OutT>
 static cudaError_t launch_stream_t(const LevelParams &p, long long ctas, cudaStream_t st) {
-    auto k = level_stream_kernel<InT, CarryT, OutT, kStreamWarps, kStreamItems, kStreamStages>;
-    constexpr size_t smem = sizeof(StreamSmem<InT, CarryT, kStreamWarps, kStreamItems, kStreamStages>);
+    const bool last = (p.e == p.emax), bas = (p.bas != nullptr);
+    if (last) return bas ? launch_stream_v<InT, CarryT, OutT, true, true>(p, ctas, st)
+                         : launch_stream_v<InT, CarryT, OutT, true, false>(p, ctas, st);
+    return bas ? launch_stream_v<InT, CarryT, OutT, false, true>(p, ctas, st)
+               : launch_stream_v<InT, CarryT, OutT, false, false>(p, ctas, st);
+}
+template <typename InT, typename CarryT>
+static cudaError_t launch_scan_stream_t(const ScanParams &p, long long ctas, cudaStream_t st) {
+    auto k = scan_stream_kernel<InT, CarryT, kStreamWarps, kStreamItems, kStreamStages>;
+    constexpr size_t smem = sizeof(StreamSmem<InT, CarryT, kStreamWarps, kStreamItems, kStreamStages, false>);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<(unsigned)ctas, (kStreamWarps + 1) * 32, smem, st>>>(p);
@@ -128,6 +145,13 @@ static cudaError_t launch_stream_t(const LevelParams &p, long long ctas, cudaStr
 }
 
 static cudaError_t launch_scan(const pyitd_plan *pl, const ScanParams &p, cudaStream_t st) {
+    if (pl->stream && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0) {
+        switch (pl->dtype) {
+            case PYITD_F64: return launch_scan_stream_t<double, double>(p, pl->S, st);
+            case PYITD_F32_MIXED: return launch_scan_stream_t<float, double>(p, pl->S, st);
+            default: return launch_scan_stream_t<float, float>(p, pl->S, st);
+        }
+    }
     const long long ctas = pl->S * pl->tiles;
     switch (pl->dtype) {
         case PYITD_F64: return launch_scan_cfg<double, double>(pl->tile_cfg, p, ctas, st);
@@ -214,9 +238,9 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
     // path choice: many signals -> one pipelined CTA per signal; few long signals -> multi-CTA
     // look-back tiles.  The streaming kernel needs 16-byte aligned rows for its TMA bulk copies.
     const long long stream_tiles = (n_samples + kStreamTile - 1) / kStreamTile;
-    bool stream = (n_samples % 4 == 0) && stream_tiles <= 2048 && n_signals >= 256;
+    bool stream = (n_samples % 4 == 0) && stream_tiles <= kStreamMaxTiles && n_signals >= 256;
     if (const char *env = getenv("PYITD_FORCE_PATH")) {
-        if (!strcmp(env, "stream")) stream = (n_samples % 4 == 0) && stream_tiles <= 2048;
+        if (!strcmp(env, "stream")) stream = (n_samples % 4 == 0) && stream_tiles <= kStreamMaxTiles;
         if (!strcmp(env, "lookback")) stream = false;
     }
     if (stream) cfg = 1;                       // both kernels must agree on the 1024-sample tile

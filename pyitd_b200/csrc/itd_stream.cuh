@@ -1,6 +1,6 @@
-// itd_stream.cuh -- the batched-channel level kernel: ONE CTA PER SIGNAL, tiles walked in order.
+// itd_stream.cuh -- the batched-channel kernels: ONE CTA PER SIGNAL, tiles walked in order.
 //
-// Same arithmetic and the same HBM data structures as level_kernel (itd_kernels.cuh); the
+// Same arithmetic and the same HBM data structures as the look-back kernels (itd_kernels.cuh); the
 // difference is how a signal is moved through the SM:
 //
 //   * a producer warp streams each tile's samples, knot-flag words and knot-table slice into a
@@ -15,54 +15,59 @@
 //     register: no look-back chain, and exactly ONE block barrier per tile (the exchange of the
 //     per-warp new-knot counts).
 //
+// scan_stream_kernel is the same pipeline for the very first pass (extrema of the raw input).
+//
 // Used when the batch has enough signals to fill the GPU with one CTA each; few long signals use
-// the multi-CTA look-back kernel instead.
+// the multi-CTA look-back kernels instead.
 #pragma once
+
+#include <type_traits>
 
 #include "itd_kernels.cuh"
 
 namespace pyitd {
 
 // ---------------------------------------------------------------------------------------------
-// mbarrier / TMA-bulk PTX wrappers
+// mbarrier / TMA-bulk PTX wrappers (all take 32-bit shared-window addresses)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) {
     return (unsigned)__cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
     unsigned ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(bar), "r"(parity)
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// the producer is normally far ahead of the math: poll politely so it does not eat issue slots
+__device__ __forceinline__ void mbar_wait_backoff(unsigned bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(200);
+}
 // global -> shared bulk copy; dst, src 16-byte aligned, bytes a multiple of 16
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes,
-                                            unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void tma_load_1d(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
 __device__ __forceinline__ void named_barrier_sync(int id, int threads) {
@@ -77,13 +82,13 @@ __device__ __forceinline__ T shfl_idx(T v, int src) {
 // ---------------------------------------------------------------------------------------------
 // shared-memory layout
 // ---------------------------------------------------------------------------------------------
-template <typename InT, typename CarryT, int WARPS, int ITEMS, int STAGES>
+template <typename InT, typename CarryT, int WARPS, int ITEMS, int STAGES, bool WITH_KNOTS>
 struct StreamSmem {
     static constexpr int T = WARPS * 32 * ITEMS;
-    static constexpr int KC = T + 16;           // knot slice capacity (T + 5, start aligned down to 4)
+    static constexpr int KC = WITH_KNOTS ? T + 16 : 4;   // knot slice capacity (T + 5, start aligned down to 4)
     static constexpr int SPAN = 32 * ITEMS;
-    static constexpr int SC = SPAN + 8;         // per-warp knot scratch
-    static constexpr int MAX_TILES = 2048;
+    static constexpr int SC = WITH_KNOTS ? SPAN + 8 : 1; // per-warp knot scratch
+    static constexpr int MAX_TILES = 1024;
     struct Stage {
         alignas(16) InT x[T];
         alignas(16) unsigned mask[(T / 32 + 3) & ~3];
@@ -95,25 +100,109 @@ struct StreamSmem {
     alignas(8) unsigned long long empty[STAGES];
     CarryT kL[WARPS][SC];
     CarryT kS[WARPS][SC];
-    int tbase[MAX_TILES + 1];
+    int tbase[WITH_KNOTS ? MAX_TILES + 1 : 1];
     int cnt[2][WARPS];
-    CarryT carry_b[2];                           // B of the previous tile's last sample (by tile parity)
+    CarryT carry_b[2];                           // value of the previous tile's last sample (by tile parity)
     CarryT endl[2];
 };
+constexpr int kStreamMaxTiles = 1024;
 
 // ---------------------------------------------------------------------------------------------
-// the kernel
+// extrema of a span held in registers (striped: v[r] is sample span0 + r*32 + lane).
+// fw[r] = flag word of samples [span0 + 32 r, +32); returns their total.  vleft / vright are the
+// samples just outside the span.  EDGE applies the 1 <= t <= n-2 rule (ITD.py:70-73).
 // ---------------------------------------------------------------------------------------------
-template <typename InT, typename CarryT, typename OutT, int WARPS, int ITEMS, int STAGES>
+template <bool EDGE, int ITEMS, typename CarryT>
+__device__ __forceinline__ int span_extrema(const CarryT (&v)[ITEMS], CarryT vleft, CarryT vright, int lane,
+                                            int tspan, int n, unsigned (&fw)[ITEMS]) {
+    const CarryT v0 = shfl_idx(v[0], 0);
+    unsigned lt_in = (vleft < v0) ? 1u : 0u;
+    unsigned gt_in = (vleft > v0) ? 1u : 0u;
+    int total = 0;
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+        CarryT nx = __shfl_down_sync(0xffffffffu, v[r], 1);
+        const CarryT wrap = (r + 1 < ITEMS) ? shfl_idx(v[(r + 1 < ITEMS) ? r + 1 : r], 0) : vright;
+        if (lane == 31) nx = wrap;
+        const unsigned LT = __ballot_sync(0xffffffffu, v[r] < nx);
+        const unsigned GT = __ballot_sync(0xffffffffu, v[r] > nx);
+        // valley: !(v[i-1] < v[i]) && v[i] < v[i+1];  peak: !(v[i-1] > v[i]) && v[i] > v[i+1]
+        unsigned f = (~((LT << 1) | lt_in) & LT) | (~((GT << 1) | gt_in) & GT);
+        lt_in = LT >> 31;
+        gt_in = GT >> 31;
+        if (EDGE) {
+            const int tw = tspan + r * 32;                            // global index of bit 0
+            if (tw == 0) f &= ~1u;
+            const int lastbit = n - 2 - tw;                           // highest valid bit
+            f = (lastbit < 0) ? 0u : ((lastbit >= 31) ? f : (f & (0xffffffffu >> (31 - lastbit))));
+        }
+        fw[r] = f;
+        total += __popc(f);
+    }
+    return total;
+}
+
+// the one block barrier per tile: exchange per-warp counts, then write the compacted knots
+template <int WARPS, int ITEMS, typename CarryT>
+__device__ __forceinline__ void compact_knots(int (&cnt)[2][WARPS], int i, int warp, int lane, int newc,
+                                              const unsigned (&fw)[ITEMS], const CarryT (&v)[ITEMS],
+                                              int tspan, int &run_total, int *ntau, CarryT *nxk, int *ntbase) {
+    if (lane == 0) cnt[i & 1][warp] = newc;
+    named_barrier_sync(1, WARPS * 32);
+    int pre = run_total, tot = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < WARPS; ++w2) {
+        const int c = cnt[i & 1][w2];
+        pre += (w2 < warp) ? c : 0;
+        tot += c;
+    }
+    if (warp == 0 && lane == 0) ntbase[i] = run_total;
+    run_total += tot;
+    const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+        if ((fw[r] >> lane) & 1u) {
+            const int rank = pre + __popc(fw[r] & lt_mask);
+            ntau[1 + rank] = tspan + r * 32 + lane;
+            nxk[1 + rank] = v[r];
+        }
+        pre += __popc(fw[r]);
+    }
+}
+
+// vectorised row copy / fill used by the trend-row fix-up
+template <typename OutT, typename CarryT>
+__device__ __forceinline__ void copy_row(OutT *dst, const CarryT *src, int n, bool zero) {
+    for (int t = threadIdx.x; t < n; t += blockDim.x * 4) {
+        CarryT a[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int tt = t + u * blockDim.x;
+            a[u] = (!zero && tt < n) ? src[tt] : (CarryT)0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int tt = t + u * blockDim.x;
+            if (tt < n) dst[tt] = (OutT)a[u];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// level_stream_kernel
+// ---------------------------------------------------------------------------------------------
+template <typename InT, typename CarryT, typename OutT, int WARPS, int ITEMS, int STAGES, bool LAST, bool BAS>
 __global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const LevelParams p) {
     using A = Arith<CarryT>;
-    using Smem = StreamSmem<InT, CarryT, WARPS, ITEMS, STAGES>;
+    using Smem = StreamSmem<InT, CarryT, WARPS, ITEMS, STAGES, true>;
     constexpr int T = Smem::T;
     constexpr int SPAN = Smem::SPAN;
-    constexpr int NWORDS = T / 32;
-    static_assert(NWORDS <= 32, "one flag word per lane");
+    static_assert(T / 32 <= 32, "one flag word per lane");
     extern __shared__ __align__(128) unsigned char smem_stream_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_stream_raw);
+    const unsigned sbase = smem_u32(smem_stream_raw);
+    const unsigned full0 = sbase + (unsigned)offsetof(Smem, full);
+    const unsigned empty0 = sbase + (unsigned)offsetof(Smem, empty);
 
     const int sig = blockIdx.x;
     const int n = p.n, e = p.e, tiles = p.tiles;
@@ -124,19 +213,17 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const Le
     const int se = p.stop_e[sig];
     if (e > se) {
         OutT *rot = reinterpret_cast<OutT *>(p.rot) + row_off;
-        OutT *bas = p.bas ? reinterpret_cast<OutT *>(p.bas) + row_off : nullptr;
+        OutT *bas = BAS ? reinterpret_cast<OutT *>(p.bas) + row_off : nullptr;
+        const CarryT *src = reinterpret_cast<const CarryT *>(p.fix_src) + (long long)sig * n;
         if (e == se + 1 && p.stop_kind[sig] == kStopKnots) {
-            const CarryT *src = reinterpret_cast<const CarryT *>(p.fix_src) + (long long)sig * n;
-            for (int t = tid; t < n; t += blockDim.x) {
-                rot[(long long)se * n + t] = (se == 0) ? (OutT)0 : (OutT)src[t];
-                if (bas && (p.opts & kOptZeroTail)) bas[(long long)se * n + t] = (OutT)0;
-            }
+            // the discarded extraction `se` wrote R_se into row se; the reference returns
+            // baselines[se-1] there, i.e. the INPUT of that extraction (zeros when se == 0)
+            copy_row(rot + (long long)se * n, src, n, se == 0);
+            if (BAS && (p.opts & kOptZeroTail)) copy_row(bas + (long long)se * n, src, n, true);
         }
         if ((p.opts & kOptZeroTail) && e < p.rows) {
-            for (int t = tid; t < n; t += blockDim.x) {
-                rot[(long long)e * n + t] = (OutT)0;
-                if (bas) bas[(long long)e * n + t] = (OutT)0;
-            }
+            copy_row(rot + (long long)e * n, src, n, true);
+            if (BAS) copy_row(bas + (long long)e * n, src, n, true);
         }
         return;
     }
@@ -153,28 +240,27 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const Le
             sm.endl[1] = gendl[1];
             sm.carry_b[0] = sm.carry_b[1] = (CarryT)0;
             for (int s = 0; s < STAGES; ++s) {
-                mbar_init(&sm.full[s], 1);
-                mbar_init(&sm.empty[s], WARPS);
+                mbar_init(full0 + 8 * s, 1);
+                mbar_init(empty0 + 8 * s, WARPS);
             }
             mbar_fence_init();
         }
     }
     __syncthreads();
 
-    const InT *x = reinterpret_cast<const InT *>(p.in) + (long long)sig * n;
-    const int *gtau = p.cur.tau + (long long)sig * p.cur.kstride;
-    const CarryT *gxk = reinterpret_cast<const CarryT *>(p.cur.xk) + (long long)sig * p.cur.kstride;
-    const unsigned *gmask_in = p.cur.mask + (long long)sig * p.cur.mstride;
-
     // =========================================================================================
     // producer warp: TMA bulk loads, STAGES tiles deep
     // =========================================================================================
     if (warp == WARPS) {
         if (lane == 0) {
+            const InT *x = reinterpret_cast<const InT *>(p.in) + (long long)sig * n;
+            const int *gtau = p.cur.tau + (long long)sig * p.cur.kstride;
+            const CarryT *gxk = reinterpret_cast<const CarryT *>(p.cur.xk) + (long long)sig * p.cur.kstride;
+            const unsigned *gmask_in = p.cur.mask + (long long)sig * p.cur.mstride;
             for (int i = 0; i < tiles; ++i) {
                 const int s = i % STAGES;
-                mbar_wait(&sm.empty[s], ((i / STAGES) & 1) ^ 1);
-                typename Smem::Stage &st = sm.stage[s];
+                mbar_wait_backoff(empty0 + 8 * s, ((i / STAGES) & 1) ^ 1);
+                const unsigned st = sbase + (unsigned)(offsetof(Smem, stage) + (size_t)s * sizeof(typename Smem::Stage));
                 const int t0 = i * T;
                 const int len = min(T, n - t0);
                 const int kb = sm.tbase[i], cnt = sm.tbase[i + 1] - kb;
@@ -185,11 +271,12 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const Le
                 const unsigned bm = (unsigned)((((len + 31) / 32 + 3) & ~3) * sizeof(unsigned));
                 const unsigned bt = (unsigned)(nk * sizeof(int));
                 const unsigned bk = (unsigned)(nk * sizeof(CarryT));
-                mbar_arrive_expect_tx(&sm.full[s], bx + bm + bt + bk);
-                tma_load_1d(st.x, x + t0, bx, &sm.full[s]);
-                tma_load_1d(st.mask, gmask_in + (t0 >> 5), bm, &sm.full[s]);
-                tma_load_1d(st.tau, gtau + lo, bt, &sm.full[s]);
-                tma_load_1d(st.xk, gxk + lo, bk, &sm.full[s]);
+                const unsigned bar = full0 + 8 * s;
+                mbar_arrive_expect_tx(bar, bx + bm + bt + bk);
+                tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, x), x + t0, bx, bar);
+                tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, mask), gmask_in + (t0 >> 5), bm, bar);
+                tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, tau), gtau + lo, bt, bar);
+                tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, xk), gxk + lo, bk, bar);
             }
         }
         return;
@@ -198,36 +285,37 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const Le
     // =========================================================================================
     // consumer warps
     // =========================================================================================
-    OutT *rot = reinterpret_cast<OutT *>(p.rot) + row_off + (long long)e * n;
-    OutT *bas = p.bas ? reinterpret_cast<OutT *>(p.bas) + row_off + (long long)e * n : nullptr;
-    CarryT *carry = reinterpret_cast<CarryT *>(p.carry_out) + (long long)sig * n;
+    const int span0 = warp * SPAN;                        // first sample of this warp's span (in tile)
+    // running per-thread output pointers (advance by T per tile)
+    OutT *rot = reinterpret_cast<OutT *>(p.rot) + row_off + (long long)e * n + span0 + lane;
+    OutT *bas = BAS ? reinterpret_cast<OutT *>(p.bas) + row_off + (long long)e * n + span0 + lane : nullptr;
+    CarryT *carry = reinterpret_cast<CarryT *>(p.carry_out) + (long long)sig * n + span0 + lane;
     int *ntau = p.next.tau + (long long)sig * p.next.kstride;
     CarryT *nxk = reinterpret_cast<CarryT *>(p.next.xk) + (long long)sig * p.next.kstride;
-    unsigned *nmask = p.next.mask + (long long)sig * p.next.mstride;
+    unsigned *nmask = p.next.mask + (long long)sig * p.next.mstride + warp * ITEMS + lane;
     int *ntbase = p.next.tbase + (long long)sig * (tiles + 1);
     CarryT *nendl = reinterpret_cast<CarryT *>(p.next.endl) + 2ll * sig;
-    const bool last_level = (e == p.emax);
     CarryT *kL = sm.kL[warp];
     CarryT *kS = sm.kS[warp];
-    const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned le_mask = 0xffffffffu >> (31 - lane);
 
     int run_total = 0;          // new-level knots found in earlier tiles (identical in every warp)
+    int cached_wb = -1;         // segment whose (L, slope) sit in kL[0..1], kS[0] from a knot-free span
     bool zero_dx = false;
 
-    for (int i = 0; i < tiles; ++i) {
+    auto tile_body = [&](auto edge_tag, const int i) {
+        constexpr bool EDGE = decltype(edge_tag)::value;
         const int s = i % STAGES;
         typename Smem::Stage &st = sm.stage[s];
         const int t0 = i * T;
-        const int len = min(T, n - t0);
-        const int span0 = warp * SPAN;                    // first sample of this warp's span (in tile)
-        const int kb = sm.tbase[i], cnt = sm.tbase[i + 1] - kb;
+        const int len = EDGE ? min(T, n - t0) : T;
+        const int kb = sm.tbase[i];
         const int lo = max(kb - 1, 0) & ~3;
-        mbar_wait(&sm.full[s], (i / STAGES) & 1);
+        mbar_wait(full0 + 8 * s, (i / STAGES) & 1);
 
         // ---- A. segment bases from the stored flag words --------------------------------------
         const int nwords = (len + 31) >> 5;
-        const unsigned word = (lane < nwords) ? st.mask[lane] : 0u;
+        const unsigned word = (!EDGE || lane < nwords) ? st.mask[lane] : 0u;
         const int pc = __popc(word);
         int incl = pc;
 #pragma unroll
@@ -243,79 +331,88 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const Le
             mw[r] = shfl_idx(word, warp * ITEMS + r);
             wpre[r] = shfl_idx(excl, warp * ITEMS + r);
         }
+        const unsigned next_word = shfl_idx(word, (warp + 1 < WARPS ? warp + 1 : warp) * ITEMS);
         const int wb = kb + wpre[0];                                  // knots before the span = seg(span0 - 1)
         const int wcnt = wpre[ITEMS - 1] + __popc(mw[ITEMS - 1]) - wpre[0];   // knots inside the span
-        const bool span_live = span0 < len;
+#pragma unroll
+        for (int r = ITEMS - 1; r >= 0; --r) wpre[r] -= wpre[0];
+        const bool span_live = !EDGE || span0 < len;
 
-        // right-halo sample (first sample after the span): value, flag, availability
-        const int tend = t0 + span0 + SPAN;                           // global index of that sample
-        bool have_right = span_live && (tend <= n - 1);
+        // right-halo sample (first sample after the span)
+        const int tend = t0 + span0 + SPAN;                           // its global index
+        const bool have_right = !EDGE || (span_live && tend <= n - 1);
         CarryT xright = (CarryT)0;
         int fright = 0;
         if (have_right) {
             if (warp < WARPS - 1) {
                 xright = (CarryT)st.x[span0 + SPAN];
-                fright = (int)(shfl_idx(word, (warp + 1) * ITEMS) & 1u);
+                fright = (int)(next_word & 1u);
             } else {
                 // first sample of the NEXT tile: the producer is ahead, wait for its stage
                 const int s2 = (i + 1) % STAGES;
-                mbar_wait(&sm.full[s2], ((i + 1) / STAGES) & 1);
+                mbar_wait(full0 + 8 * s2, ((i + 1) / STAGES) & 1);
                 xright = (CarryT)sm.stage[s2].x[0];
                 fright = (int)(sm.stage[s2].mask[0] & 1u);
             }
         }
 
         // ---- B. knot baseline + slopes for the knots this span touches (warp-private) ----------
-        // L for k in [wb, wb + wcnt + 2], slope for segments [wb, wb + wcnt + 1], clipped to the table
-        if (span_live) {
+        // L for k in [wb, wb + wcnt + 2], slope for segments [wb, wb + wcnt + 1], clipped to the table.
+        // A knot-free span inside the same segment as the previous tile reuses the cached pair.
+        const CarryT *xkb = st.xk + (wb - lo);                        // xkb[j] = X of knot wb + j
+        const bool knot_free = (wcnt == 0 && fright == 0);
+        if (span_live && !(knot_free && wb == cached_wb)) {
+            const int *taub = st.tau + (wb - lo);
             const int nl = min(wcnt + 3, K + 2 - wb);
             for (int j = lane; j < nl; j += 32) {
                 const int k = wb + j;
-                const int q = k - lo;
                 CarryT L;
                 if (k == 0) {
                     L = sm.endl[0];
                 } else if (k == K + 1) {
                     L = sm.endl[1];
                 } else {
-                    const CarryT w = A::ratio(st.tau[q] - st.tau[q - 1], st.tau[q + 1] - st.tau[q - 1]);
-                    const CarryT d = A::sub(st.xk[q + 1], st.xk[q - 1]);
-                    const CarryT qq = A::add(st.xk[q - 1], A::mul(w, d));
-                    L = A::add(A::mul((CarryT)0.5, qq), A::mul((CarryT)0.5, st.xk[q]));
+                    const CarryT w = A::ratio(taub[j] - taub[j - 1], taub[j + 1] - taub[j - 1]);
+                    const CarryT d = A::sub(xkb[j + 1], xkb[j - 1]);
+                    const CarryT qq = A::add(xkb[j - 1], A::mul(w, d));
+                    L = A::add(A::mul((CarryT)0.5, qq), A::mul((CarryT)0.5, xkb[j]));
                 }
                 kL[j] = L;
             }
             __syncwarp();
             const int ns = min(wcnt + 2, K + 1 - wb);
             for (int j = lane; j < ns; j += 32) {
-                const int q = wb + j - lo;
-                const CarryT den = A::sub(st.xk[q + 1], st.xk[q]);
+                const CarryT den = A::sub(xkb[j + 1], xkb[j]);
                 kS[j] = A::div(A::sub(kL[j + 1], kL[j]), den);
                 zero_dx |= (den == (CarryT)0);
             }
             __syncwarp();
         }
+        cached_wb = (span_live && knot_free) ? wb : -1;
 
         // ---- C. B, R for the span (+ one halo sample each side) --------------------------------
         CarryT b[ITEMS];
+        const InT *xs = st.x + span0 + lane;
 #pragma unroll
         for (int r = 0; r < ITEMS; ++r) {
             const int jt = span0 + r * 32 + lane;
-            const int t = t0 + jt;
-            const CarryT xv = (jt < len) ? (CarryT)st.x[jt] : (CarryT)0;
-            const int j = min(wpre[r] - wpre[0] + __popc(mw[r] & le_mask), K - wb);
             CarryT bv = (CarryT)0;
-            if (jt < len) {
-                bv = A::add(kL[j], A::mul(kS[j], A::sub(xv, st.xk[wb + j - lo])));
-                if (t == n - 1) bv = (CarryT)0;                       // ITD.py:112
+            if (!EDGE || jt < len) {
+                const CarryT xv = (CarryT)xs[r * 32];
+                const int j = wpre[r] + __popc(mw[r] & le_mask);
+                bv = A::add(kL[j], A::mul(kS[j], A::sub(xv, xkb[j])));
+                if (EDGE && t0 + jt == n - 1) bv = (CarryT)0;         // ITD.py:112
                 const CarryT rr = A::sub(xv, bv);
-                rot[t] = (OutT)(last_level ? A::add(rr, bv) : rr);    // ITD.py:119 / :420
-                carry[t] = bv;
-                if (bas) bas[t] = last_level ? (OutT)0 : (OutT)bv;    // ITD.py:424
-                if (t == n - 2) nendl[1] = mean2<CarryT>(bv, (CarryT)0);
+                rot[r * 32] = (OutT)(LAST ? A::add(rr, bv) : rr);     // ITD.py:119 / :420
+                carry[r * 32] = bv;
+                if (BAS) bas[r * 32] = LAST ? (OutT)0 : (OutT)bv;     // ITD.py:424
+                if (EDGE && t0 + jt == n - 2) nendl[1] = mean2<CarryT>(bv, (CarryT)0);
             }
             b[r] = bv;
         }
+        rot += T;
+        carry += T;
+        if (BAS) bas += T;
         // left halo B[span0 - 1]: previous warp's last sample (same tile) or the previous tile's
         CarryT bleft = (CarryT)0;
         if (span_live) {
@@ -323,56 +420,29 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const Le
                 bleft = sm.carry_b[(i + 1) & 1];
             } else {
                 const CarryT xl = (CarryT)st.x[span0 - 1];
-                const int j = min(0, K - wb);
-                bleft = A::add(kL[j], A::mul(kS[j], A::sub(xl, st.xk[wb + j - lo])));
+                bleft = A::add(kL[0], A::mul(kS[0], A::sub(xl, xkb[0])));
             }
         }
         CarryT bright = (CarryT)0;
-        if (have_right && tend < n - 1) {
-            const int j = min(wcnt + fright, K - wb);
-            bright = A::add(kL[j], A::mul(kS[j], A::sub(xright, st.xk[wb + j - lo])));
+        if (have_right && (!EDGE || tend < n - 1)) {
+            const int j = wcnt + fright;
+            bright = A::add(kL[j], A::mul(kS[j], A::sub(xright, xkb[j])));
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[s]);                     // stage consumed by this warp
+        if (lane == 0) mbar_arrive(empty0 + 8 * s);                   // stage consumed by this warp
 
         // ---- D. extrema of B: next level's flag words -----------------------------------------
         unsigned fw[ITEMS];
-        int newc = 0;
-        {
-            unsigned lt_in, gt_in;
-            {
-                const CarryT b0 = shfl_idx(b[0], 0);
-                lt_in = (bleft < b0) ? 1u : 0u;
-                gt_in = (bleft > b0) ? 1u : 0u;
-            }
-#pragma unroll
-            for (int r = 0; r < ITEMS; ++r) {
-                CarryT nx = __shfl_down_sync(0xffffffffu, b[r], 1);
-                const CarryT wrap = (r + 1 < ITEMS) ? shfl_idx(b[(r + 1 < ITEMS) ? r + 1 : r], 0) : bright;
-                if (lane == 31) nx = wrap;
-                const unsigned LT = __ballot_sync(0xffffffffu, b[r] < nx);
-                const unsigned GT = __ballot_sync(0xffffffffu, b[r] > nx);
-                unsigned f = (~((LT << 1) | lt_in) & LT) | (~((GT << 1) | gt_in) & GT);
-                lt_in = LT >> 31;
-                gt_in = GT >> 31;
-                // valid positions: 1 <= t <= n-2
-                const int tw = t0 + span0 + r * 32;                   // global index of bit 0
-                if (tw == 0) f &= ~1u;
-                const int lastbit = n - 2 - tw;                       // highest valid bit
-                f = (lastbit < 0) ? 0u : ((lastbit >= 31) ? f : (f & (0xffffffffu >> (31 - lastbit))));
-                fw[r] = f;
-                newc += __popc(f);
-            }
-        }
-        if (lane == 0) sm.cnt[i & 1][warp] = newc;
-        if (lane < ITEMS && span0 + lane * 32 < len) {
+        const int newc = span_extrema<EDGE, ITEMS, CarryT>(b, bleft, bright, lane, t0 + span0, n, fw);
+        if (lane < ITEMS && (!EDGE || span0 + lane * 32 < len)) {
             unsigned v = fw[0];
 #pragma unroll
             for (int r = 1; r < ITEMS; ++r) v = (lane == r) ? fw[r] : v;
-            nmask[(t0 + span0) / 32 + lane] = v;
+            nmask[0] = v;
         }
+        nmask += T / 32;
         if (warp == WARPS - 1 && lane == 31) sm.carry_b[i & 1] = b[ITEMS - 1];
-        if (i == 0 && warp == 0) {
+        if (EDGE && i == 0 && warp == 0) {
             const CarryT b1 = shfl_idx(b[0], 1);
             if (lane == 0) {
                 ntau[0] = 0;
@@ -380,29 +450,16 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const Le
                 nendl[0] = mean2<CarryT>(b[0], b1);
             }
         }
+        // ---- E/F/G. one block barrier, then compact the new knots ------------------------------
+        compact_knots<WARPS, ITEMS, CarryT>(sm.cnt, i, warp, lane, newc, fw, b, t0 + span0, run_total, ntau, nxk,
+                                            ntbase);
+    };
 
-        // ---- E. the one block barrier per tile -----------------------------------------------
-        named_barrier_sync(1, WARPS * 32);
-
-        // ---- F/G. compact the new knots -------------------------------------------------------
-        int pre = run_total, tot = 0;
-#pragma unroll
-        for (int w2 = 0; w2 < WARPS; ++w2) {
-            const int c = sm.cnt[i & 1][w2];
-            pre += (w2 < warp) ? c : 0;
-            tot += c;
-        }
-        if (warp == 0 && lane == 0) ntbase[i] = run_total;
-        run_total += tot;
-#pragma unroll
-        for (int r = 0; r < ITEMS; ++r) {
-            if ((fw[r] >> lane) & 1u) {
-                const int rank = pre + __popc(fw[r] & lt_mask);
-                ntau[1 + rank] = t0 + span0 + r * 32 + lane;
-                nxk[1 + rank] = b[r];
-            }
-            pre += __popc(fw[r]);
-        }
+    for (int i = 0; i < tiles; ++i) {
+        if (i == 0 || i == tiles - 1)
+            tile_body(std::true_type{}, i);
+        else
+            tile_body(std::false_type{}, i);
     }
 
     if (zero_dx) atomicOr(p.status + sig, kStZeroDx);
@@ -417,11 +474,162 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const Le
             p.stop_kind[sig] = kStopKnots;
             p.n_rows[sig] = e + 1;
             p.stop_e[sig] = e;
-        } else if (last_level) {                                      // ITD.py:418
+        } else if (LAST) {                                            // ITD.py:418
             p.stop_kind[sig] = kStopIter;
             p.n_rows[sig] = e + 1;
             p.stop_e[sig] = e;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scan_stream_kernel: extrema detection + compaction on the raw input (ITD.py:87-98), same
+// pipeline, one CTA per signal.  Writes the same table/mask/tbase/endl as knot_scan_kernel.
+// ---------------------------------------------------------------------------------------------
+template <typename InT, typename CarryT, int WARPS, int ITEMS, int STAGES>
+__global__ void __launch_bounds__((WARPS + 1) * 32) scan_stream_kernel(const ScanParams p) {
+    using Smem = StreamSmem<InT, CarryT, WARPS, ITEMS, STAGES, false>;
+    constexpr int T = Smem::T;
+    constexpr int SPAN = Smem::SPAN;
+    extern __shared__ __align__(128) unsigned char smem_stream_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_stream_raw);
+    const unsigned sbase = smem_u32(smem_stream_raw);
+    const unsigned full0 = sbase + (unsigned)offsetof(Smem, full);
+    const unsigned empty0 = sbase + (unsigned)offsetof(Smem, empty);
+
+    const int sig = blockIdx.x;
+    const int n = p.n, tiles = p.tiles;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        sm.carry_b[0] = sm.carry_b[1] = (CarryT)0;
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const InT *x = reinterpret_cast<const InT *>(p.x) + (long long)sig * n;
+
+    if (warp == WARPS) {
+        if (lane == 0) {
+            for (int i = 0; i < tiles; ++i) {
+                const int s = i % STAGES;
+                mbar_wait_backoff(empty0 + 8 * s, ((i / STAGES) & 1) ^ 1);
+                const unsigned st = sbase + (unsigned)(offsetof(Smem, stage) + (size_t)s * sizeof(typename Smem::Stage));
+                const int t0 = i * T;
+                const unsigned bx = (unsigned)(min(T, n - t0) * sizeof(InT));
+                mbar_arrive_expect_tx(full0 + 8 * s, bx);
+                tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, x), x + t0, bx, full0 + 8 * s);
+            }
+        }
+        return;
+    }
+
+    const int span0 = warp * SPAN;
+    int *ntau = p.out.tau + (long long)sig * p.out.kstride;
+    CarryT *nxk = reinterpret_cast<CarryT *>(p.out.xk) + (long long)sig * p.out.kstride;
+    unsigned *nmask = p.out.mask + (long long)sig * p.out.mstride + warp * ITEMS + lane;
+    int *ntbase = p.out.tbase + (long long)sig * (tiles + 1);
+    CarryT *nendl = reinterpret_cast<CarryT *>(p.out.endl) + 2ll * sig;
+    int run_total = 0;
+    bool bad = false;
+
+    auto tile_body = [&](auto edge_tag, const int i) {
+        constexpr bool EDGE = decltype(edge_tag)::value;
+        const int s = i % STAGES;
+        typename Smem::Stage &st = sm.stage[s];
+        const int t0 = i * T;
+        const int len = EDGE ? min(T, n - t0) : T;
+        mbar_wait(full0 + 8 * s, (i / STAGES) & 1);
+        const bool span_live = !EDGE || span0 < len;
+        const int tend = t0 + span0 + SPAN;
+        const bool have_right = !EDGE || (span_live && tend <= n - 1);
+        CarryT v[ITEMS];
+        const InT *xs = st.x + span0 + lane;
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+            const int jt = span0 + r * 32 + lane;
+            v[r] = (!EDGE || jt < len) ? (CarryT)xs[r * 32] : (CarryT)0;
+            bad |= !isfinite(v[r]);
+            if (EDGE && t0 + jt == n - 2) {
+                const CarryT xl = (CarryT)st.x[jt + 1 < len ? jt + 1 : jt];   // x[n-1] is in this tile iff jt+1 < len
+                if (jt + 1 < len) nendl[1] = mean2<CarryT>(v[r], xl);
+            }
+        }
+        CarryT vleft = (CarryT)0, vright = (CarryT)0;
+        if (span_live) vleft = (warp == 0) ? sm.carry_b[(i + 1) & 1] : (CarryT)st.x[span0 - 1];
+        if (have_right) {
+            if (warp < WARPS - 1) {
+                vright = (CarryT)st.x[span0 + SPAN];
+            } else {
+                const int s2 = (i + 1) % STAGES;
+                mbar_wait(full0 + 8 * s2, ((i + 1) / STAGES) & 1);
+                vright = (CarryT)sm.stage[s2].x[0];
+            }
+        }
+        // x[n-1] opens a tile of its own: x[n-2] is the previous tile's last sample
+        if (EDGE && t0 == n - 1 && warp == 0 && lane == 0) nendl[1] = mean2<CarryT>(vleft, v[0]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * s);
+
+        unsigned fw[ITEMS];
+        int newc = span_extrema<EDGE, ITEMS, CarryT>(v, vleft, vright, lane, t0 + span0, n, fw);
+        if (p.kinds != 3) {
+            // detect_peaks(x) alone (valleys) or detect_peaks(-x) alone (peaks): filter the union
+            newc = 0;
+#pragma unroll
+            for (int r = 0; r < ITEMS; ++r) {
+                CarryT nx = __shfl_down_sync(0xffffffffu, v[r], 1);
+                const CarryT wrap = (r + 1 < ITEMS) ? shfl_idx(v[(r + 1 < ITEMS) ? r + 1 : r], 0) : vright;
+                if (lane == 31) nx = wrap;
+                const unsigned LT = __ballot_sync(0xffffffffu, v[r] < nx);   // rising after the sample = valley
+                fw[r] &= (p.kinds == 1) ? LT : ~LT;
+                newc += __popc(fw[r]);
+            }
+        }
+        if (lane < ITEMS && (!EDGE || span0 + lane * 32 < len)) {
+            unsigned w = fw[0];
+#pragma unroll
+            for (int r = 1; r < ITEMS; ++r) w = (lane == r) ? fw[r] : w;
+            nmask[0] = w;
+        }
+        nmask += T / 32;
+        if (warp == WARPS - 1 && lane == 31) sm.carry_b[i & 1] = v[ITEMS - 1];
+        if (EDGE && i == 0 && warp == 0) {
+            const CarryT v1 = shfl_idx(v[0], 1);
+            if (lane == 0) {
+                ntau[0] = 0;
+                nxk[0] = v[0];
+                nendl[0] = mean2<CarryT>(v[0], v1);
+            }
+        }
+        if (EDGE && t0 + span0 <= n - 1 && n - 1 < t0 + span0 + SPAN) {
+            // the lane holding x[n-1] publishes the closing knot's value (index written at the end)
+            const int q = n - 1 - t0 - span0;
+#pragma unroll
+            for (int r = 0; r < ITEMS; ++r)
+                if (q == r * 32 + lane) sm.endl[0] = v[r];
+        }
+        compact_knots<WARPS, ITEMS, CarryT>(sm.cnt, i, warp, lane, newc, fw, v, t0 + span0, run_total, ntau, nxk,
+                                            ntbase);
+    };
+
+    for (int i = 0; i < tiles; ++i) {
+        if (i == 0 || i == tiles - 1)
+            tile_body(std::true_type{}, i);
+        else
+            tile_body(std::false_type{}, i);
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.status + sig, kStNonFinite);
+    named_barrier_sync(1, WARPS * 32);                  // sm.endl[0] (x[n-1]) is visible
+    if (warp == 0 && lane == 0) {
+        const int K = run_total;
+        ntbase[tiles] = K;
+        p.out.kcount[sig] = K;
+        ntau[K + 1] = n - 1;
+        nxk[K + 1] = sm.endl[0];
+        if (p.input_knots) p.input_knots[sig] = K;
     }
 }
 
