@@ -113,8 +113,8 @@ static cudaError_t launch_level_cfg(int cfg, const LevelParams &p, long long cta
     }
 }
 
-// one CTA per signal, 8 consumer warps x 4 samples/lane = 1024-sample tiles, 3-stage TMA ring
-constexpr int kStreamWarps = 8, kStreamItems = 4, kStreamStages = 3;
+// one CTA per signal, 8 warps x 4 samples/lane = 1024-sample tiles, 2-stage TMA ring, 3 CTAs per SM
+constexpr int kStreamWarps = 8, kStreamItems = 4, kStreamStages = 2;
 constexpr int kStreamTile = kStreamWarps * 32 * kStreamItems;
 
 template <typename InT, typename CarryT, typename OutT, bool LAST, bool BAS>
@@ -123,7 +123,7 @@ static cudaError_t launch_stream_v(const LevelParams &p, long long ctas, cudaStr
     constexpr size_t smem = sizeof(StreamSmem<InT, CarryT, kStreamWarps, kStreamItems, kStreamStages, true>);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<(unsigned)ctas, (kStreamWarps + 1) * 32, smem, st>>>(p);
+    k<<<(unsigned)ctas, kStreamWarps * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 template <typename InT, typename CarryT, typename OutT>
@@ -140,7 +140,7 @@ static cudaError_t launch_scan_stream_t(const ScanParams &p, long long ctas, cud
     constexpr size_t smem = sizeof(StreamSmem<InT, CarryT, kStreamWarps, kStreamItems, kStreamStages, false>);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<(unsigned)ctas, (kStreamWarps + 1) * 32, smem, st>>>(p);
+    k<<<(unsigned)ctas, kStreamWarps * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -3,9 +3,9 @@
 // Same arithmetic and the same HBM data structures as the look-back kernels (itd_kernels.cuh); the
 // difference is how a signal is moved through the SM:
 //
-//   * a producer warp streams each tile's samples, knot-flag words and knot-table slice into a
-//     shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), several
-//     tiles ahead of the math;
+//   * each tile's samples, knot-flag words and knot-table slice arrive in a shared-memory ring by
+//     TMA bulk copies (cp.async.bulk + mbarrier complete_tx) issued STAGES tiles ahead of the math
+//     by one elected thread right after the per-tile barrier (which also proves the stage free);
 //   * eight consumer warps each own a contiguous 32*ITEMS-sample span of the tile.  A warp derives
 //     its segment ids from the stored flag words (no stencil re-run, no block scan), evaluates the
 //     knot baseline / slopes for exactly the knots its span touches (ITD.py:106-110,116) in warp-
@@ -42,9 +42,6 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
     unsigned ok;
     asm volatile(
@@ -59,10 +56,6 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
-}
-// the producer is normally far ahead of the math: poll politely so it does not eat issue slots
-__device__ __forceinline__ void mbar_wait_backoff(unsigned bar, unsigned parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(200);
 }
 // global -> shared bulk copy; dst, src 16-byte aligned, bytes a multiple of 16
 __device__ __forceinline__ void tma_load_1d(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
@@ -95,11 +88,12 @@ struct StreamSmem {
         alignas(16) int tau[KC];
         alignas(16) CarryT xk[KC];
     };
+    struct alignas(2 * sizeof(CarryT)) LS {
+        CarryT L, s;                             // knot baseline L_k and slope of segment [k, k+1)
+    };
     Stage stage[STAGES];
     alignas(8) unsigned long long full[STAGES];
-    alignas(8) unsigned long long empty[STAGES];
-    CarryT kL[WARPS][SC];
-    CarryT kS[WARPS][SC];
+    LS ls[WARPS][SC];
     int tbase[WITH_KNOTS ? MAX_TILES + 1 : 1];
     int cnt[2][WARPS];
     CarryT carry_b[2];                           // value of the previous tile's last sample (by tile parity)
@@ -121,9 +115,9 @@ __device__ __forceinline__ int span_extrema(const CarryT (&v)[ITEMS], CarryT vle
     int total = 0;
 #pragma unroll
     for (int r = 0; r < ITEMS; ++r) {
-        CarryT nx = __shfl_down_sync(0xffffffffu, v[r], 1);
-        const CarryT wrap = (r + 1 < ITEMS) ? shfl_idx(v[(r + 1 < ITEMS) ? r + 1 : r], 0) : vright;
-        if (lane == 31) nx = wrap;
+        // right neighbour: lane+1 of the same round; lane 31 takes lane 0 of the next round
+        const CarryT give = (lane == 0) ? ((r + 1 < ITEMS) ? v[(r + 1 < ITEMS) ? r + 1 : r] : vright) : v[r];
+        const CarryT nx = shfl_idx(give, (lane + 1) & 31);
         const unsigned LT = __ballot_sync(0xffffffffu, v[r] < nx);
         const unsigned GT = __ballot_sync(0xffffffffu, v[r] > nx);
         // valley: !(v[i-1] < v[i]) && v[i] < v[i+1];  peak: !(v[i-1] > v[i]) && v[i] > v[i+1]
@@ -149,13 +143,9 @@ __device__ __forceinline__ void compact_knots(int (&cnt)[2][WARPS], int i, int w
                                               int tspan, int &run_total, int *ntau, CarryT *nxk, int *ntbase) {
     if (lane == 0) cnt[i & 1][warp] = newc;
     named_barrier_sync(1, WARPS * 32);
-    int pre = run_total, tot = 0;
-#pragma unroll
-    for (int w2 = 0; w2 < WARPS; ++w2) {
-        const int c = cnt[i & 1][w2];
-        pre += (w2 < warp) ? c : 0;
-        tot += c;
-    }
+    const int c = (lane < WARPS) ? cnt[i & 1][lane] : 0;
+    const int tot = __reduce_add_sync(0xffffffffu, c);
+    int pre = run_total + __reduce_add_sync(0xffffffffu, (lane < warp) ? c : 0);
     if (warp == 0 && lane == 0) ntbase[i] = run_total;
     run_total += tot;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -192,17 +182,18 @@ __device__ __forceinline__ void copy_row(OutT *dst, const CarryT *src, int n, bo
 // level_stream_kernel
 // ---------------------------------------------------------------------------------------------
 template <typename InT, typename CarryT, typename OutT, int WARPS, int ITEMS, int STAGES, bool LAST, bool BAS>
-__global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const LevelParams p) {
+__global__ void __launch_bounds__(WARPS * 32, 3) level_stream_kernel(const LevelParams p) {
     using A = Arith<CarryT>;
     using Smem = StreamSmem<InT, CarryT, WARPS, ITEMS, STAGES, true>;
+    using LS = typename Smem::LS;
     constexpr int T = Smem::T;
     constexpr int SPAN = Smem::SPAN;
-    static_assert(T / 32 <= 32, "one flag word per lane");
+    static_assert(T / 32 <= 32 && ITEMS == 4, "one flag word per lane, four words per warp (LDS.128)");
     extern __shared__ __align__(128) unsigned char smem_stream_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_stream_raw);
-    const unsigned sbase = smem_u32(smem_stream_raw);
+    unsigned sbase = smem_u32(smem_stream_raw);
+    asm volatile("" : "+r"(sbase));                       // keep it in a register (no S2R re-derivation)
     const unsigned full0 = sbase + (unsigned)offsetof(Smem, full);
-    const unsigned empty0 = sbase + (unsigned)offsetof(Smem, empty);
 
     const int sig = blockIdx.x;
     const int n = p.n, e = p.e, tiles = p.tiles;
@@ -239,52 +230,40 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const Le
             sm.endl[0] = gendl[0];
             sm.endl[1] = gendl[1];
             sm.carry_b[0] = sm.carry_b[1] = (CarryT)0;
-            for (int s = 0; s < STAGES; ++s) {
-                mbar_init(full0 + 8 * s, 1);
-                mbar_init(empty0 + 8 * s, WARPS);
-            }
+            for (int s = 0; s < STAGES; ++s) mbar_init(full0 + 8 * s, 1);
             mbar_fence_init();
         }
     }
     __syncthreads();
 
-    // =========================================================================================
-    // producer warp: TMA bulk loads, STAGES tiles deep
-    // =========================================================================================
-    if (warp == WARPS) {
-        if (lane == 0) {
-            const InT *x = reinterpret_cast<const InT *>(p.in) + (long long)sig * n;
-            const int *gtau = p.cur.tau + (long long)sig * p.cur.kstride;
-            const CarryT *gxk = reinterpret_cast<const CarryT *>(p.cur.xk) + (long long)sig * p.cur.kstride;
-            const unsigned *gmask_in = p.cur.mask + (long long)sig * p.cur.mstride;
-            for (int i = 0; i < tiles; ++i) {
-                const int s = i % STAGES;
-                mbar_wait_backoff(empty0 + 8 * s, ((i / STAGES) & 1) ^ 1);
-                const unsigned st = sbase + (unsigned)(offsetof(Smem, stage) + (size_t)s * sizeof(typename Smem::Stage));
-                const int t0 = i * T;
-                const int len = min(T, n - t0);
-                const int kb = sm.tbase[i], cnt = sm.tbase[i + 1] - kb;
-                const int lo = max(kb - 1, 0) & ~3;
-                const int hi = min(kb + cnt + 3, K + 1);
-                const int nk = (hi - lo + 1 + 3) & ~3;
-                const unsigned bx = (unsigned)(len * sizeof(InT));
-                const unsigned bm = (unsigned)((((len + 31) / 32 + 3) & ~3) * sizeof(unsigned));
-                const unsigned bt = (unsigned)(nk * sizeof(int));
-                const unsigned bk = (unsigned)(nk * sizeof(CarryT));
-                const unsigned bar = full0 + 8 * s;
-                mbar_arrive_expect_tx(bar, bx + bm + bt + bk);
-                tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, x), x + t0, bx, bar);
-                tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, mask), gmask_in + (t0 >> 5), bm, bar);
-                tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, tau), gtau + lo, bt, bar);
-                tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, xk), gxk + lo, bk, bar);
-            }
-        }
-        return;
-    }
+    // TMA bulk loads of tile i into stage i % STAGES (one thread)
+    const InT *x = reinterpret_cast<const InT *>(p.in) + (long long)sig * n;
+    const int *gtau = p.cur.tau + (long long)sig * p.cur.kstride;
+    const CarryT *gxk = reinterpret_cast<const CarryT *>(p.cur.xk) + (long long)sig * p.cur.kstride;
+    const unsigned *gmask_in = p.cur.mask + (long long)sig * p.cur.mstride;
+    auto issue_tile = [&](const int i) {
+        const int s = i % STAGES;
+        const unsigned st = sbase + (unsigned)(offsetof(Smem, stage) + (size_t)s * sizeof(typename Smem::Stage));
+        const int t0 = i * T;
+        const int len = min(T, n - t0);
+        const int kb = sm.tbase[i], cnt = sm.tbase[i + 1] - kb;
+        const int lo = max(kb - 1, 0) & ~3;
+        const int hi = min(kb + cnt + 3, K + 1);
+        const int nk = (hi - lo + 1 + 3) & ~3;
+        const unsigned bx = (unsigned)(len * sizeof(InT));
+        const unsigned bm = (unsigned)((((len + 31) / 32 + 3) & ~3) * sizeof(unsigned));
+        const unsigned bt = (unsigned)(nk * sizeof(int));
+        const unsigned bk = (unsigned)(nk * sizeof(CarryT));
+        const unsigned bar = full0 + 8 * s;
+        mbar_arrive_expect_tx(bar, bx + bm + bt + bk);
+        tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, x), x + t0, bx, bar);
+        tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, mask), gmask_in + (t0 >> 5), bm, bar);
+        tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, tau), gtau + lo, bt, bar);
+        tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, xk), gxk + lo, bk, bar);
+    };
+    if (tid == 0)
+        for (int i = 0; i < STAGES && i < tiles; ++i) issue_tile(i);
 
-    // =========================================================================================
-    // consumer warps
-    // =========================================================================================
     const int span0 = warp * SPAN;                        // first sample of this warp's span (in tile)
     // running per-thread output pointers (advance by T per tile)
     OutT *rot = reinterpret_cast<OutT *>(p.rot) + row_off + (long long)e * n + span0 + lane;
@@ -295,12 +274,11 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const Le
     unsigned *nmask = p.next.mask + (long long)sig * p.next.mstride + warp * ITEMS + lane;
     int *ntbase = p.next.tbase + (long long)sig * (tiles + 1);
     CarryT *nendl = reinterpret_cast<CarryT *>(p.next.endl) + 2ll * sig;
-    CarryT *kL = sm.kL[warp];
-    CarryT *kS = sm.kS[warp];
+    LS *ls = sm.ls[warp];
     const unsigned le_mask = 0xffffffffu >> (31 - lane);
 
     int run_total = 0;          // new-level knots found in earlier tiles (identical in every warp)
-    int cached_wb = -1;         // segment whose (L, slope) sit in kL[0..1], kS[0] from a knot-free span
+    int cached_wb = -1;         // segment whose (L, slope) sit in ls[0..1] from a knot-free span
     bool zero_dx = false;
 
     auto tile_body = [&](auto edge_tag, const int i) {
@@ -316,26 +294,23 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const Le
         // ---- A. segment bases from the stored flag words --------------------------------------
         const int nwords = (len + 31) >> 5;
         const unsigned word = (!EDGE || lane < nwords) ? st.mask[lane] : 0u;
-        const int pc = __popc(word);
-        int incl = pc;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const int excl = incl - pc;
+        // knots of the tile before this warp's span
+        const int wpre0 = __reduce_add_sync(0xffffffffu, (lane < warp * ITEMS) ? __popc(word) : 0);
         unsigned mw[ITEMS];
-        int wpre[ITEMS];
+        {
+            const uint4 q = *reinterpret_cast<const uint4 *>(&st.mask[warp * ITEMS]);
+            mw[0] = q.x; mw[1] = q.y; mw[2] = q.z; mw[3] = q.w;
+            if (EDGE) {
 #pragma unroll
-        for (int r = 0; r < ITEMS; ++r) {
-            mw[r] = shfl_idx(word, warp * ITEMS + r);
-            wpre[r] = shfl_idx(excl, warp * ITEMS + r);
+                for (int r = 0; r < ITEMS; ++r) mw[r] = (warp * ITEMS + r < nwords) ? mw[r] : 0u;
+            }
         }
-        const unsigned next_word = shfl_idx(word, (warp + 1 < WARPS ? warp + 1 : warp) * ITEMS);
-        const int wb = kb + wpre[0];                                  // knots before the span = seg(span0 - 1)
-        const int wcnt = wpre[ITEMS - 1] + __popc(mw[ITEMS - 1]) - wpre[0];   // knots inside the span
+        int wpre[ITEMS];                                              // knots of the span before word r
+        wpre[0] = 0;
 #pragma unroll
-        for (int r = ITEMS - 1; r >= 0; --r) wpre[r] -= wpre[0];
+        for (int r = 1; r < ITEMS; ++r) wpre[r] = wpre[r - 1] + __popc(mw[r - 1]);
+        const int wb = kb + wpre0;                                    // knots before the span = seg(span0 - 1)
+        const int wcnt = wpre[ITEMS - 1] + __popc(mw[ITEMS - 1]);     // knots inside the span
         const bool span_live = !EDGE || span0 < len;
 
         // right-halo sample (first sample after the span)
@@ -346,9 +321,9 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const Le
         if (have_right) {
             if (warp < WARPS - 1) {
                 xright = (CarryT)st.x[span0 + SPAN];
-                fright = (int)(next_word & 1u);
+                fright = (int)(st.mask[(warp + 1) * ITEMS] & 1u);
             } else {
-                // first sample of the NEXT tile: the producer is ahead, wait for its stage
+                // first sample of the NEXT tile: its load was issued STAGES-1 tiles ago
                 const int s2 = (i + 1) % STAGES;
                 mbar_wait(full0 + 8 * s2, ((i + 1) / STAGES) & 1);
                 xright = (CarryT)sm.stage[s2].x[0];
@@ -364,27 +339,35 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const Le
         if (span_live && !(knot_free && wb == cached_wb)) {
             const int *taub = st.tau + (wb - lo);
             const int nl = min(wcnt + 3, K + 2 - wb);
-            for (int j = lane; j < nl; j += 32) {
-                const int k = wb + j;
-                CarryT L;
-                if (k == 0) {
-                    L = sm.endl[0];
-                } else if (k == K + 1) {
-                    L = sm.endl[1];
-                } else {
-                    const CarryT w = A::ratio(taub[j] - taub[j - 1], taub[j + 1] - taub[j - 1]);
-                    const CarryT d = A::sub(xkb[j + 1], xkb[j - 1]);
-                    const CarryT qq = A::add(xkb[j - 1], A::mul(w, d));
-                    L = A::add(A::mul((CarryT)0.5, qq), A::mul((CarryT)0.5, xkb[j]));
-                }
-                kL[j] = L;
-            }
-            __syncwarp();
             const int ns = min(wcnt + 2, K + 1 - wb);
-            for (int j = lane; j < ns; j += 32) {
-                const CarryT den = A::sub(xkb[j + 1], xkb[j]);
-                kS[j] = A::div(A::sub(kL[j + 1], kL[j]), den);
-                zero_dx |= (den == (CarryT)0);
+            auto knot_L = [&](const int j) -> CarryT {                // ITD.py:100-110
+                const int k = wb + j;
+                if (k == 0) return sm.endl[0];
+                if (k == K + 1) return sm.endl[1];
+                const CarryT w = A::ratio(taub[j] - taub[j - 1], taub[j + 1] - taub[j - 1]);
+                const CarryT d = A::sub(xkb[j + 1], xkb[j - 1]);
+                const CarryT qq = A::add(xkb[j - 1], A::mul(w, d));
+                return A::add(A::mul((CarryT)0.5, qq), A::mul((CarryT)0.5, xkb[j]));
+            };
+            if (nl <= 32) {
+                // one knot per lane; the neighbour's L comes by shuffle
+                const CarryT L = (lane < nl) ? knot_L(lane) : (CarryT)0;
+                const CarryT Ln = __shfl_down_sync(0xffffffffu, L, 1);
+                CarryT sl = (CarryT)0;
+                if (lane < ns) {
+                    const CarryT den = A::sub(xkb[lane + 1], xkb[lane]);     // ITD.py:116
+                    sl = A::div(A::sub(Ln, L), den);
+                    zero_dx |= (den == (CarryT)0);
+                }
+                if (lane < nl) ls[lane] = LS{L, sl};
+            } else {
+                for (int j = lane; j < nl; j += 32) ls[j].L = knot_L(j);
+                __syncwarp();
+                for (int j = lane; j < ns; j += 32) {
+                    const CarryT den = A::sub(xkb[j + 1], xkb[j]);
+                    ls[j].s = A::div(A::sub(ls[j + 1].L, ls[j].L), den);
+                    zero_dx |= (den == (CarryT)0);
+                }
             }
             __syncwarp();
         }
@@ -400,7 +383,8 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const Le
             if (!EDGE || jt < len) {
                 const CarryT xv = (CarryT)xs[r * 32];
                 const int j = wpre[r] + __popc(mw[r] & le_mask);
-                bv = A::add(kL[j], A::mul(kS[j], A::sub(xv, xkb[j])));
+                const LS q = ls[j];
+                bv = A::add(q.L, A::mul(q.s, A::sub(xv, xkb[j])));    // ITD.py:115-117
                 if (EDGE && t0 + jt == n - 1) bv = (CarryT)0;         // ITD.py:112
                 const CarryT rr = A::sub(xv, bv);
                 rot[r * 32] = (OutT)(LAST ? A::add(rr, bv) : rr);     // ITD.py:119 / :420
@@ -420,16 +404,16 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const Le
                 bleft = sm.carry_b[(i + 1) & 1];
             } else {
                 const CarryT xl = (CarryT)st.x[span0 - 1];
-                bleft = A::add(kL[0], A::mul(kS[0], A::sub(xl, xkb[0])));
+                const LS q = ls[0];
+                bleft = A::add(q.L, A::mul(q.s, A::sub(xl, xkb[0])));
             }
         }
         CarryT bright = (CarryT)0;
         if (have_right && (!EDGE || tend < n - 1)) {
             const int j = wcnt + fright;
-            bright = A::add(kL[j], A::mul(kS[j], A::sub(xright, xkb[j])));
+            const LS q = ls[j];
+            bright = A::add(q.L, A::mul(q.s, A::sub(xright, xkb[j])));
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty0 + 8 * s);                   // stage consumed by this warp
 
         // ---- D. extrema of B: next level's flag words -----------------------------------------
         unsigned fw[ITEMS];
@@ -453,6 +437,8 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const Le
         // ---- E/F/G. one block barrier, then compact the new knots ------------------------------
         compact_knots<WARPS, ITEMS, CarryT>(sm.cnt, i, warp, lane, newc, fw, b, t0 + span0, run_total, ntau, nxk,
                                             ntbase);
+        // every warp is past its reads of stage s: refill it with the tile STAGES ahead
+        if (tid == 0 && i + STAGES < tiles) issue_tile(i + STAGES);
     };
 
     for (int i = 0; i < tiles; ++i) {
@@ -487,44 +473,36 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) level_stream_kernel(const Le
 // pipeline, one CTA per signal.  Writes the same table/mask/tbase/endl as knot_scan_kernel.
 // ---------------------------------------------------------------------------------------------
 template <typename InT, typename CarryT, int WARPS, int ITEMS, int STAGES>
-__global__ void __launch_bounds__((WARPS + 1) * 32) scan_stream_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(WARPS * 32, 3) scan_stream_kernel(const ScanParams p) {
     using Smem = StreamSmem<InT, CarryT, WARPS, ITEMS, STAGES, false>;
     constexpr int T = Smem::T;
     constexpr int SPAN = Smem::SPAN;
     extern __shared__ __align__(128) unsigned char smem_stream_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_stream_raw);
-    const unsigned sbase = smem_u32(smem_stream_raw);
+    unsigned sbase = smem_u32(smem_stream_raw);
+    asm volatile("" : "+r"(sbase));
     const unsigned full0 = sbase + (unsigned)offsetof(Smem, full);
-    const unsigned empty0 = sbase + (unsigned)offsetof(Smem, empty);
 
     const int sig = blockIdx.x;
     const int n = p.n, tiles = p.tiles;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         sm.carry_b[0] = sm.carry_b[1] = (CarryT)0;
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, WARPS);
-        }
+        for (int s = 0; s < STAGES; ++s) mbar_init(full0 + 8 * s, 1);
         mbar_fence_init();
     }
     __syncthreads();
     const InT *x = reinterpret_cast<const InT *>(p.x) + (long long)sig * n;
-
-    if (warp == WARPS) {
-        if (lane == 0) {
-            for (int i = 0; i < tiles; ++i) {
-                const int s = i % STAGES;
-                mbar_wait_backoff(empty0 + 8 * s, ((i / STAGES) & 1) ^ 1);
-                const unsigned st = sbase + (unsigned)(offsetof(Smem, stage) + (size_t)s * sizeof(typename Smem::Stage));
-                const int t0 = i * T;
-                const unsigned bx = (unsigned)(min(T, n - t0) * sizeof(InT));
-                mbar_arrive_expect_tx(full0 + 8 * s, bx);
-                tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, x), x + t0, bx, full0 + 8 * s);
-            }
-        }
-        return;
-    }
+    auto issue_tile = [&](const int i) {
+        const int s = i % STAGES;
+        const unsigned st = sbase + (unsigned)(offsetof(Smem, stage) + (size_t)s * sizeof(typename Smem::Stage));
+        const int t0 = i * T;
+        const unsigned bx = (unsigned)(min(T, n - t0) * sizeof(InT));
+        mbar_arrive_expect_tx(full0 + 8 * s, bx);
+        tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, x), x + t0, bx, full0 + 8 * s);
+    };
+    if (tid == 0)
+        for (int i = 0; i < STAGES && i < tiles; ++i) issue_tile(i);
 
     const int span0 = warp * SPAN;
     int *ntau = p.out.tau + (long long)sig * p.out.kstride;
@@ -570,8 +548,6 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) scan_stream_kernel(const Sca
         }
         // x[n-1] opens a tile of its own: x[n-2] is the previous tile's last sample
         if (EDGE && t0 == n - 1 && warp == 0 && lane == 0) nendl[1] = mean2<CarryT>(vleft, v[0]);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty0 + 8 * s);
 
         unsigned fw[ITEMS];
         int newc = span_extrema<EDGE, ITEMS, CarryT>(v, vleft, vright, lane, t0 + span0, n, fw);
@@ -580,9 +556,8 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) scan_stream_kernel(const Sca
             newc = 0;
 #pragma unroll
             for (int r = 0; r < ITEMS; ++r) {
-                CarryT nx = __shfl_down_sync(0xffffffffu, v[r], 1);
-                const CarryT wrap = (r + 1 < ITEMS) ? shfl_idx(v[(r + 1 < ITEMS) ? r + 1 : r], 0) : vright;
-                if (lane == 31) nx = wrap;
+                const CarryT give = (lane == 0) ? ((r + 1 < ITEMS) ? v[(r + 1 < ITEMS) ? r + 1 : r] : vright) : v[r];
+                const CarryT nx = shfl_idx(give, (lane + 1) & 31);
                 const unsigned LT = __ballot_sync(0xffffffffu, v[r] < nx);   // rising after the sample = valley
                 fw[r] &= (p.kinds == 1) ? LT : ~LT;
                 newc += __popc(fw[r]);
@@ -613,6 +588,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) scan_stream_kernel(const Sca
         }
         compact_knots<WARPS, ITEMS, CarryT>(sm.cnt, i, warp, lane, newc, fw, v, t0 + span0, run_total, ntau, nxk,
                                             ntbase);
+        if (tid == 0 && i + STAGES < tiles) issue_tile(i + STAGES);
     };
 
     for (int i = 0; i < tiles; ++i) {
