@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--channels", type=int, default=CHANNELS_PER_GPU, help="channels per GPU")
     ap.add_argument("--samples", type=int, default=N_SAMPLES)
-    ap.add_argument("--e2e-channels", type=int, default=1024, help="channels per e2e step (host buffers)")
+    ap.add_argument("--e2e-channels", type=int, default=2048, help="channels per e2e step (host buffers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -325,10 +325,12 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         h2d = hx.numel() * 8
-        d2h = hrot.numel() * 8 + (hn.numel() + hc.numel() + hs.numel()) * 4
+        # only the rows each channel produced come back (rows beyond n_rows are unspecified by contract)
+        d2h = int(hn.long().sum()) * N * 8 + (hn.numel() + hc.numel() + hs.numel()) * 4
         e2e = {"value": world * Se * N * k_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "channels_per_step": Se, "steps": k_e2e,
-               "api": "pyitd_decompose_host (C ABI, pinned host buffers, all rotation rows copied back)"}
+               "api": "pyitd_decompose_host (C ABI, pinned host buffers; chunked H2D/kernel/D2H pipeline, "
+                      "every produced rotation row copied back)"}
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
     cpu = None

@@ -55,10 +55,16 @@ struct pyitd_plan {
     bool timing = false;
     cudaEvent_t *events = nullptr;
     int n_events = 0, events_used = 0;
-    // lazily allocated device mirrors for the _host entry point
-    void *h_x = nullptr, *h_rot = nullptr, *h_bas = nullptr;
-    int *h_ints = nullptr;    // n_rows | knot_counts | input_knots | stop_kind | status
-    cudaStream_t h_stream = nullptr;
+    // the _host entry point walks the batch in chunks through two slots (sub-plans with their own
+    // workspace, device mirrors and stream) so that H2D, the kernels and D2H of neighbouring chunks overlap
+    struct HostSlot {
+        pyitd_plan *sub = nullptr;
+        void *x = nullptr, *rot = nullptr, *bas = nullptr;
+        int *ints = nullptr;      // n_rows | knot_counts | input_knots | stop_kind | status
+        int *h_rows = nullptr;    // pinned host copy of n_rows (valid-rows-only D2H)
+        cudaStream_t stream = nullptr;
+    } slot[2];
+    long long host_chunk = 0;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -253,6 +259,15 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
         return fail(PYITD_E_INVALID, "n_signals * tiles exceeds the grid limit; split the batch");
     }
 
+    *out = pl;
+    return 0;
+}
+
+// the device workspace is allocated on the first device call: a plan that is only used through
+// pyitd_decompose_host never needs the full-batch workspace (its chunk sub-plans own theirs)
+static int ensure_workspace(pyitd_plan *pl) {
+    if (pl->ws) return 0;
+    CU(cudaSetDevice(pl->device));
     const size_t SN = (size_t)pl->S * (size_t)pl->n;
     const long long kstride = (((long long)pl->n + 3) & ~3ll) + 4;
     const long long mstride = ((((long long)pl->n + 31) / 32) + 3) & ~3ll;
@@ -270,7 +285,7 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
     cudaError_t ce = cudaMalloc(&pl->ws, total);
     if (ce != cudaSuccess) {
         cudaGetLastError();
-        delete pl;
+        pl->ws = nullptr;
         return fail(PYITD_E_NOMEM, "cudaMalloc of " + std::to_string(total) + " workspace bytes failed: " + cudaGetErrorString(ce));
     }
     char *c = (char *)pl->ws;
@@ -294,25 +309,28 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
     ce = cudaMemset(pl->desc, 0, b_desc);
     if (ce != cudaSuccess) {
         cudaFree(pl->ws);
-        delete pl;
+        pl->ws = nullptr;
         return fail(PYITD_E_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(ce));
     }
-    *out = pl;
     return 0;
 }
 
 extern "C" void pyitd_plan_destroy(pyitd_plan *pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);
-    if (pl->h_stream) cudaStreamDestroy(pl->h_stream);
+    for (auto &sl : pl->slot) {
+        if (sl.sub) pyitd_plan_destroy(sl.sub);
+        cudaFree(sl.x);
+        cudaFree(sl.rot);
+        cudaFree(sl.bas);
+        cudaFree(sl.ints);
+        if (sl.h_rows) cudaFreeHost(sl.h_rows);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
     if (pl->events) {
         for (int i = 0; i < pl->n_events; ++i) cudaEventDestroy(pl->events[i]);
         delete[] pl->events;
     }
-    cudaFree(pl->h_x);
-    cudaFree(pl->h_rot);
-    cudaFree(pl->h_bas);
-    cudaFree(pl->h_ints);
     cudaFree(pl->ws);
     delete pl;
 }
@@ -365,6 +383,7 @@ extern "C" int pyitd_decompose_device(pyitd_plan *pl, const void *x, void *rotat
     if (!(pl->opts & kOptBaselines)) baselines = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(pl->device));
+    if (int rc = ensure_workspace(pl)) return rc;
     pl->launches = 0;
     pl->events_used = 0;
     int *sk = stop_kind ? stop_kind : pl->stop_kind;
@@ -441,6 +460,7 @@ extern "C" int pyitd_extract_level_device(pyitd_plan *pl, const void *x, void *r
         return fail(PYITD_E_INVALID, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(pl->device));
+    if (int rc = ensure_workspace(pl)) return rc;
     pl->launches = 0;
     const size_t b_sig = (size_t)pl->S * sizeof(int);
     CU(cudaMemsetAsync(pl->stop_e, 0x7f, b_sig, st));
@@ -482,6 +502,7 @@ extern "C" int pyitd_find_knots_device(pyitd_plan *pl, const void *x, int kinds,
     if (kinds < 1 || kinds > 3) return fail(PYITD_E_INVALID, "kinds must be 1 (valleys), 2 (peaks) or 3 (both)");
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(pl->device));
+    if (int rc = ensure_workspace(pl)) return rc;
     pl->launches = 0;
     CU(cudaMemsetAsync(status, 0, (size_t)pl->S * sizeof(int), st));
     if (int rc = run_scan(pl, x, status, nullptr, st, kinds)) return rc;
@@ -501,8 +522,47 @@ extern "C" int pyitd_find_knots_device(pyitd_plan *pl, const void *x, int kinds,
 }
 
 // ---------------------------------------------------------------------------------------------
-// host-buffer entry point: H2D, decompose, D2H, synchronise
+// host-buffer entry point: the batch is walked in chunks through two slots so that the H2D copy of
+// chunk c+1 and its kernels overlap the D2H copy of chunk c (PCIe is the bottleneck of this call:
+// ~8 x rows bytes come back for every 8 bytes that go in).  Only the rows a signal actually
+// produced are copied back unless PYITD_OPT_ZERO_TAIL asks for the zero-filled tail.
 // ---------------------------------------------------------------------------------------------
+static long long pick_host_chunk(const pyitd_plan *pl) {
+    if (const char *env = getenv("PYITD_HOST_CHUNK")) {
+        long long v = atoll(env);
+        if (v >= 1) return v < pl->S ? v : pl->S;
+    }
+    // ~128 MiB of input per chunk, at least 256 signals when the batch has them (the one-CTA-per-
+    // signal kernels want a full GPU), and at least 4 chunks for the pipeline to overlap anything
+    long long c = (long long)((128ull << 20) / ((size_t)pl->n * pl->io_elem));
+    if (c < 256) c = 256;
+    if (c > pl->S / 4 && pl->S >= 1024) c = pl->S / 4;
+    if (c > pl->S) c = pl->S;
+    return c < 1 ? 1 : c;
+}
+
+static int ensure_host_slots(pyitd_plan *pl) {
+    if (pl->host_chunk) return 0;
+    const long long C = pick_host_chunk(pl);
+    const bool want_bas = (pl->opts & kOptBaselines) != 0;
+    const int nslots = (C < pl->S) ? 2 : 1;
+    for (int b = 0; b < nslots; ++b) {
+        auto &sl = pl->slot[b];
+        if (int rc = pyitd_plan_create(&sl.sub, pl->device, C, pl->n, pl->dtype, pl->max_iteration,
+                                       pl->min_extrema, (int)pl->opts))
+            return rc;
+        const size_t b_in = (size_t)C * pl->n * pl->io_elem, b_out = b_in * pl->rows;
+        CU(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        CU(cudaMalloc(&sl.x, b_in));
+        CU(cudaMalloc(&sl.rot, b_out));
+        if (want_bas) CU(cudaMalloc(&sl.bas, b_out));
+        CU(cudaMalloc((void **)&sl.ints, (4 + (size_t)pl->rows) * (size_t)C * sizeof(int)));
+        CU(cudaMallocHost((void **)&sl.h_rows, 2 * (size_t)C * sizeof(int)));
+    }
+    pl->host_chunk = C;
+    return 0;
+}
+
 extern "C" int pyitd_decompose_host(pyitd_plan *pl, const void *x, void *rotations, void *baselines,
                                     int32_t *n_rows, int32_t *knot_counts, int32_t *input_knots,
                                     int32_t *stop_kind, int32_t *status) {
@@ -511,28 +571,67 @@ extern "C" int pyitd_decompose_host(pyitd_plan *pl, const void *x, void *rotatio
     const bool want_bas = (pl->opts & kOptBaselines) != 0;
     if (want_bas && !baselines) return fail(PYITD_E_INVALID, "baselines is null");
     CU(cudaSetDevice(pl->device));
-    const size_t SN = (size_t)pl->S * pl->n;
-    const size_t b_in = SN * pl->io_elem, b_out = b_in * pl->rows;
-    const size_t S = (size_t)pl->S;
-    if (!pl->h_stream) CU(cudaStreamCreateWithFlags(&pl->h_stream, cudaStreamNonBlocking));
-    if (!pl->h_x) CU(cudaMalloc(&pl->h_x, b_in));
-    if (!pl->h_rot) CU(cudaMalloc(&pl->h_rot, b_out));
-    if (want_bas && !pl->h_bas) CU(cudaMalloc(&pl->h_bas, b_out));
-    if (!pl->h_ints) CU(cudaMalloc((void **)&pl->h_ints, (4 + (size_t)pl->rows) * S * sizeof(int)));
-    int *d_nrows = pl->h_ints, *d_counts = d_nrows + S, *d_ik = d_counts + S * pl->rows,
-        *d_kind = d_ik + S, *d_status = d_kind + S;
-    cudaStream_t st = pl->h_stream;
-    CU(cudaMemcpyAsync(pl->h_x, x, b_in, cudaMemcpyHostToDevice, st));
-    if (int rc = pyitd_decompose_device(pl, pl->h_x, pl->h_rot, want_bas ? pl->h_bas : nullptr, d_nrows,
-                                        d_counts, d_ik, d_kind, d_status, st))
-        return rc;
-    CU(cudaMemcpyAsync(rotations, pl->h_rot, b_out, cudaMemcpyDeviceToHost, st));
-    if (want_bas) CU(cudaMemcpyAsync(baselines, pl->h_bas, b_out, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(n_rows, d_nrows, S * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(knot_counts, d_counts, S * pl->rows * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (input_knots) CU(cudaMemcpyAsync(input_knots, d_ik, S * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (stop_kind) CU(cudaMemcpyAsync(stop_kind, d_kind, S * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(status, d_status, S * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    if (int rc = ensure_host_slots(pl)) return rc;
+    const long long C = pl->host_chunk;
+    const size_t row_b = (size_t)pl->n * pl->io_elem;          // bytes of one row
+    const size_t sig_out_b = row_b * pl->rows;                 // bytes of one signal's output block
+    const bool all_rows = (pl->opts & kOptZeroTail) != 0;
+    pl->launches = 0;
+    int nchunk = 0;
+    for (long long s0 = 0; s0 < pl->S; s0 += C, ++nchunk) {
+        auto &sl = pl->slot[nchunk & 1];
+        const long long cs = (pl->S - s0 < C) ? pl->S - s0 : C;
+        cudaStream_t st = sl.stream;
+        // the slot's previous chunk (two chunks ago) must have left the device buffers
+        CU(cudaStreamSynchronize(st));
+        int *d_nrows = sl.ints, *d_counts = d_nrows + C, *d_ik = d_counts + C * pl->rows, *d_kind = d_ik + C,
+            *d_status = d_kind + C;
+        CU(cudaMemcpyAsync(sl.x, (const char *)x + (size_t)s0 * row_b, (size_t)cs * row_b, cudaMemcpyHostToDevice, st));
+        // a short last chunk runs on the full-size sub-plan: the tail signals decompose stale data
+        // that is never copied back
+        if (int rc = pyitd_decompose_device(sl.sub, sl.x, sl.rot, want_bas ? sl.bas : nullptr, d_nrows, d_counts,
+                                            d_ik, d_kind, d_status, st))
+            return rc;
+        pl->launches += sl.sub->launches;
+        CU(cudaMemcpyAsync(sl.h_rows, d_nrows, (size_t)cs * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(sl.h_rows + C, d_kind, (size_t)cs * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(knot_counts + s0 * pl->rows, d_counts, (size_t)cs * pl->rows * sizeof(int),
+                           cudaMemcpyDeviceToHost, st));
+        if (input_knots) CU(cudaMemcpyAsync(input_knots + s0, d_ik, (size_t)cs * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(status + s0, d_status, (size_t)cs * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (all_rows) {
+            CU(cudaMemcpyAsync((char *)rotations + (size_t)s0 * sig_out_b, sl.rot, (size_t)cs * sig_out_b,
+                               cudaMemcpyDeviceToHost, st));
+            if (want_bas)
+                CU(cudaMemcpyAsync((char *)baselines + (size_t)s0 * sig_out_b, sl.bas, (size_t)cs * sig_out_b,
+                                   cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        } else {
+            // the kernels of this chunk are done once n_rows is on the host; the other slot's D2H
+            // keeps the copy engine busy while this thread waits here
+            CU(cudaStreamSynchronize(st));
+            for (long long s = 0; s < cs; ++s) {
+                int nr = sl.h_rows[s];
+                if (nr < 0) nr = 0;
+                if (nr > pl->rows) nr = pl->rows;
+                if (nr == 0) continue;
+                CU(cudaMemcpyAsync((char *)rotations + (size_t)(s0 + s) * sig_out_b, (const char *)sl.rot + (size_t)s * sig_out_b,
+                                   (size_t)nr * row_b, cudaMemcpyDeviceToHost, st));
+                if (want_bas) {
+                    // valid baseline rows: n_rows on the iteration stop, n_rows - 1 on the knot stop
+                    const int nb = (sl.h_rows[C + s] == kStopIter) ? nr : nr - 1;
+                    if (nb > 0)
+                        CU(cudaMemcpyAsync((char *)baselines + (size_t)(s0 + s) * sig_out_b,
+                                           (const char *)sl.bas + (size_t)s * sig_out_b, (size_t)nb * row_b,
+                                           cudaMemcpyDeviceToHost, st));
+                }
+            }
+        }
+        for (long long s = 0; s < cs; ++s) n_rows[s0 + s] = sl.h_rows[s];
+        if (stop_kind)
+            for (long long s = 0; s < cs; ++s) stop_kind[s0 + s] = sl.h_rows[C + s];
+    }
+    for (auto &sl : pl->slot)
+        if (sl.stream) CU(cudaStreamSynchronize(sl.stream));
     return 0;
 }

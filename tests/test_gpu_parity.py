@@ -246,6 +246,51 @@ def test_host_entry_point_matches_device_entry():
     assert torch.equal(a.n_rows, b.n_rows.cpu()) and torch.equal(a.status, b.status.cpu())
 
 
+@pytest.mark.parametrize("chunk,zero_tail", [(3, False), (3, True), (1, False), (8, False)])
+def test_host_entry_point_chunked_pipeline(chunk, zero_tail, monkeypatch):
+    """pyitd_decompose_host walks the batch in chunks through two device slots (H2D / kernels / D2H of
+    neighbouring chunks overlap) and copies back only the rows each signal produced."""
+    monkeypatch.setenv("PYITD_HOST_CHUNK", str(chunk))
+    pyitd_b200.clear_plan_cache()
+    try:
+        rng = np.random.default_rng(140 + chunk)
+        x = _mixed_batch(rng, 8, 5000)
+        for mi in (11, 2):
+            a = pyitd_b200.decompose(x, max_iteration=mi, return_baselines=True, zero_tail=zero_tail)
+            st = a.status.numpy()
+            for s in range(8):
+                try:
+                    want = o.c_decompose(x[s], mi)
+                except o.OracleError as e:
+                    assert st[s] & e.status
+                    continue
+                assert a.rows_of(s).numpy().tobytes() == want.rotations.tobytes(), (mi, s)
+                assert a.baselines_of(s).numpy().tobytes() == want.baselines.tobytes(), (mi, s)
+                assert int(a.stop_kind[s]) == want.stop_kind
+                if zero_tail:
+                    nr = int(a.n_rows[s])
+                    assert float(a.rotations[s, nr:].abs().sum()) == 0.0
+    finally:
+        pyitd_b200.clear_plan_cache()
+
+
+def test_sharded_driver_on_gpu():
+    """pyitd_b200.shard.decompose_sharded on one process (world 1): same driver code bench.py --gpus N runs."""
+    from pyitd_b200 import shard
+    rng = np.random.default_rng(150)
+    x = _mixed_batch(rng, 6, 3000)
+    res, summ = shard.decompose_sharded(lambda a, b: gpu(x[a:b]), 6, max_iteration=11, return_baselines=True)
+    torch.cuda.synchronize()
+    for s in range(6):
+        try:
+            want = o.c_decompose(x[s], 11)
+        except o.OracleError:
+            assert int(summ.status[s]) != 0
+            continue
+        assert res.rows_of(s).cpu().numpy().tobytes() == want.rotations.tobytes()
+    assert torch.equal(summ.n_rows, res.n_rows)
+
+
 def test_repeated_calls_reuse_the_plan_and_stay_exact():
     rng = np.random.default_rng(15)
     x = _mixed_batch(rng, 8, 6000)
