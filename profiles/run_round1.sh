@@ -1,6 +1,6 @@
 #!/bin/bash
-# GPU-box script: parity tests, the bench line, the ncu launch list and one full capture of the level kernel.
-# usage (from the repo root): gpurun --timeout 1500 -- bash profiles/run_round1.sh
+# GPU-box script: parity tests, the bench line, the ncu launch list and (optionally) one full capture.
+# usage (from the repo root): gpurun --timeout 1500 -- bash profiles/run_round1.sh [full]
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
@@ -8,8 +8,10 @@ tail -5 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 tail -c 600 gpurun_out/bench.err
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2>> gpurun_out/bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:pyitd -c 60 --csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:stream_kernel|level_kernel|scan_kernel|resident" -c 60 --csv \
     --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_under_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:level_stream_kernel -s 14 -c 3 \
+if [ "$1" = "full" ]; then
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:level_stream_kernel|resident" -s 14 -c 3 \
     -f -o gpurun_out/prof_level python bench.py --channels 1024 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1
+fi
 ls -la gpurun_out
