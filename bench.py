@@ -61,7 +61,7 @@ def workload_config(args, n_gpus):
         "workload": "configs[1]: batched 4096 x 65536-sample synthetic EEG-like channels, fp64, "
                     "knot-count stopping (max_iteration=11), per GPU",
         "channels_per_gpu": args.channels, "n_samples": args.samples, "max_iteration": MAX_ITERATION,
-        "generator": "pyitd_b200.synth.eeg_like(seed=1234+rank)", "parallelism": f"channel-shard x{n_gpus}, no collective",
+        "generator": "pyitd_b200.synth.eeg_like(seed=1234+rank)", "parallelism": f"channel-shard x{n_gpus}, no collective", "kernel_path": os.environ.get("PYITD_FORCE_PATH", "auto"),
         "l2": "inputs (2 GiB) and outputs (26 GiB) per step are larger than the 126 MB L2; no explicit flush",
     }
 
@@ -253,7 +253,7 @@ def main():
     ms_per_step = ms_total / args.steps
     value = world * S * N / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (level_kernel), per-launch CUDA events ------------------
+    # ---- roofline of the dominant kernel, per-launch CUDA events on the launching stream ----------
     plan.enable_timing(True)
     lvl_ms = None
     reps = 3
@@ -265,13 +265,8 @@ def main():
     lvl_ms = [v / reps for v in lvl_ms]
     nr = n_rows.long()
     active = [int((nr >= e + 1).sum()) for e in range(rows)]        # signals that execute extraction e
-    level_bytes = [a * N * 24 for a in active]                      # read X + write R + write B, fp64
-    # launch 0 is the knot scan, launches 1..rows are extractions 0..rows-1, the last is the fix-up
-    lv_times = lvl_ms[1:1 + rows]
-    n_lv = sum(1 for a in active if a > 0)
+    level_bytes = [a * N * 24 for a in active]                      # read X + write R + write B, fp64 (SURVEY 8d)
     alg_bytes = sum(level_bytes)
-    lv_time_ms = sum(tm for tm, a in zip(lv_times, active) if a > 0)
-    achieved = alg_bytes / (lv_time_ms * 1e-3) / 1e9
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -279,22 +274,49 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
+    path, cluster = plan.path
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "level_kernel_traffic.json"))).get("traffic_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"))).get("traffic_bytes_per_launch")
     except Exception:
         pass
-    roofline = {
-        "bound": "hbm", "kernel": "pyitd::level_kernel<double,double,double>",
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-        "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
-        "algorithmic_bytes_per_launch": alg_bytes / max(n_lv, 1),
-        "avg_launch_ms": lv_time_ms / max(n_lv, 1), "level_launches": n_lv,
-        "per_level": [{"e": e, "active_signals": a, "ms": round(tm, 4),
-                       "GBps": (round(b / (tm * 1e-3) / 1e9, 1) if a > 0 and tm > 0 else None)}
-                      for e, (a, tm, b) in enumerate(zip(active, lv_times, level_bytes))],
-        "knot_scan_ms": lvl_ms[0], "sample_levels_per_s": world * int(nr.sum()) * N / (ms_per_step * 1e-3),
-    }
+    sample_levels = int(nr.sum()) * N
+    if path == "resident":
+        # ONE launch decomposes the whole batch; the carry never leaves the SMs, so the bytes that MUST
+        # cross HBM are: x once + every produced row once
+        k_ms = lvl_ms[0]
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        compulsory = (S + int(nr.sum())) * N * 8
+        roofline = {
+            "bound": "hbm", "kernel": f"pyitd::resident_kernel<double,double,double> (cluster of {cluster} CTAs per signal)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
+            "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_ms, "level_launches": 1,
+            "algorithmic_bytes_definition": "24 B per sample per executed level (read X, write R, write B: SURVEY.md 8d, "
+                                            "an HBM-resident carry); this kernel keeps the carry on chip",
+            "compulsory_bytes_per_launch": compulsory,
+            "achieved_compulsory_GBps": compulsory / (k_ms * 1e-3) / 1e9,
+            "frac_compulsory": compulsory / (k_ms * 1e-3) / 1e9 / peak,
+            "active_signals_per_level": active,
+            "sample_levels_per_s": world * sample_levels / (ms_per_step * 1e-3),
+        }
+    else:
+        # launch 0 is the knot scan, launches 1..rows are extractions 0..rows-1, the last is the fix-up
+        lv_times = lvl_ms[1:1 + rows]
+        n_lv = sum(1 for a in active if a > 0)
+        lv_time_ms = sum(tm for tm, a in zip(lv_times, active) if a > 0)
+        achieved = alg_bytes / (lv_time_ms * 1e-3) / 1e9
+        roofline = {
+            "bound": "hbm", "kernel": f"pyitd::level_{'stream_' if path == 'stream' else ''}kernel<double,double,double>",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
+            "algorithmic_bytes_per_launch": alg_bytes / max(n_lv, 1),
+            "avg_launch_ms": lv_time_ms / max(n_lv, 1), "level_launches": n_lv,
+            "per_level": [{"e": e, "active_signals": a, "ms": round(tm, 4),
+                           "GBps": (round(b / (tm * 1e-3) / 1e9, 1) if a > 0 and tm > 0 else None)}
+                          for e, (a, tm, b) in enumerate(zip(active, lv_times, level_bytes))],
+            "knot_scan_ms": lvl_ms[0], "sample_levels_per_s": world * sample_levels / (ms_per_step * 1e-3),
+        }
 
     # ---- e2e: host buffers through the C ABI (pyitd_decompose_host) -------------------------------
     e2e = None

@@ -77,6 +77,14 @@ PYITD_API void pyitd_plan_destroy(pyitd_plan *plan);
 PYITD_API int     pyitd_plan_rows(const pyitd_plan *plan);             /* max_iteration + 2 */
 PYITD_API int64_t pyitd_plan_workspace_bytes(const pyitd_plan *plan);
 PYITD_API int     pyitd_plan_launches(const pyitd_plan *plan);         /* kernel launches of the last call */
+/* Which kernel family pyitd_decompose_* uses for this shape: PYITD_PATH_RESIDENT (signal kept on chip by a
+ * thread-block cluster, one launch per batch), PYITD_PATH_STREAM (one CTA per signal, carry in HBM) or
+ * PYITD_PATH_LOOKBACK (many CTAs per signal, carry in HBM: long single signals).  *cluster_size (may be NULL)
+ * receives the CTAs per cluster of the resident kernel, else 1. */
+#define PYITD_PATH_LOOKBACK 0
+#define PYITD_PATH_STREAM   1
+#define PYITD_PATH_RESIDENT 2
+PYITD_API int     pyitd_plan_path(const pyitd_plan *plan, int *cluster_size);
 
 /* Measurement aid: with timing enabled every kernel launch of pyitd_decompose_device is bracketed by
  * CUDA events on the launching stream; pyitd_plan_launch_times waits for the last one and returns the

@@ -70,6 +70,8 @@ def lib() -> ctypes.CDLL:
     L.pyitd_plan_workspace_bytes.argtypes = [vp]
     L.pyitd_plan_launches.restype = ci
     L.pyitd_plan_launches.argtypes = [vp]
+    L.pyitd_plan_path.restype = ci
+    L.pyitd_plan_path.argtypes = [vp, ctypes.POINTER(ci)]
     L.pyitd_plan_enable_timing.restype = ci
     L.pyitd_plan_enable_timing.argtypes = [vp, ci]
     L.pyitd_plan_launch_times.restype = ci
@@ -123,6 +125,13 @@ class Plan:
     @property
     def launches(self) -> int:
         return int(self._L.pyitd_plan_launches(self.handle))
+
+    @property
+    def path(self) -> tuple[str, int]:
+        """('resident' | 'stream' | 'lookback', CTAs per cluster)."""
+        cl = ctypes.c_int(1)
+        code = int(self._L.pyitd_plan_path(self.handle, ctypes.byref(cl)))
+        return {0: "lookback", 1: "stream", 2: "resident"}[code], int(cl.value)
 
     def enable_timing(self, on: bool = True) -> None:
         check(self._L.pyitd_plan_enable_timing(self.handle, int(on)), "pyitd_plan_enable_timing")

@@ -13,6 +13,7 @@
 
 #include "itd_kernels.cuh"
 #include "itd_stream.cuh"
+#include "itd_resident.cuh"
 
 using namespace pyitd;
 
@@ -41,6 +42,14 @@ struct pyitd_plan {
     int tile_cfg = 1;         // index into the (THREADS, ITEMS) table
     int tile = 1024, tiles = 0;
     bool stream = false;      // one-CTA-per-signal TMA-pipelined level kernel (itd_stream.cuh)
+    // whole-decomposition-on-chip kernel (itd_resident.cuh): one cluster per signal, one launch per batch
+    bool resident = false;
+    int res_cfg = 0;          // 0: 8 warps x 8 samples/lane, 1: 16 warps x 4 samples/lane
+    int res_cl = 1;           // CTAs per cluster
+    int res_nu = 0, res_chunk_units = 0, res_clusters = 0;
+    size_t res_smem = 0;
+    void *res_backup = nullptr;
+    int *res_kind = nullptr;
     size_t carry_elem = 8, io_elem = 8;
     // workspace
     void *ws = nullptr;
@@ -187,6 +196,98 @@ static cudaError_t launch_level(const pyitd_plan *pl, const LevelParams &p, bool
 }
 
 // ---------------------------------------------------------------------------------------------
+// resident kernel: configuration and launch
+// ---------------------------------------------------------------------------------------------
+constexpr size_t kMaxSmemOptin = 227 * 1024;
+
+template <typename InT, typename CarryT, typename OutT, int W, int SPL>
+static cudaError_t res_launch_t(const ResidentParams &p, int cl, int clusters, size_t smem, cudaStream_t st,
+                                int *max_clusters_out) {
+    auto k = resident_kernel<InT, CarryT, OutT, W, SPL>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(W * 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (max_clusters_out) {
+        cfg.gridDim = dim3((unsigned)cl, 1, 1);
+        int nc = 0;
+        e = cudaOccupancyMaxActiveClusters(&nc, k, &cfg);
+        if (e != cudaSuccess) return e;
+        *max_clusters_out = nc;
+        return cudaSuccess;
+    }
+    cfg.gridDim = dim3((unsigned)(clusters * cl), 1, 1);
+    return cudaLaunchKernelEx(&cfg, k, p);
+}
+
+template <int W, int SPL>
+static cudaError_t res_launch_d(int dtype, const ResidentParams &p, int cl, int clusters, size_t smem,
+                                cudaStream_t st, int *mc) {
+    switch (dtype) {
+        case PYITD_F64: return res_launch_t<double, double, double, W, SPL>(p, cl, clusters, smem, st, mc);
+        case PYITD_F32_MIXED: return res_launch_t<float, double, float, W, SPL>(p, cl, clusters, smem, st, mc);
+        default: return res_launch_t<float, float, float, W, SPL>(p, cl, clusters, smem, st, mc);
+    }
+}
+static cudaError_t res_launch(const pyitd_plan *pl, const ResidentParams &p, int clusters, cudaStream_t st, int *mc) {
+    if (pl->res_cfg == 0) return res_launch_d<8, 8>(pl->dtype, p, pl->res_cl, clusters, pl->res_smem, st, mc);
+    return res_launch_d<16, 4>(pl->dtype, p, pl->res_cl, clusters, pl->res_smem, st, mc);
+}
+
+// shared-memory layout of configuration (cfg, cl) for n samples; returns false when it does not fit
+static bool res_geometry(int cfg, int dtype, int n, int cl, ResidentParams &p, size_t &smem) {
+    const int W = cfg == 0 ? 8 : 16, SPL = cfg == 0 ? 8 : 4, UNIT = 32 * SPL;
+    if (cl - 1 + W > 32) return false;
+    const int nu = (n + UNIT - 1) / UNIT, gw = cl * W;
+    int chunk = 1;
+    for (int r = 0; r < cl; ++r) {
+        const int c = res_unit_begin((r + 1) * W, gw, nu) - res_unit_begin(r * W, gw, nu);
+        if (c > chunk) chunk = c;
+    }
+    p.nu = nu;
+    p.chunk_units = chunk;
+    if (dtype == PYITD_F32) {
+        if (cfg == 0) ResidentGeom<float, 8, 8>::layout(chunk, p, smem);
+        else ResidentGeom<float, 16, 4>::layout(chunk, p, smem);
+    } else {
+        if (cfg == 0) ResidentGeom<double, 8, 8>::layout(chunk, p, smem);
+        else ResidentGeom<double, 16, 4>::layout(chunk, p, smem);
+    }
+    return smem <= kMaxSmemOptin;
+}
+
+// picks the smallest cluster that holds the signal on chip; false when none does
+static bool res_configure(pyitd_plan *pl) {
+    int cfg = 0;
+    if (const char *env = getenv("PYITD_RES_CFG")) cfg = atoi(env) ? 1 : 0;
+    int force_cl = 0;
+    if (const char *env = getenv("PYITD_RES_CL")) force_cl = atoi(env);
+    for (int cl = 1; cl <= 8; cl *= 2) {
+        if (force_cl && cl != force_cl) continue;
+        ResidentParams p = {};
+        size_t smem = 0;
+        if (!res_geometry(cfg, pl->dtype, pl->n, cl, p, smem)) continue;
+        // a cluster wider than the signal has units would leave CTAs without work: still correct, but pointless
+        pl->res_cfg = cfg;
+        pl->res_cl = cl;
+        pl->res_nu = p.nu;
+        pl->res_chunk_units = p.chunk_units;
+        pl->res_smem = smem;
+        return true;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------------------------
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -251,6 +352,12 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
     }
     if (stream) cfg = 1;                       // both kernels must agree on the 1024-sample tile
     pl->stream = stream;
+    // signals that fit on chip (a cluster of up to 8 CTAs) are decomposed by ONE resident-kernel launch
+    {
+        bool want = true;
+        if (const char *env = getenv("PYITD_FORCE_PATH")) want = !strcmp(env, "resident");
+        pl->resident = want && res_configure(pl);
+    }
     pl->tile_cfg = cfg;
     pl->tile = kTileCfgs[cfg].threads * kTileCfgs[cfg].items;
     pl->tiles = (int)((n_samples + pl->tile - 1) / pl->tile);
@@ -331,6 +438,8 @@ extern "C" void pyitd_plan_destroy(pyitd_plan *pl) {
         for (int i = 0; i < pl->n_events; ++i) cudaEventDestroy(pl->events[i]);
         delete[] pl->events;
     }
+    cudaFree(pl->res_backup);
+    cudaFree(pl->res_kind);
     cudaFree(pl->ws);
     delete pl;
 }
@@ -338,6 +447,11 @@ extern "C" void pyitd_plan_destroy(pyitd_plan *pl) {
 extern "C" int pyitd_plan_rows(const pyitd_plan *pl) { return pl ? pl->rows : PYITD_E_INVALID; }
 extern "C" int64_t pyitd_plan_workspace_bytes(const pyitd_plan *pl) { return pl ? (int64_t)pl->ws_bytes : 0; }
 extern "C" int pyitd_plan_launches(const pyitd_plan *pl) { return pl ? pl->launches : 0; }
+extern "C" int pyitd_plan_path(const pyitd_plan *pl, int *cluster_size) {
+    if (!pl) return PYITD_E_INVALID;
+    if (cluster_size) *cluster_size = pl->resident ? pl->res_cl : 1;
+    return pl->resident ? PYITD_PATH_RESIDENT : (pl->stream ? PYITD_PATH_STREAM : PYITD_PATH_LOOKBACK);
+}
 
 // a fresh look-back tag for every launch; descriptors are only cleared when the 30-bit tag wraps
 static int next_tag(pyitd_plan *pl, cudaStream_t st, unsigned *tag) {
@@ -373,6 +487,61 @@ static int run_scan(pyitd_plan *pl, const void *x, int *status, int *input_knots
     return mark(pl, st);
 }
 
+static int run_resident(pyitd_plan *pl, const void *x, void *rotations, void *baselines, int32_t *n_rows,
+                        int32_t *knot_counts, int32_t *input_knots, int32_t *stop_kind, int32_t *status,
+                        cudaStream_t st) {
+    ResidentParams rp = {};
+    size_t smem = 0;
+    if (!res_geometry(pl->res_cfg, pl->dtype, pl->n, pl->res_cl, rp, smem))
+        return fail(PYITD_E_INVALID, "resident configuration no longer fits");
+    const int unit = pl->res_cfg == 0 ? 256 : 128;
+    if (!pl->res_clusters) {
+        int mc = 0;
+        CU(res_launch(pl, rp, 0, st, &mc));
+        if (mc < 1) return fail(PYITD_E_CUDA, "no resident cluster fits on this device");
+        if (const char *env = getenv("PYITD_RES_CLUSTERS")) {
+            const int v = atoi(env);
+            if (v >= 1 && v < mc) mc = v;
+        }
+        pl->res_clusters = (int)((long long)mc < pl->S ? mc : pl->S);
+        const size_t b_backup = (size_t)pl->res_clusters * rp.nu * unit * pl->carry_elem;
+        cudaError_t ce = cudaMalloc(&pl->res_backup, b_backup);
+        if (ce == cudaSuccess) ce = cudaMalloc((void **)&pl->res_kind, (size_t)pl->S * sizeof(int));
+        if (ce != cudaSuccess) {
+            cudaGetLastError();
+            pl->res_clusters = 0;
+            return fail(PYITD_E_NOMEM, std::string("resident scratch allocation failed: ") + cudaGetErrorString(ce));
+        }
+        pl->ws_bytes = b_backup + (size_t)pl->S * sizeof(int);
+    }
+    pl->launches = 0;
+    pl->events_used = 0;
+    const size_t b_sig = (size_t)pl->S * sizeof(int);
+    CU(cudaMemsetAsync(status, 0, b_sig, st));
+    CU(cudaMemsetAsync(knot_counts, 0, b_sig * pl->rows, st));
+    rp.x = x;
+    rp.rot = rotations;
+    rp.bas = baselines;
+    rp.backup = pl->res_backup;
+    rp.out_sig_stride = (long long)pl->rows * pl->n;
+    rp.backup_stride = (long long)rp.nu * unit;
+    rp.n_rows = n_rows;
+    rp.knot_counts = knot_counts;
+    rp.input_knots = input_knots;
+    rp.stop_kind = stop_kind ? stop_kind : pl->res_kind;
+    rp.status = status;
+    rp.S = pl->S;
+    rp.n = pl->n;
+    rp.emax = pl->emax;
+    rp.rows = pl->rows;
+    rp.min_extrema = pl->min_extrema;
+    rp.opts = pl->opts;
+    if (int rc = mark(pl, st)) return rc;
+    CU(res_launch(pl, rp, pl->res_clusters, st, nullptr));
+    pl->launches = 1;
+    return mark(pl, st);
+}
+
 extern "C" int pyitd_decompose_device(pyitd_plan *pl, const void *x, void *rotations, void *baselines,
                                       int32_t *n_rows, int32_t *knot_counts, int32_t *input_knots,
                                       int32_t *stop_kind, int32_t *status, void *stream) {
@@ -383,6 +552,8 @@ extern "C" int pyitd_decompose_device(pyitd_plan *pl, const void *x, void *rotat
     if (!(pl->opts & kOptBaselines)) baselines = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(pl->device));
+    if (pl->resident)
+        return run_resident(pl, x, rotations, baselines, n_rows, knot_counts, input_knots, stop_kind, status, st);
     if (int rc = ensure_workspace(pl)) return rc;
     pl->launches = 0;
     pl->events_used = 0;

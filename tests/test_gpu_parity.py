@@ -157,6 +157,7 @@ def _mixed_batch(rng, S, n):
 @pytest.mark.parametrize("cfg", [0, 1, 2, 3])
 def test_tile_boundaries_all_configs(cfg, monkeypatch):
     monkeypatch.setenv("PYITD_TILE_CFG", str(cfg))
+    monkeypatch.setenv("PYITD_FORCE_PATH", "lookback")
     pyitd_b200.clear_plan_cache()
     rng = np.random.default_rng(100 + cfg)
     T = (512, 1024, 2048, 2048)[cfg]
@@ -192,6 +193,88 @@ def test_both_level_kernels_agree_with_oracle(path, monkeypatch):
                 assert res.rows_of(s).cpu().numpy().tobytes() == want.rotations.astype(np.float32).tobytes(), (dt, s)
     finally:
         pyitd_b200.clear_plan_cache()
+
+
+RES_SIZES = (3, 4, 5, 31, 33, 127, 128, 129, 255, 256, 257, 258, 511, 513, 1023, 1024, 1025, 2047, 2049, 4096,
+             4097, 7777, 8192, 10004, 16385, 20000)
+
+
+@pytest.mark.parametrize("cfg", [0, 1])
+@pytest.mark.parametrize("cl", [0, 1, 2, 4, 8])
+def test_resident_kernel_cluster_shapes(cfg, cl, monkeypatch):
+    """The on-chip kernel (whole decomposition in one launch, signal resident in a cluster's shared memory)
+    for both warp configurations and every cluster size, over sizes around the unit (128/256 samples) and
+    the per-warp / per-CTA range boundaries.  A cluster wider than the signal leaves warps without samples."""
+    from pyitd_b200.itd import get_plan
+    monkeypatch.setenv("PYITD_FORCE_PATH", "resident")
+    monkeypatch.setenv("PYITD_RES_CFG", str(cfg))
+    if cl:
+        monkeypatch.setenv("PYITD_RES_CL", str(cl))
+    pyitd_b200.clear_plan_cache()
+    rng = np.random.default_rng(500 + 10 * cfg + cl)
+    try:
+        used = 0
+        for n in RES_SIZES:
+            plan = get_plan(0, 7, n, _capi.F64, 11, 2, _capi.OPT_BASELINES)
+            path, csize = plan.path
+            if path != "resident":
+                continue                                  # this cluster size cannot hold n samples on chip
+            assert cl == 0 or csize == cl
+            used += 1
+            check_against_oracle(_mixed_batch(rng, 7, n), max_iteration=11)
+        assert used >= 10, used
+    finally:
+        pyitd_b200.clear_plan_cache()
+
+
+@pytest.mark.parametrize("cfg", [0, 1])
+def test_resident_kernel_many_signals_per_cluster(cfg, monkeypatch):
+    """More signals than resident clusters: every cluster walks several signals (buffer parity, halo
+    values and backup area are reused across signals)."""
+    monkeypatch.setenv("PYITD_FORCE_PATH", "resident")
+    monkeypatch.setenv("PYITD_RES_CFG", str(cfg))
+    monkeypatch.setenv("PYITD_RES_CLUSTERS", "3")
+    pyitd_b200.clear_plan_cache()
+    rng = np.random.default_rng(520 + cfg)
+    try:
+        for n, mi in ((700, 11), (4100, 3), (9000, 0)):
+            check_against_oracle(_mixed_batch(rng, 23, n), max_iteration=mi)
+            check_against_oracle(_mixed_batch(rng, 23, n), max_iteration=mi, zero_tail=True)
+    finally:
+        pyitd_b200.clear_plan_cache()
+
+
+@pytest.mark.parametrize("cfg", [0, 1])
+def test_resident_kernel_fp32_variants(cfg, monkeypatch):
+    monkeypatch.setenv("PYITD_FORCE_PATH", "resident")
+    monkeypatch.setenv("PYITD_RES_CFG", str(cfg))
+    pyitd_b200.clear_plan_cache()
+    rng = np.random.default_rng(540 + cfg)
+    try:
+        for n in (5, 130, 1000, 8192, 8195, 30000):
+            x32 = _mixed_batch(rng, 6, n).astype(np.float32)
+            for dt in ("f32_mixed", "f32"):
+                res = pyitd_b200.decompose(gpu(x32), max_iteration=7, dtype=dt, return_baselines=True)
+                for s in range(6):
+                    src = x32[s].astype(np.float64) if dt == "f32_mixed" else x32[s]
+                    try:
+                        want = o.c_decompose(src, 7)
+                    except o.OracleError:
+                        assert int(res.status[s]) != 0
+                        continue
+                    assert int(res.status[s]) == 0
+                    assert res.rows_of(s).cpu().numpy().tobytes() == want.rotations.astype(np.float32).tobytes(), (dt, n, s)
+                    assert res.baselines_of(s).cpu().numpy().tobytes() == want.baselines.astype(np.float32).tobytes(), (dt, n, s)
+    finally:
+        pyitd_b200.clear_plan_cache()
+
+
+def test_resident_is_the_default_for_on_chip_sizes():
+    from pyitd_b200.itd import get_plan
+    assert get_plan(0, 64, 65536, _capi.F64, 11, 2, 0).path == ("resident", 4)
+    assert get_plan(0, 64, 8192, _capi.F32_MIXED, 7, 2, 0).path[0] == "resident"
+    assert get_plan(0, 1, 1 << 22, _capi.F32, 11, 2, 0).path[0] == "lookback"
+    pyitd_b200.clear_plan_cache()
 
 
 @pytest.mark.parametrize("max_iteration", [0, 1, 3, 7, 20])
