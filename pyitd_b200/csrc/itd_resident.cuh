@@ -34,6 +34,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "itd_kernels.cuh"
 
 namespace pyitd {
@@ -83,12 +85,20 @@ struct alignas(2 * sizeof(CarryT)) KnotLS {
     CarryT L, s;
 };
 
+// the resolved neighbourhood of a warp's range: two knots before (nearest first), three after
+template <typename CarryT>
+struct alignas(16) HaloKnots {
+    int bt[2], at[3], pad_[3];
+    CarryT bx[2], ax[3], padv_[1];
+};
+
 template <typename CarryT, int WARPS, int SPL>
 struct ResidentGeom {
     static constexpr int UNIT = 32 * SPL;
     static constexpr int CAP = UNIT + 8;                       // knot-table capacity per warp
-    static constexpr size_t tab_bytes_per_warp =
+    static constexpr size_t tab_core_bytes =
         ((size_t)CAP * (sizeof(int) + sizeof(CarryT) + sizeof(KnotLS<CarryT>)) + 15) & ~(size_t)15;
+    static constexpr size_t tab_bytes_per_warp = tab_core_bytes + sizeof(HaloKnots<CarryT>);
     // byte offsets for a CTA holding chunk_units units
     static void layout(int chunk_units, ResidentParams &p, size_t &total) {
         size_t o = (size_t)chunk_units * UNIT * sizeof(CarryT);
@@ -109,32 +119,51 @@ struct ResidentGeom {
 };
 
 // ---------------------------------------------------------------------------------------------
+// comparison bits.  cmp_bits ORs `mask` into lt when a < b and into gt when a > b (IEEE compare:
+// -0 == +0, exactly what numpy's `>` / `<=` on the differences do in ITD.py:59).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cmp_bits(double a, double b, unsigned mask, unsigned &lt, unsigned &gt) {
+    asm("{\n\t.reg .pred p, q;\n\t"
+        "setp.lt.f64 p, %2, %3;\n\t"
+        "setp.gt.f64 q, %2, %3;\n\t"
+        "@p or.b32 %0, %0, %4;\n\t"
+        "@q or.b32 %1, %1, %4;\n\t}"
+        : "+r"(lt), "+r"(gt)
+        : "d"(a), "d"(b), "r"(mask));
+}
+__device__ __forceinline__ void cmp_bits(float a, float b, unsigned mask, unsigned &lt, unsigned &gt) {
+    asm("{\n\t.reg .pred p, q;\n\t"
+        "setp.lt.f32 p, %2, %3;\n\t"
+        "setp.gt.f32 q, %2, %3;\n\t"
+        "@p or.b32 %0, %0, %4;\n\t"
+        "@q or.b32 %1, %1, %4;\n\t}"
+        : "+r"(lt), "+r"(gt)
+        : "f"(a), "f"(b), "r"(mask));
+}
+
 // per-lane knot flags of SPL consecutive values.  lt/gt bit j = comparison of sample j-1 with sample j
 // (j = 0 compares the left neighbour vl).  The flag of the lane's last sample needs the next lane's
 // first comparison (one shuffle); lane 31's last flag is left to the caller (deferred to the next unit).
-// ---------------------------------------------------------------------------------------------
 template <int SPL, typename CarryT>
 __device__ __forceinline__ unsigned lane_flags(const CarryT (&v)[SPL], CarryT vl, int lane, unsigned &pk_first,
                                                unsigned &pk_last) {
-    unsigned lt = (vl < v[0]) ? 1u : 0u, gt = (vl > v[0]) ? 1u : 0u;
+    unsigned lt = 0u, gt = 0u;
+    cmp_bits(vl, v[0], 1u, lt, gt);
 #pragma unroll
-    for (int j = 1; j < SPL; ++j) {
-        lt |= (v[j - 1] < v[j]) ? (1u << j) : 0u;
-        gt |= (v[j - 1] > v[j]) ? (1u << j) : 0u;
-    }
+    for (int j = 1; j < SPL; ++j) cmp_bits(v[j - 1], v[j], 1u << j, lt, gt);
     pk_first = (lt & 1u) | ((gt & 1u) << 1);
     pk_last = ((lt >> (SPL - 1)) & 1u) | (((gt >> (SPL - 1)) & 1u) << 1);
     const unsigned nx = __shfl_down_sync(0xffffffffu, pk_first, 1);
     const unsigned lte = lt | ((nx & 1u) << SPL), gte = gt | ((nx >> 1) << SPL);
     // valley: !(x[t-1] < x[t]) && x[t] < x[t+1];  peak: !(x[t-1] > x[t]) && x[t] > x[t+1]   (ITD.py:59 on x and -x)
     unsigned f = ((~lt) & (lte >> 1)) | ((~gt) & (gte >> 1));
-    f &= (1u << SPL) - 1u;
-    if (lane == 31) f &= (1u << (SPL - 1)) - 1u;
+    f &= (lane == 31) ? ((1u << (SPL - 1)) - 1u) : ((1u << SPL) - 1u);
     return f;
 }
 __device__ __forceinline__ unsigned flag_from_pk(unsigned pk_left, unsigned pk_right) {
     // pk = (lt | gt << 1) of (t-1, t) resp. (t, t+1)
-    return ((~pk_left & pk_right) & 1u) | (((~pk_left & pk_right) >> 1) & 1u);
+    const unsigned m = ~pk_left & pk_right;
+    return (m | (m >> 1)) & 1u;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -147,12 +176,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) resident_kernel(const ResidentP
     using Summary = KnotSummary<CarryT>;
     using Misc = LevelMisc<CarryT>;
     using LS = KnotLS<CarryT>;
+    using Halo = HaloKnots<CarryT>;
+    using CVec = typename std::conditional<sizeof(CarryT) == 8, double2, float4>::type;
+    using OVec = typename std::conditional<sizeof(OutT) == 8, double2, float4>::type;
     constexpr int UNIT = G::UNIT, CAP = G::CAP;
     constexpr int EPC = 16 / (int)sizeof(CarryT);          // carry elements per 16-byte chunk
     constexpr int LCH = SPL / EPC;                         // chunks per lane per unit
+    constexpr int OPV = 16 / (int)sizeof(OutT);            // output elements per 16-byte store
     constexpr int LPW = 32 / SPL;                          // lanes per mask word
     constexpr unsigned FBM = (1u << SPL) - 1u;
-    static_assert(SPL >= 2 && SPL <= 16 && (SPL & (SPL - 1)) == 0, "SPL must be 2, 4, 8 or 16");
+    static_assert(SPL == 4 || SPL == 8, "SPL must be 4 or 8");
     static_assert(LCH >= 1 && LCH <= 4, "a lane owns 1..4 16-byte chunks of the carry per unit");
     constexpr unsigned FULL = 0xffffffffu;
 
@@ -177,6 +210,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) resident_kernel(const ResidentP
     LS *ls = reinterpret_cast<LS *>(tab);
     CarryT *XT = reinterpret_cast<CarryT *>(tab + (size_t)CAP * sizeof(LS));
     int *TAU = reinterpret_cast<int *>(tab + (size_t)CAP * (sizeof(LS) + sizeof(CarryT)));
+    Halo *hk = reinterpret_cast<Halo *>(tab + G::tab_core_bytes);
     Summary *WS = reinterpret_cast<Summary *>(smem_res + p.off_ws);       // [2][WARPS]
     Summary *CS = reinterpret_cast<Summary *>(smem_res + p.off_cs);       // [2]
     Misc *MISC = reinterpret_cast<Misc *>(smem_res + p.off_misc);         // [2], the copy in CTA 0 is the live one
@@ -190,6 +224,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) resident_kernel(const ResidentP
         const int c = trel / EPC;
         return ((c ^ ((c >> 3) & (LCH - 1))) * EPC) + (trel % EPC);
     };
+    // element offsets (inside a unit) of the lane's LCH chunks
+    int coff[LCH];
+#pragma unroll
+    for (int qc = 0; qc < LCH; ++qc) coff[qc] = (lane * LCH + (qc ^ xorv)) * EPC;
 
     int par = 0;                       // parity of the mask / summary buffers holding the CURRENT level's knots
     CarryT *bk = reinterpret_cast<CarryT *>(p.backup) + (long long)cid * p.backup_stride;
@@ -206,117 +244,120 @@ __global__ void __launch_bounds__(WARPS * 32, 1) resident_kernel(const ResidentP
         CarryT hxl = (CarryT)0, hxr = (CarryT)0;      // values of samples a-1 and b at the current level
 
         // =====================================================================================
-        // generic helpers (lambdas capture the per-signal state)
+        // helpers
         // =====================================================================================
-        // store the lane's flag bits of unit `cu` (chunk-relative) into mask buffer `q`
-        auto store_flags = [&](int q, int cu, unsigned f) {
+        // flag bits of the lane -> mask word of unit `cu` (chunk-relative) in buffer mkq
+        auto store_flags = [&](unsigned *mkq, int cu, unsigned f) {
             unsigned w = f << lsh;
 #pragma unroll
             for (int o = 1; o < LPW; o <<= 1) w |= __shfl_xor_sync(FULL, w, o);
-            if ((lane % LPW) == 0) Mk[q * mwords + cu * SPL + lw] = w;
+            if ((lane % LPW) == 0) mkq[cu * SPL + lw] = w;
+        };
+        // first three / last two set bits of my range in mask buffer mkq (global sample positions, -1 = none)
+        auto range_ends = [&](const unsigned *mkq, int &tF0, int &tF1, int &tF2, int &tL0, int &tL1) {
+            const int w0 = (u0 - cu0) * SPL, w1 = (u1 - cu0) * SPL;
+            int found = 0;
+            for (int wb = w0; wb < w1 && found < 3; wb += 32) {
+                const unsigned wd = (wb + lane < w1) ? mkq[wb + lane] : 0u;
+                unsigned nz = __ballot_sync(FULL, wd != 0u);
+                while (nz && found < 3) {
+                    const int fl = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    unsigned ww = __shfl_sync(FULL, wd, fl);
+                    while (ww && found < 3) {
+                        const int t = (cu0 * SPL + wb + fl) * 32 + (__ffs(ww) - 1);
+                        ww &= ww - 1;
+                        if (found == 0) tF0 = t; else if (found == 1) tF1 = t; else tF2 = t;
+                        ++found;
+                    }
+                }
+            }
+            found = 0;
+            for (int we = w1; we > w0 && found < 2; we -= 32) {
+                const int wi = we - 1 - lane;                       // lane 0 = highest word
+                const unsigned wd = (wi >= w0) ? mkq[wi] : 0u;
+                unsigned nz = __ballot_sync(FULL, wd != 0u);
+                while (nz && found < 2) {
+                    const int fl = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    unsigned ww = __shfl_sync(FULL, wd, fl);
+                    while (ww && found < 2) {
+                        const int hb = 31 - __clz(ww);
+                        const int t = (cu0 * SPL + we - 1 - fl) * 32 + hb;
+                        ww &= ~(1u << hb);
+                        if (found == 0) tL0 = t; else tL1 = t;
+                        ++found;
+                    }
+                }
+            }
         };
         // publish this warp's summary of mask buffer q: count + first three / last two knots with values
         auto publish = [&](int q, int cnt_total) {
             Summary *me = &WS[q * WARPS + warp];
             int tF0 = -1, tF1 = -1, tF2 = -1, tL0 = -1, tL1 = -1;
-            if (have) {
-                const int w0 = (u0 - cu0) * SPL, w1 = (u1 - cu0) * SPL;
-                const unsigned *mk = Mk + q * mwords;
-                int found = 0;
-                for (int wb = w0; wb < w1 && found < 3; wb += 32) {
-                    const unsigned wd = (wb + lane < w1) ? mk[wb + lane] : 0u;
-                    unsigned nz = __ballot_sync(FULL, wd != 0u);
-                    while (nz && found < 3) {
-                        const int fl = __ffs(nz) - 1;
-                        nz &= nz - 1;
-                        unsigned ww = __shfl_sync(FULL, wd, fl);
-                        while (ww && found < 3) {
-                            const int t = (cu0 * SPL + wb + fl) * 32 + (__ffs(ww) - 1);
-                            ww &= ww - 1;
-                            if (found == 0) tF0 = t; else if (found == 1) tF1 = t; else tF2 = t;
-                            ++found;
-                        }
-                    }
-                }
-                found = 0;
-                for (int we = w1; we > w0 && found < 2; we -= 32) {
-                    const int wi = we - 1 - lane;                       // lane 0 = highest word
-                    const unsigned wd = (wi >= w0) ? mk[wi] : 0u;
-                    unsigned nz = __ballot_sync(FULL, wd != 0u);
-                    while (nz && found < 2) {
-                        const int fl = __ffs(nz) - 1;
-                        nz &= nz - 1;
-                        unsigned ww = __shfl_sync(FULL, wd, fl);
-                        while (ww && found < 2) {
-                            const int hb = 31 - __clz(ww);
-                            const int t = (cu0 * SPL + we - 1 - fl) * 32 + hb;
-                            ww &= ~(1u << hb);
-                            if (found == 0) tL0 = t; else tL1 = t;
-                            ++found;
-                        }
-                    }
-                }
-            }
+            if (cnt_total > 0) range_ends(Mk + q * mwords, tF0, tF1, tF2, tL0, tL1);
             if (lane == 0) {
                 me->cnt = cnt_total;
-                me->tF[0] = tF0; me->tF[1] = tF1; me->tF[2] = tF2;
-                me->tL[0] = tL0; me->tL[1] = tL1;
-                me->xF[0] = tF0 >= 0 ? Xs[swz(tF0 - cu0 * UNIT)] : (CarryT)0;
-                me->xF[1] = tF1 >= 0 ? Xs[swz(tF1 - cu0 * UNIT)] : (CarryT)0;
-                me->xF[2] = tF2 >= 0 ? Xs[swz(tF2 - cu0 * UNIT)] : (CarryT)0;
-                me->xL[0] = tL0 >= 0 ? Xs[swz(tL0 - cu0 * UNIT)] : (CarryT)0;
-                me->xL[1] = tL1 >= 0 ? Xs[swz(tL1 - cu0 * UNIT)] : (CarryT)0;
+                if (cnt_total > 0) {
+                    me->tF[0] = tF0; me->tF[1] = tF1; me->tF[2] = tF2;
+                    me->tL[0] = tL0; me->tL[1] = tL1;
+                    me->xF[0] = Xs[swz(tF0 - cu0 * UNIT)];
+                    me->xL[0] = Xs[swz(tL0 - cu0 * UNIT)];
+                    if (tF1 >= 0) me->xF[1] = Xs[swz(tF1 - cu0 * UNIT)];
+                    if (tF2 >= 0) me->xF[2] = Xs[swz(tF2 - cu0 * UNIT)];
+                    if (tL1 >= 0) me->xL[1] = Xs[swz(tL1 - cu0 * UNIT)];
+                }
             }
         };
         // block barrier, CTA aggregate for the other CTAs, cluster barrier
         auto level_sync = [&](int q) {
-            __syncthreads();
-            if (warp == 0) {
-                const Summary *src = &WS[q * WARPS];
-                const int c = (lane < WARPS) ? src[lane].cnt : 0;
-                const int tot = __reduce_add_sync(FULL, c);
-                int tF0 = -1, tF1 = -1, tF2 = -1, tL0 = -1, tL1 = -1;
-                CarryT xF0 = 0, xF1 = 0, xF2 = 0, xL0 = 0, xL1 = 0;
-                unsigned m = __ballot_sync(FULL, c > 0);
-                int found = 0;
-                unsigned mm = m;
-                while (mm && found < 3) {
-                    const int j = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    const int cj = min(src[j].cnt, 3);
-                    for (int i = 0; i < cj && found < 3; ++i, ++found) {
-                        const int t = src[j].tF[i];
-                        const CarryT v = src[j].xF[i];
-                        if (found == 0) { tF0 = t; xF0 = v; } else if (found == 1) { tF1 = t; xF1 = v; } else { tF2 = t; xF2 = v; }
+            if (CL > 1) {
+                __syncthreads();
+                if (warp == 0) {
+                    const Summary *src = &WS[q * WARPS];
+                    const int c = (lane < WARPS) ? src[lane].cnt : 0;
+                    const int tot = __reduce_add_sync(FULL, c);
+                    int tF0 = -1, tF1 = -1, tF2 = -1, tL0 = -1, tL1 = -1;
+                    CarryT xF0 = 0, xF1 = 0, xF2 = 0, xL0 = 0, xL1 = 0;
+                    const unsigned m = __ballot_sync(FULL, c > 0);
+                    int found = 0;
+                    unsigned mm = m;
+                    while (mm && found < 3) {
+                        const int j = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        const int cj = min(src[j].cnt, 3);
+                        for (int i = 0; i < cj && found < 3; ++i, ++found) {
+                            const int t = src[j].tF[i];
+                            const CarryT v = src[j].xF[i];
+                            if (found == 0) { tF0 = t; xF0 = v; } else if (found == 1) { tF1 = t; xF1 = v; } else { tF2 = t; xF2 = v; }
+                        }
                     }
-                }
-                found = 0;
-                mm = m;
-                while (mm && found < 2) {
-                    const int j = 31 - __clz(mm);
-                    mm &= ~(1u << j);
-                    const int cj = min(src[j].cnt, 2);
-                    for (int i = 0; i < cj && found < 2; ++i, ++found) {
-                        const int t = src[j].tL[i];
-                        const CarryT v = src[j].xL[i];
-                        if (found == 0) { tL0 = t; xL0 = v; } else { tL1 = t; xL1 = v; }
+                    found = 0;
+                    mm = m;
+                    while (mm && found < 2) {
+                        const int j = 31 - __clz(mm);
+                        mm &= ~(1u << j);
+                        const int cj = min(src[j].cnt, 2);
+                        for (int i = 0; i < cj && found < 2; ++i, ++found) {
+                            const int t = src[j].tL[i];
+                            const CarryT v = src[j].xL[i];
+                            if (found == 0) { tL0 = t; xL0 = v; } else { tL1 = t; xL1 = v; }
+                        }
                     }
-                }
-                if (lane == 0) {
-                    Summary *d = &CS[q];
-                    d->cnt = tot;
-                    d->tF[0] = tF0; d->tF[1] = tF1; d->tF[2] = tF2; d->tL[0] = tL0; d->tL[1] = tL1;
-                    d->xF[0] = xF0; d->xF[1] = xF1; d->xF[2] = xF2; d->xL[0] = xL0; d->xL[1] = xL1;
+                    if (lane == 0) {
+                        Summary *d = &CS[q];
+                        d->cnt = tot;
+                        d->tF[0] = tF0; d->tF[1] = tF1; d->tF[2] = tF2; d->tL[0] = tL0; d->tL[1] = tL1;
+                        d->xF[0] = xF0; d->xF[1] = xF1; d->xF[2] = xF2; d->xL[0] = xL0; d->xL[1] = xL1;
+                    }
                 }
             }
             cluster.sync();
         };
 
-        // the resolved neighbourhood of this warp's range at the current level
+        // neighbourhood of this warp's range at the current level: scalars in registers, knots in hk
         int K = 0, kb = 0, mycnt = 0;
-        int bt0 = 0, bt1 = 0, at0 = 0, at1 = 0, at2 = 0;       // knot positions before (nearest first) / after
-        CarryT bx0 = 0, bx1 = 0, ax0 = 0, ax1 = 0, ax2 = 0;
-        CarryT endl0 = 0, endl1 = 0, x0v = 0, xlastv = 0;
+        CarryT endl0 = 0, endl1 = 0;
         auto resolve = [&](int q) {
             // entry list in sample order: CTAs before mine (aggregates), my CTA's warps, CTAs after mine
             const int ne = CL - 1 + WARPS, me = rank + warp;
@@ -324,15 +365,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) resident_kernel(const ResidentP
             if (lane < rank) e = cluster.map_shared_rank(&CS[q], lane);
             else if (lane < rank + WARPS) e = &WS[q * WARPS + (lane - rank)];
             else if (lane < ne) e = cluster.map_shared_rank(&CS[q], lane - WARPS + 1);
-            int c = 0, tF0 = 0, tF1 = 0, tF2 = 0, tL0 = 0, tL1 = 0;
+            const int c = e ? e->cnt : 0;
+            int tF0 = 0, tF1 = 0, tF2 = 0, tL0 = 0, tL1 = 0;
             CarryT xF0 = 0, xF1 = 0, xF2 = 0, xL0 = 0, xL1 = 0;
-            if (e) {
-                c = e->cnt;
+            if (c > 0) {
                 tF0 = e->tF[0]; tF1 = e->tF[1]; tF2 = e->tF[2]; tL0 = e->tL[0]; tL1 = e->tL[1];
                 xF0 = e->xF[0]; xF1 = e->xF[1]; xF2 = e->xF[2]; xL0 = e->xL[0]; xL1 = e->xL[1];
             }
             const Misc mi = MISC0[q];
-            endl0 = mi.endl0; endl1 = mi.endl1; x0v = mi.x0; xlastv = mi.xlast;
+            endl0 = mi.endl0; endl1 = mi.endl1;
+            const CarryT x0v = mi.x0, xlastv = mi.xlast;
             K = __reduce_add_sync(FULL, c);
             kb = __reduce_add_sync(FULL, (lane < me) ? c : 0);
             mycnt = __shfl_sync(FULL, c, me);
@@ -340,8 +382,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) resident_kernel(const ResidentP
             // two nearest real knots before the range
             int nb = 0;
             unsigned m = nzm & ((1u << me) - 1u);
-            int rt[2] = {0, 0};
-            CarryT rx[2] = {(CarryT)0, (CarryT)0};
+            int rt0 = 0, rt1 = 0;
+            CarryT rx0 = 0, rx1 = 0;
 #pragma unroll
             for (int it = 0; it < 2; ++it) {
                 if (m && nb < 2) {
@@ -350,19 +392,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) resident_kernel(const ResidentP
                     const int cj = __shfl_sync(FULL, c, j);
                     const int t0_ = __shfl_sync(FULL, tL0, j), t1_ = __shfl_sync(FULL, tL1, j);
                     const CarryT v0_ = __shfl_sync(FULL, xL0, j), v1_ = __shfl_sync(FULL, xL1, j);
-                    if (nb == 0) { rt[0] = t0_; rx[0] = v0_; } else { rt[1] = t0_; rx[1] = v0_; }
+                    if (nb == 0) { rt0 = t0_; rx0 = v0_; } else { rt1 = t0_; rx1 = v0_; }
                     ++nb;
-                    if (nb < 2 && cj >= 2) { rt[1] = t1_; rx[1] = v1_; ++nb; }
+                    if (nb < 2 && cj >= 2) { rt1 = t1_; rx1 = v1_; ++nb; }
                 }
             }
-            // knot kb (nearest before) and kb-1: real, or the virtual start knot (tau 0, x[0]), or nothing
-            if (kb >= 1) { bt0 = rt[0]; bx0 = rx[0]; } else { bt0 = 0; bx0 = x0v; }
-            if (kb >= 2) { bt1 = rt[1]; bx1 = rx[1]; } else { bt1 = 0; bx1 = x0v; }
             // three nearest real knots after the range
             int na = 0;
             m = (me >= 31) ? 0u : (nzm & ~((2u << me) - 1u));
-            int qt[3] = {0, 0, 0};
-            CarryT qx[3] = {(CarryT)0, (CarryT)0, (CarryT)0};
+            int qt0 = 0, qt1 = 0, qt2 = 0;
+            CarryT qx0 = 0, qx1 = 0, qx2 = 0;
 #pragma unroll
             for (int it = 0; it < 3; ++it) {
                 if (m && na < 3) {
@@ -376,26 +415,75 @@ __global__ void __launch_bounds__(WARPS * 32, 1) resident_kernel(const ResidentP
                         if (i < cj && na < 3) {
                             const int t = (i == 0) ? t0_ : (i == 1) ? t1_ : t2_;
                             const CarryT v = (i == 0) ? v0_ : (i == 1) ? v1_ : v2_;
-                            if (na == 0) { qt[0] = t; qx[0] = v; } else if (na == 1) { qt[1] = t; qx[1] = v; } else { qt[2] = t; qx[2] = v; }
+                            if (na == 0) { qt0 = t; qx0 = v; } else if (na == 1) { qt1 = t; qx1 = v; } else { qt2 = t; qx2 = v; }
                             ++na;
                         }
                     }
                 }
             }
-            // knots ka+1.. with ka = kb + mycnt: real while <= K, then the virtual end knot (tau n-1, x[n-1])
-            const int ka = kb + mycnt;
-            at0 = (ka + 1 <= K) ? qt[0] : n - 1; ax0 = (ka + 1 <= K) ? qx[0] : xlastv;
-            at1 = (ka + 2 <= K) ? qt[1] : n - 1; ax1 = (ka + 2 <= K) ? qx[1] : xlastv;
-            at2 = (ka + 3 <= K) ? qt[2] : n - 1; ax2 = (ka + 3 <= K) ? qx[2] : xlastv;
+            if (lane == 0) {
+                // knot kb (nearest before) and kb-1: real, or the virtual start knot (tau 0, x[0]), or unused
+                hk->bt[0] = (kb >= 1) ? rt0 : 0; hk->bx[0] = (kb >= 1) ? rx0 : x0v;
+                hk->bt[1] = (kb >= 2) ? rt1 : 0; hk->bx[1] = (kb >= 2) ? rx1 : x0v;
+                // knots ka+1.. (ka = kb + mycnt): real while <= K, then the virtual end knot (tau n-1, x[n-1])
+                const int ka = kb + mycnt;
+                hk->at[0] = (ka + 1 <= K) ? qt0 : n - 1; hk->ax[0] = (ka + 1 <= K) ? qx0 : xlastv;
+                hk->at[1] = (ka + 2 <= K) ? qt1 : n - 1; hk->ax[1] = (ka + 2 <= K) ? qx1 : xlastv;
+                hk->at[2] = (ka + 3 <= K) ? qt2 : n - 1; hk->ax[2] = (ka + 3 <= K) ? qx2 : xlastv;
+            }
+            __syncwarp();
+        };
+
+        // per-warp streaming state of a pass over the range
+        int cnt_lane = 0;
+        unsigned pend = 0;             // pk_last of lane 31 of the previous unit
+        CarryT vlast = (CarryT)0;      // value of the previous unit's last sample
+        // flags of one unit from its values (in registers) -> mask buffer mkq; counts into cnt_lane
+        auto emit_flags = [&](auto edge_c, const CarryT (&v)[SPL], unsigned *mkq, int uu) {
+            constexpr bool EDGE = decltype(edge_c)::value;
+            const int cu = uu - cu0, t0 = uu * UNIT;
+            CarryT vl = __shfl_up_sync(FULL, v[SPL - 1], 1);
+            if (lane == 0) vl = vlast;
+            unsigned pkf, pkl;
+            unsigned f = lane_flags<SPL, CarryT>(v, vl, lane, pkf, pkl);
+            if (EDGE) {
+                const int tl = t0 + lane * SPL;
+                const int lo = max(0, 1 - tl), hi = n - 2 - tl;            // valid bits [lo, hi]
+                unsigned vm = (hi < 0) ? 0u : ((hi >= 31) ? FULL : ((2u << hi) - 1u));
+                vm &= (lo >= 32) ? 0u : (FULL << lo);
+                f &= vm;
+            }
+            // deferred flag of the previous unit's last sample (position t0 - 1, inside this range)
+            const unsigned pk0 = __shfl_sync(FULL, pkf, 0);
+            if (uu > u0 && flag_from_pk(pend, pk0) && (!EDGE || (t0 - 1 >= 1 && t0 - 1 <= n - 2))) {
+                if (lane == 0) {
+                    mkq[(cu - 1) * SPL + SPL - 1] |= 0x80000000u;
+                    ++cnt_lane;
+                }
+            }
+            pend = __shfl_sync(FULL, pkl, 31);
+            vlast = __shfl_sync(FULL, v[SPL - 1], 31);
+            cnt_lane += __popc(f);
+            store_flags(mkq, cu, f);
+            __syncwarp();
+        };
+        // the range's very last sample: its right neighbour (value hr) lives in the next warp's range
+        auto close_range = [&](unsigned *mkq, CarryT hr) {
+            if (have && b < n && lane == 0) {
+                const unsigned pkr = (vlast < hr ? 1u : 0u) | (vlast > hr ? 2u : 0u);
+                if (b - 1 >= 1 && b - 1 <= n - 2 && flag_from_pk(pend, pkr)) {
+                    mkq[(u1 - 1 - cu0) * SPL + SPL - 1] |= 0x80000000u;
+                    ++cnt_lane;
+                }
+            }
+            __syncwarp();
         };
 
         // =====================================================================================
         // 0. load the chunk, detect the extrema of the input (ITD.py:87-98) -> mask[par]
         // =====================================================================================
         {
-            int cnt_lane = 0;
-            unsigned pend = 0;             // pk_last of lane 31 of the previous unit
-            CarryT vlast = (CarryT)0;      // value of the previous unit's last sample
+            unsigned *mkq = Mk + par * mwords;
             if (have) {
                 if (a > 0) hxl = (CarryT)__ldg(x + a - 1);
                 if (b < n) hxr = (CarryT)__ldg(x + b);
@@ -424,46 +512,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) resident_kernel(const ResidentP
 #pragma unroll
                 for (int j = 0; j < SPL; ++j) bad |= !isfinite(v[j]);
                 // carry <- x (swizzled 16-byte chunks)
-                {
-                    const int cbase = (cu * UNIT + lane * SPL) / EPC;
+                CarryT *xu = Xs + (size_t)cu * UNIT;
 #pragma unroll
-                    for (int qc = 0; qc < LCH; ++qc) {
-                        CarryT *dst = Xs + (size_t)(cbase + (qc ^ xorv)) * EPC;
-#pragma unroll
-                        for (int i = 0; i < EPC; ++i) dst[i] = v[qc * EPC + i];
-                    }
+                for (int qc = 0; qc < LCH; ++qc) {
+                    CVec o;
+                    if constexpr (sizeof(CarryT) == 8) { o.x = v[qc * 2]; o.y = v[qc * 2 + 1]; }
+                    else { o.x = v[qc * 4]; o.y = v[qc * 4 + 1]; o.z = v[qc * 4 + 2]; o.w = v[qc * 4 + 3]; }
+                    *reinterpret_cast<CVec *>(xu + coff[qc]) = o;
                 }
-                CarryT vl = __shfl_up_sync(FULL, v[SPL - 1], 1);
-                if (lane == 0) vl = vlast;
-                unsigned pkf, pkl;
-                unsigned f = lane_flags<SPL, CarryT>(v, vl, lane, pkf, pkl);
-                if (edge) {
-                    const int lo = max(0, 1 - tl), hi = n - 2 - tl;        // valid bits [lo, hi]
-                    unsigned vm = (hi < 0) ? 0u : ((hi >= 31) ? FULL : ((2u << hi) - 1u));
-                    vm &= (lo >= 32) ? 0u : (FULL << lo);
-                    f &= vm;
-                }
-                // deferred flag of the previous unit's last sample (position t0 - 1, inside this range)
-                const unsigned pk0 = __shfl_sync(FULL, pkf, 0);
-                if (u > u0 && lane == 0 && t0 - 1 >= 1 && t0 - 1 <= n - 2 && flag_from_pk(pend, pk0)) {
-                    Mk[par * mwords + (cu - 1) * SPL + SPL - 1] |= 0x80000000u;
-                    ++cnt_lane;
-                }
-                pend = __shfl_sync(FULL, pkl, 31);
-                vlast = __shfl_sync(FULL, v[SPL - 1], 31);
-                cnt_lane += __popc(f);
-                store_flags(par, cu, f);
-                __syncwarp();
+                if (edge) emit_flags(std::true_type{}, v, mkq, u);
+                else emit_flags(std::false_type{}, v, mkq, u);
             }
-            // the range's very last sample: its right neighbour lives in the next warp's range
-            if (have && b < n && lane == 0) {
-                const unsigned pkr = (vlast < hxr ? 1u : 0u) | (vlast > hxr ? 2u : 0u);
-                if (b - 1 >= 1 && b - 1 <= n - 2 && flag_from_pk(pend, pkr)) {
-                    Mk[par * mwords + (u1 - 1 - cu0) * SPL + SPL - 1] |= 0x80000000u;
-                    ++cnt_lane;
-                }
-            }
-            __syncwarp();
+            close_range(mkq, hxr);
             const int cnt_total = __reduce_add_sync(FULL, cnt_lane);
             publish(par, cnt_total);
             if (g == 0 && lane == 0) {
@@ -490,23 +550,132 @@ __global__ void __launch_bounds__(WARPS * 32, 1) resident_kernel(const ResidentP
             const int qn = par ^ 1;                        // buffers of the NEXT level
             OutT *rrow = rot + (long long)e * n;
             OutT *brow = bas ? bas + (long long)e * n : nullptr;
-            int cnt_lane = 0;
-            unsigned pend = 0;
-            CarryT vlast = (CarryT)0;
+            const bool gen = last || brow != nullptr || !out_vec;
+            cnt_lane = 0;
+            pend = 0;
+            vlast = (CarryT)0;
             CarryT hbl = (CarryT)0, hbr = (CarryT)0;       // B at samples a-1 and b (next level's halo values)
             // knots kb-1 (p2) and kb (p1) relative to the current run start
-            int p1t = bt0, p2t = bt1;
-            CarryT p1x = bx0, p2x = bx1;
+            int p1t = hk->bt[0], p2t = hk->bt[1];
+            CarryT p1x = hk->bx[0], p2x = hk->bx[1];
             int krun = kb;                                 // global index of knot p1
             const unsigned *mk = Mk + par * mwords;
+            unsigned *mkn = Mk + qn * mwords;
             const int wend = (u1 - cu0) * SPL;             // end of my mask words (chunk-relative)
+            Misc *mo = &MISC0[qn];
+
+            // one unit of samples.  slot: table slot of the segment holding the sample before the lane's first
+            auto unit_body = [&](auto edge_c, auto dense_c, auto gen_c, int uu, unsigned fb, int slot) {
+                constexpr bool EDGE = decltype(edge_c)::value, DENSE = decltype(dense_c)::value, GEN = decltype(gen_c)::value;
+                const int cu = uu - cu0, tl = uu * UNIT + lane * SPL;
+                CarryT *xu = Xs + (size_t)cu * UNIT;
+                // x of the unit (swizzled chunks) -> registers; save it for the knot-stop trend row
+                CarryT xv[SPL];
+#pragma unroll
+                for (int qc = 0; qc < LCH; ++qc) {
+                    const CVec d = *reinterpret_cast<const CVec *>(xu + coff[qc]);
+                    *reinterpret_cast<CVec *>(bk + tl + qc * EPC) = d;
+                    if constexpr (sizeof(CarryT) == 8) { xv[qc * 2] = d.x; xv[qc * 2 + 1] = d.y; }
+                    else { xv[qc * 4] = d.x; xv[qc * 4 + 1] = d.y; xv[qc * 4 + 2] = d.z; xv[qc * 4 + 3] = d.w; }
+                }
+                CarryT bv[SPL];
+                if (DENSE) {
+                    const CarryT *xt = XT + slot;
+                    const LS *lp = ls + slot;
+#pragma unroll
+                    for (int j = 0; j < SPL; ++j) {
+                        const unsigned bit = (fb >> j) & 1u;
+                        xt += bit;
+                        lp += bit;
+                        const LS q1 = *lp;
+                        bv[j] = A::add(q1.L, A::mul(q1.s, A::sub(xv[j], *xt)));      // ITD.py:115-117
+                    }
+                } else {
+                    const CarryT Xk = XT[slot];
+                    const LS q1 = ls[slot];
+#pragma unroll
+                    for (int j = 0; j < SPL; ++j) bv[j] = A::add(q1.L, A::mul(q1.s, A::sub(xv[j], Xk)));
+                }
+                if (EDGE) {
+#pragma unroll
+                    for (int j = 0; j < SPL; ++j)
+                        if (tl + j >= n - 1) bv[j] = (CarryT)0;                         // ITD.py:112
+                }
+                // R = x - B (ITD.py:119); the iteration stop's last row is R + B (ITD.py:420)
+                if (!EDGE && !GEN) {
+#pragma unroll
+                    for (int qv = 0; qv < SPL / OPV; ++qv) {
+                        OVec o;
+                        if constexpr (sizeof(OutT) == 8) {
+                            o.x = (OutT)A::sub(xv[qv * 2], bv[qv * 2]); o.y = (OutT)A::sub(xv[qv * 2 + 1], bv[qv * 2 + 1]);
+                        } else {
+                            o.x = (OutT)A::sub(xv[qv * 4], bv[qv * 4]); o.y = (OutT)A::sub(xv[qv * 4 + 1], bv[qv * 4 + 1]);
+                            o.z = (OutT)A::sub(xv[qv * 4 + 2], bv[qv * 4 + 2]); o.w = (OutT)A::sub(xv[qv * 4 + 3], bv[qv * 4 + 3]);
+                        }
+                        *reinterpret_cast<OVec *>(rrow + tl + qv * OPV) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < SPL; ++j) {
+                        if (!EDGE || tl + j < n) {
+                            const CarryT r0 = A::sub(xv[j], bv[j]);
+                            rrow[tl + j] = (OutT)(last ? A::add(r0, bv[j]) : r0);
+                            if (brow) brow[tl + j] = last ? (OutT)0 : (OutT)bv[j];      // ITD.py:424
+                        }
+                    }
+                }
+                // carry <- B
+#pragma unroll
+                for (int qc = 0; qc < LCH; ++qc) {
+                    CVec o;
+                    if constexpr (sizeof(CarryT) == 8) { o.x = bv[qc * 2]; o.y = bv[qc * 2 + 1]; }
+                    else { o.x = bv[qc * 4]; o.y = bv[qc * 4 + 1]; o.z = bv[qc * 4 + 2]; o.w = bv[qc * 4 + 3]; }
+                    *reinterpret_cast<CVec *>(xu + coff[qc]) = o;
+                }
+                // the two end-knot baselines of the next level (ITD.py:101-102 on B)
+                if (EDGE) {
+                    if (tl == 0) {
+                        mo->x0 = bv[0];
+                        mo->endl0 = mean2<CarryT>(bv[0], bv[1]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < SPL; ++j) {
+                        if (tl + j == n - 2) {
+                            mo->endl1 = mean2<CarryT>(bv[j], (CarryT)0);
+                            mo->xlast = (CarryT)0;
+                        }
+                    }
+                }
+                // extrema of B: the stop test (ITD.py:400-404) and the next level's knots
+                emit_flags(edge_c, bv, mkn, uu);
+            };
+
+            // per-unit knot counts of my range, one unit per lane (window of 32 units starting at ub)
+            int ub = u0;
+            auto load_counts = [&](int ubase) -> int {
+                const int uu = ubase + lane;
+                int c = 0;
+                if (uu < u1) {
+                    const uint4 *w4 = reinterpret_cast<const uint4 *>(mk + (uu - cu0) * SPL);
+#pragma unroll
+                    for (int i = 0; i < SPL / 4; ++i) {
+                        const uint4 w = w4[i];
+                        c += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+                    }
+                }
+                return c;
+            };
+            int cntv = load_counts(ub);
 
             for (int u = u0; u < u1;) {
                 // ---- run = units [u, ue) with at most UNIT knots in total -------------------------
                 int ue = u, cntrun = 0;
                 while (ue < u1) {
-                    const unsigned wd = (lane < SPL) ? mk[(ue - cu0) * SPL + lane] : 0u;
-                    const int c = __reduce_add_sync(FULL, __popc(wd));
+                    if (ue - ub >= 32) {
+                        ub = ue;
+                        cntv = load_counts(ub);
+                    }
+                    const int c = __shfl_sync(FULL, cntv, ue - ub);
                     if (ue > u && cntrun + c > UNIT) break;
                     cntrun += c;
                     ++ue;
@@ -516,12 +685,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) resident_kernel(const ResidentP
                     TAU[0] = p2t; XT[0] = p2x;
                     TAU[1] = p1t; XT[1] = p1x;
                 }
-                {
+                if (cntrun > 0) {
                     int runpre = 0;
                     for (int uu = u; uu < ue; ++uu) {
                         const int cu = uu - cu0;
-                        const unsigned wd = mk[cu * SPL + lw];
-                        unsigned fb = (wd >> lsh) & FBM;
+                        unsigned fb = (mk[cu * SPL + lw] >> lsh) & FBM;
+                        if (!__any_sync(FULL, fb != 0u)) continue;
                         const int c = __popc(fb);
                         int inc = c;
 #pragma unroll
@@ -531,11 +700,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) resident_kernel(const ResidentP
                         }
                         int idx = 2 + runpre + inc - c;
                         const int trel0 = cu * UNIT + lane * SPL;
+                        const CarryT *xu = Xs + (size_t)cu * UNIT;
                         while (fb) {
                             const int j = __ffs(fb) - 1;
                             fb &= fb - 1;
                             TAU[idx] = cu0 * UNIT + trel0 + j;
-                            XT[idx] = Xs[swz(trel0 + j)];
+                            XT[idx] = xu[(lane * LCH + ((j / EPC) ^ xorv)) * EPC + (j % EPC)];
                             ++idx;
                         }
                         runpre += __shfl_sync(FULL, inc, 31);
@@ -560,21 +730,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) resident_kernel(const ResidentP
                         }
                     }
                     if (lane < 3) {
-                        // own-range knots first, then the neighbours' (at*, ax*), which already end in the virtual end knot
-                        const int i = lane;
+                        // own-range knots first, then the neighbours' (hk->at), which already end in the virtual end knot
                         int t;
                         CarryT v;
-                        if (i < found) {
-                            const int tr = (i == 0) ? ft0 : (i == 1) ? ft1 : ft2;
+                        if (lane < found) {
+                            const int tr = (lane == 0) ? ft0 : (lane == 1) ? ft1 : ft2;
                             t = cu0 * UNIT + tr;
                             v = Xs[swz(tr)];
                         } else {
-                            const int k2 = i - found;
-                            t = (k2 == 0) ? at0 : (k2 == 1) ? at1 : at2;
-                            v = (k2 == 0) ? ax0 : (k2 == 1) ? ax1 : ax2;
+                            t = hk->at[lane - found];
+                            v = hk->ax[lane - found];
                         }
-                        TAU[2 + cntrun + i] = t;
-                        XT[2 + cntrun + i] = v;
+                        TAU[2 + cntrun + lane] = t;
+                        XT[2 + cntrun + lane] = v;
                     }
                 }
                 __syncwarp();
@@ -622,127 +790,34 @@ __global__ void __launch_bounds__(WARPS * 32, 1) resident_kernel(const ResidentP
                 // ---- the samples of the run ----------------------------------------------------------
                 int runpre = 0;
                 for (int uu = u; uu < ue; ++uu) {
-                    const int cu = uu - cu0, t0 = uu * UNIT, tl = t0 + lane * SPL;
+                    const int t0 = uu * UNIT;
                     const bool edge = (uu == 0) || (t0 + UNIT >= n - 1);
-                    const unsigned wd = mk[cu * SPL + lw];
-                    const unsigned fb = (wd >> lsh) & FBM;
-                    const int c = __popc(fb);
-                    int inc = c;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int t = __shfl_up_sync(FULL, inc, o);
-                        if (lane >= o) inc += t;
+                    unsigned fb = 0u;
+                    bool dense = false;
+                    if (cntrun > 0) {
+                        fb = (mk[(uu - cu0) * SPL + lw] >> lsh) & FBM;
+                        dense = __any_sync(FULL, fb != 0u);
                     }
-                    int seg = 1 + runpre + inc - c;
-                    runpre += __shfl_sync(FULL, inc, 31);
-                    // x of the unit (swizzled chunks) -> registers; save it for the knot-stop trend row
-                    CarryT xv[SPL];
-                    const int cbase = (cu * UNIT + lane * SPL) / EPC;
+                    int slot = 1 + runpre;
+                    if (dense) {
+                        const int c = __popc(fb);
+                        int inc = c;
 #pragma unroll
-                    for (int qc = 0; qc < LCH; ++qc) {
-                        const CarryT *src = Xs + (size_t)(cbase + (qc ^ xorv)) * EPC;
-                        if constexpr (sizeof(CarryT) == 8) {
-                            const double2 d = *reinterpret_cast<const double2 *>(src);
-                            xv[qc * 2] = d.x; xv[qc * 2 + 1] = d.y;
-                            *reinterpret_cast<double2 *>(bk + tl + qc * 2) = d;
-                        } else {
-                            const float4 d = *reinterpret_cast<const float4 *>(src);
-                            xv[qc * 4] = d.x; xv[qc * 4 + 1] = d.y; xv[qc * 4 + 2] = d.z; xv[qc * 4 + 3] = d.w;
-                            *reinterpret_cast<float4 *>(bk + tl + qc * 4) = d;
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int t = __shfl_up_sync(FULL, inc, o);
+                            if (lane >= o) inc += t;
                         }
+                        slot += inc - c;
+                        runpre += __shfl_sync(FULL, inc, 31);
                     }
-                    CarryT Xk = XT[seg];
-                    LS q1 = ls[seg];
-                    CarryT bv[SPL];
-#pragma unroll
-                    for (int j = 0; j < SPL; ++j) {
-                        if ((fb >> j) & 1u) {
-                            ++seg;
-                            Xk = XT[seg];
-                            q1 = ls[seg];
-                        }
-                        CarryT bb = A::add(q1.L, A::mul(q1.s, A::sub(xv[j], Xk)));      // ITD.py:115-117
-                        if (edge && tl + j >= n - 1) bb = (CarryT)0;                    // ITD.py:112
-                        bv[j] = bb;
-                    }
-                    // R = x - B (ITD.py:119); the iteration stop's last row is R + B (ITD.py:420)
-                    if (!edge && out_vec) {
-                        constexpr int OPV = 16 / (int)sizeof(OutT);
-#pragma unroll
-                        for (int qv = 0; qv < SPL / OPV; ++qv) {
-                            OutT rr[OPV], bo[OPV];
-#pragma unroll
-                            for (int i = 0; i < OPV; ++i) {
-                                const int j = qv * OPV + i;
-                                const CarryT r0 = A::sub(xv[j], bv[j]);
-                                rr[i] = (OutT)(last ? A::add(r0, bv[j]) : r0);
-                                bo[i] = last ? (OutT)0 : (OutT)bv[j];                   // ITD.py:424
-                            }
-                            if constexpr (sizeof(OutT) == 8) {
-                                *reinterpret_cast<double2 *>(rrow + tl + qv * 2) = make_double2(rr[0], rr[1]);
-                                if (brow) *reinterpret_cast<double2 *>(brow + tl + qv * 2) = make_double2(bo[0], bo[1]);
-                            } else {
-                                *reinterpret_cast<float4 *>(rrow + tl + qv * 4) = make_float4(rr[0], rr[1], rr[2], rr[3]);
-                                if (brow) *reinterpret_cast<float4 *>(brow + tl + qv * 4) = make_float4(bo[0], bo[1], bo[2], bo[3]);
-                            }
-                        }
+                    if (edge) unit_body(std::true_type{}, std::true_type{}, std::true_type{}, uu, fb, slot);
+                    else if (gen) {
+                        if (dense) unit_body(std::false_type{}, std::true_type{}, std::true_type{}, uu, fb, slot);
+                        else unit_body(std::false_type{}, std::false_type{}, std::true_type{}, uu, fb, slot);
                     } else {
-#pragma unroll
-                        for (int j = 0; j < SPL; ++j) {
-                            if (tl + j < n) {
-                                const CarryT r0 = A::sub(xv[j], bv[j]);
-                                rrow[tl + j] = (OutT)(last ? A::add(r0, bv[j]) : r0);
-                                if (brow) brow[tl + j] = last ? (OutT)0 : (OutT)bv[j];
-                            }
-                        }
+                        if (dense) unit_body(std::false_type{}, std::true_type{}, std::false_type{}, uu, fb, slot);
+                        else unit_body(std::false_type{}, std::false_type{}, std::false_type{}, uu, fb, slot);
                     }
-                    // carry <- B
-#pragma unroll
-                    for (int qc = 0; qc < LCH; ++qc) {
-                        CarryT *dst = Xs + (size_t)(cbase + (qc ^ xorv)) * EPC;
-                        if constexpr (sizeof(CarryT) == 8) {
-                            *reinterpret_cast<double2 *>(dst) = make_double2(bv[qc * 2], bv[qc * 2 + 1]);
-                        } else {
-                            *reinterpret_cast<float4 *>(dst) = make_float4(bv[qc * 4], bv[qc * 4 + 1], bv[qc * 4 + 2], bv[qc * 4 + 3]);
-                        }
-                    }
-                    // the two end-knot baselines of the next level (ITD.py:101-102 on B)
-                    if (edge) {
-                        if (tl == 0) {
-                            Misc *mo = &MISC0[qn];
-                            mo->x0 = bv[0];
-                            mo->endl0 = mean2<CarryT>(bv[0], bv[1]);
-                        }
-#pragma unroll
-                        for (int j = 0; j < SPL; ++j) {
-                            if (tl + j == n - 2) {
-                                Misc *mo = &MISC0[qn];
-                                mo->endl1 = mean2<CarryT>(bv[j], (CarryT)0);
-                                mo->xlast = (CarryT)0;
-                            }
-                        }
-                    }
-                    // extrema of B: the stop test (ITD.py:400-404) and the next level's knots
-                    CarryT vl = __shfl_up_sync(FULL, bv[SPL - 1], 1);
-                    if (lane == 0) vl = vlast;
-                    unsigned pkf, pkl;
-                    unsigned f = lane_flags<SPL, CarryT>(bv, vl, lane, pkf, pkl);
-                    if (edge) {
-                        const int lo = max(0, 1 - tl), hi = n - 2 - tl;
-                        unsigned vm = (hi < 0) ? 0u : ((hi >= 31) ? FULL : ((2u << hi) - 1u));
-                        vm &= (lo >= 32) ? 0u : (FULL << lo);
-                        f &= vm;
-                    }
-                    const unsigned pk0 = __shfl_sync(FULL, pkf, 0);
-                    if (uu > u0 && lane == 0 && t0 - 1 >= 1 && t0 - 1 <= n - 2 && flag_from_pk(pend, pk0)) {
-                        Mk[qn * mwords + (cu - 1) * SPL + SPL - 1] |= 0x80000000u;
-                        ++cnt_lane;
-                    }
-                    pend = __shfl_sync(FULL, pkl, 31);
-                    vlast = __shfl_sync(FULL, bv[SPL - 1], 31);
-                    cnt_lane += __popc(f);
-                    store_flags(qn, cu, f);
-                    __syncwarp();
                 }
                 // ---- the run's last two knots become the next run's "before" knots -------------------
                 if (cntrun >= 2) {
@@ -756,14 +831,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) resident_kernel(const ResidentP
                 u = ue;
                 __syncwarp();
             }
-            if (have && b < n && lane == 0) {
-                const unsigned pkr = (vlast < hbr ? 1u : 0u) | (vlast > hbr ? 2u : 0u);
-                if (b - 1 >= 1 && b - 1 <= n - 2 && flag_from_pk(pend, pkr)) {
-                    Mk[qn * mwords + (u1 - 1 - cu0) * SPL + SPL - 1] |= 0x80000000u;
-                    ++cnt_lane;
-                }
-            }
-            __syncwarp();
+            close_range(mkn, hbr);
             hxl = hbl;
             hxr = hbr;
             const int cnt_total = __reduce_add_sync(FULL, cnt_lane);
