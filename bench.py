@@ -281,14 +281,14 @@ def main():
     except Exception:
         pass
     sample_levels = int(nr.sum()) * N
-    if path == "resident":
+    if path in ("resident", "regres"):
         # ONE launch decomposes the whole batch; the carry never leaves the SMs, so the bytes that MUST
         # cross HBM are: x once + every produced row once
         k_ms = lvl_ms[0]
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         compulsory = (S + int(nr.sum())) * N * 8
         roofline = {
-            "bound": "hbm", "kernel": f"pyitd::resident_kernel<double,double,double> (cluster of {cluster} CTAs per signal)",
+            "bound": "hbm", "kernel": f"pyitd::{path}_kernel<double,double,double> (cluster of {cluster} CTAs per signal)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
             "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_ms, "level_launches": 1,

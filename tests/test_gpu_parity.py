@@ -269,10 +269,79 @@ def test_resident_kernel_fp32_variants(cfg, monkeypatch):
         pyitd_b200.clear_plan_cache()
 
 
-def test_resident_is_the_default_for_on_chip_sizes():
+@pytest.mark.parametrize("spl", [8, 16])
+@pytest.mark.parametrize("cl", [0, 1, 2, 4, 8])
+def test_regres_kernel_cluster_shapes(spl, cl, monkeypatch):
+    """The register-resident kernel (whole decomposition in one launch, every lane keeps its samples of the
+    carry in registers) for both samples-per-lane settings and every cluster size, over sizes around the
+    lane (8/16 samples), warp (256/512) and CTA (4096/8192) boundaries."""
     from pyitd_b200.itd import get_plan
-    assert get_plan(0, 64, 65536, _capi.F64, 11, 2, 0).path == ("resident", 4)
-    assert get_plan(0, 64, 8192, _capi.F32_MIXED, 7, 2, 0).path[0] == "resident"
+    monkeypatch.setenv("PYITD_FORCE_PATH", "regres")
+    monkeypatch.setenv("PYITD_RR_SPL", str(spl))
+    if cl:
+        monkeypatch.setenv("PYITD_RR_CL", str(cl))
+    pyitd_b200.clear_plan_cache()
+    rng = np.random.default_rng(600 + spl + cl)
+    sizes = RES_SIZES + (15, 16, 17, 4095, 8191, 8193, 16383, 32768, 32769, 40000, 65535, 65536)
+    try:
+        used = 0
+        for n in sizes:
+            plan = get_plan(0, 5, n, _capi.F64, 11, 2, _capi.OPT_BASELINES)
+            path, csize = plan.path
+            if path != "regres":
+                continue                                  # this cluster cannot hold n samples in registers
+            assert cl == 0 or csize == cl
+            used += 1
+            check_against_oracle(_mixed_batch(rng, 5, n), max_iteration=11)
+        assert used >= 8, used
+    finally:
+        pyitd_b200.clear_plan_cache()
+
+
+@pytest.mark.parametrize("spl", [8, 16])
+def test_regres_kernel_many_signals_per_cluster(spl, monkeypatch):
+    monkeypatch.setenv("PYITD_FORCE_PATH", "regres")
+    monkeypatch.setenv("PYITD_RR_SPL", str(spl))
+    monkeypatch.setenv("PYITD_RES_CLUSTERS", "3")
+    pyitd_b200.clear_plan_cache()
+    rng = np.random.default_rng(620 + spl)
+    try:
+        for n, mi in ((700, 11), (4100, 3), (9000, 0), (20000, 11)):
+            check_against_oracle(_mixed_batch(rng, 23, n), max_iteration=mi)
+            check_against_oracle(_mixed_batch(rng, 23, n), max_iteration=mi, zero_tail=True)
+    finally:
+        pyitd_b200.clear_plan_cache()
+
+
+@pytest.mark.parametrize("spl", [8, 16])
+def test_regres_kernel_fp32_variants(spl, monkeypatch):
+    monkeypatch.setenv("PYITD_FORCE_PATH", "regres")
+    monkeypatch.setenv("PYITD_RR_SPL", str(spl))
+    pyitd_b200.clear_plan_cache()
+    rng = np.random.default_rng(640 + spl)
+    try:
+        for n in (5, 130, 1000, 8192, 8195, 30000):
+            x32 = _mixed_batch(rng, 6, n).astype(np.float32)
+            for dt in ("f32_mixed", "f32"):
+                res = pyitd_b200.decompose(gpu(x32), max_iteration=7, dtype=dt, return_baselines=True)
+                for s in range(6):
+                    src = x32[s].astype(np.float64) if dt == "f32_mixed" else x32[s]
+                    try:
+                        want = o.c_decompose(src, 7)
+                    except o.OracleError:
+                        assert int(res.status[s]) != 0
+                        continue
+                    assert int(res.status[s]) == 0
+                    assert res.rows_of(s).cpu().numpy().tobytes() == want.rotations.astype(np.float32).tobytes(), (dt, n, s)
+                    assert res.baselines_of(s).cpu().numpy().tobytes() == want.baselines.astype(np.float32).tobytes(), (dt, n, s)
+    finally:
+        pyitd_b200.clear_plan_cache()
+
+
+def test_default_path_by_shape():
+    from pyitd_b200.itd import get_plan
+    assert get_plan(0, 64, 65536, _capi.F64, 11, 2, 0).path == ("regres", 8)
+    assert get_plan(0, 64, 8192, _capi.F32_MIXED, 7, 2, 0).path == ("regres", 1)
     assert get_plan(0, 1, 1 << 22, _capi.F32, 11, 2, 0).path[0] == "lookback"
     pyitd_b200.clear_plan_cache()
 
