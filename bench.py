@@ -275,11 +275,12 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
     path, cluster = plan.path
-    traffic = None
+    traffic_ratio = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"))).get("traffic_bytes_per_launch")
+        traffic_ratio = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"))).get("traffic_over_algorithmic")
     except Exception:
         pass
+    traffic = None
     sample_levels = int(nr.sum()) * N
     if path in ("resident", "regres"):
         # ONE launch decomposes the whole batch; the carry never leaves the SMs, so the bytes that MUST
@@ -317,6 +318,11 @@ def main():
                           for e, (a, tm, b) in enumerate(zip(active, lv_times, level_bytes))],
             "knot_scan_ms": lvl_ms[0], "sample_levels_per_s": world * sample_levels / (ms_per_step * 1e-3),
         }
+        if traffic_ratio and path == "stream":
+            # dram__bytes_read+write of this kernel from the committed ncu --set full capture, as a ratio to the
+            # algorithmic bytes of the captured launch, applied to this run's average launch
+            roofline["traffic"] = traffic_ratio * roofline["algorithmic_bytes_per_launch"]
+            roofline["traffic_source"] = "profiles/dominant_kernel_traffic.json (ncu dram bytes / algorithmic bytes = %.2f)" % traffic_ratio
 
     # ---- e2e: host buffers through the C ABI (pyitd_decompose_host) -------------------------------
     e2e = None

@@ -84,7 +84,6 @@ PYITD_API int     pyitd_plan_launches(const pyitd_plan *plan);         /* kernel
 #define PYITD_PATH_LOOKBACK 0
 #define PYITD_PATH_STREAM   1
 #define PYITD_PATH_RESIDENT 2
-#define PYITD_PATH_REGRES   3   /* signal kept in the registers of a cluster, one launch per batch */
 PYITD_API int     pyitd_plan_path(const pyitd_plan *plan, int *cluster_size);
 
 /* Measurement aid: with timing enabled every kernel launch of pyitd_decompose_device is bracketed by

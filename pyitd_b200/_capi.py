@@ -131,7 +131,7 @@ class Plan:
         """('resident' | 'stream' | 'lookback', CTAs per cluster)."""
         cl = ctypes.c_int(1)
         code = int(self._L.pyitd_plan_path(self.handle, ctypes.byref(cl)))
-        return {0: "lookback", 1: "stream", 2: "resident", 3: "regres"}[code], int(cl.value)
+        return {0: "lookback", 1: "stream", 2: "resident"}[code], int(cl.value)
 
     def enable_timing(self, on: bool = True) -> None:
         check(self._L.pyitd_plan_enable_timing(self.handle, int(on)), "pyitd_plan_enable_timing")

@@ -14,7 +14,6 @@
 #include "itd_kernels.cuh"
 #include "itd_stream.cuh"
 #include "itd_resident.cuh"
-#include "itd_regres.cuh"
 
 using namespace pyitd;
 
@@ -51,9 +50,7 @@ struct pyitd_plan {
     size_t res_smem = 0;
     void *res_backup = nullptr;
     int *res_kind = nullptr;
-    // whole-decomposition-in-registers kernel (itd_regres.cuh): 16 warps per CTA, one unit per warp
-    bool regres = false;
-    int rr_cl = 1, rr_spl = 16;
+
     size_t carry_elem = 8, io_elem = 8;
     // workspace
     void *ws = nullptr;
@@ -271,7 +268,7 @@ static bool res_geometry(int cfg, int dtype, int n, int cl, ResidentParams &p, s
 
 // picks the smallest cluster that holds the signal on chip; false when none does
 static bool res_configure(pyitd_plan *pl) {
-    int cfg = 0;
+    int cfg = 1;                               // 16 warps x 4 samples per lane measured faster than 8 x 8
     if (const char *env = getenv("PYITD_RES_CFG")) cfg = atoi(env) ? 1 : 0;
     int force_cl = 0;
     if (const char *env = getenv("PYITD_RES_CL")) force_cl = atoi(env);
@@ -287,71 +284,6 @@ static bool res_configure(pyitd_plan *pl) {
         pl->res_chunk_units = p.chunk_units;
         pl->res_smem = smem;
         return true;
-    }
-    return false;
-}
-
-// ---------------------------------------------------------------------------------------------
-// register-resident kernel: configuration and launch
-// ---------------------------------------------------------------------------------------------
-constexpr int kRRWarps = 16;
-
-template <typename InT, typename CarryT, typename OutT, int SPL>
-static cudaError_t rr_launch_t(const RegResParams &p, int cl, int clusters, cudaStream_t st, int *max_clusters_out) {
-    auto k = regres_kernel<InT, CarryT, OutT, kRRWarps, SPL>;
-    constexpr size_t smem = RegResGeom<CarryT, kRRWarps, SPL>::smem_bytes;
-    static_assert(smem <= kMaxSmemOptin, "register-resident kernel tables exceed shared memory");
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(kRRWarps * 32, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cl;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (max_clusters_out) {
-        cfg.gridDim = dim3((unsigned)cl, 1, 1);
-        int nc = 0;
-        e = cudaOccupancyMaxActiveClusters(&nc, k, &cfg);
-        if (e != cudaSuccess) return e;
-        *max_clusters_out = nc;
-        return cudaSuccess;
-    }
-    cfg.gridDim = dim3((unsigned)(clusters * cl), 1, 1);
-    return cudaLaunchKernelEx(&cfg, k, p);
-}
-template <int SPL>
-static cudaError_t rr_launch_d(int dtype, const RegResParams &p, int cl, int clusters, cudaStream_t st, int *mc) {
-    switch (dtype) {
-        case PYITD_F64: return rr_launch_t<double, double, double, SPL>(p, cl, clusters, st, mc);
-        case PYITD_F32_MIXED: return rr_launch_t<float, double, float, SPL>(p, cl, clusters, st, mc);
-        default: return rr_launch_t<float, float, float, SPL>(p, cl, clusters, st, mc);
-    }
-}
-static cudaError_t rr_launch(const pyitd_plan *pl, const RegResParams &p, int clusters, cudaStream_t st, int *mc) {
-    if (pl->rr_spl == 8) return rr_launch_d<8>(pl->dtype, p, pl->rr_cl, clusters, st, mc);
-    return rr_launch_d<16>(pl->dtype, p, pl->rr_cl, clusters, st, mc);
-}
-// smallest cluster (then fewest samples per lane) whose registers hold the signal; false when none does
-static bool rr_configure(pyitd_plan *pl) {
-    int force_cl = 0, force_spl = 0;
-    if (const char *env = getenv("PYITD_RR_CL")) force_cl = atoi(env);
-    if (const char *env = getenv("PYITD_RR_SPL")) force_spl = atoi(env);
-    for (int cl = 1; cl <= 8; cl *= 2) {
-        if (force_cl && cl != force_cl) continue;
-        for (int spl = 8; spl <= 16; spl *= 2) {
-            if (force_spl && spl != force_spl) continue;
-            if ((long long)cl * kRRWarps * 32 * spl >= pl->n) {
-                pl->rr_cl = cl;
-                pl->rr_spl = spl;
-                return true;
-            }
-        }
     }
     return false;
 }
@@ -411,26 +343,23 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
         int v = atoi(env);
         if (v >= 0 && v < kNumTileCfgs) cfg = v;
     }
-    // path choice: many signals -> one pipelined CTA per signal; few long signals -> multi-CTA
-    // look-back tiles.  The streaming kernel needs 16-byte aligned rows for its TMA bulk copies.
+    // path choice (measured on B200, profiles/r1/path_sweep_r1.json):
+    //   many signals            -> one TMA-pipelined CTA per signal, carry in HBM (stream)
+    //   a few dozen signals     -> one cluster per signal, carry on chip, one launch (resident)
+    //   a handful / long / tiny -> many look-back CTAs per signal (lookback)
+    // The streaming kernel needs 16-byte aligned rows for its TMA bulk copies.
     const long long stream_tiles = (n_samples + kStreamTile - 1) / kStreamTile;
-    bool stream = (n_samples % 4 == 0) && stream_tiles <= kStreamMaxTiles && n_signals >= 256;
+    const bool stream_ok = (n_samples % 4 == 0) && stream_tiles <= kStreamMaxTiles;
+    bool stream = stream_ok && n_samples >= 2048 && n_signals >= 160;
+    bool resident = !stream && n_signals > 16 && n_signals < 160 && n_samples >= 4096;
     if (const char *env = getenv("PYITD_FORCE_PATH")) {
-        if (!strcmp(env, "stream")) stream = (n_samples % 4 == 0) && stream_tiles <= kStreamMaxTiles;
-        if (!strcmp(env, "lookback")) stream = false;
+        stream = !strcmp(env, "stream") && stream_ok;
+        resident = !strcmp(env, "resident");
     }
+    pl->resident = resident && res_configure(pl);
+    if (pl->resident) stream = false;
     if (stream) cfg = 1;                       // both kernels must agree on the 1024-sample tile
     pl->stream = stream;
-    // signals that fit on chip (a cluster of up to 8 CTAs) are decomposed by ONE resident-kernel launch
-    {
-        bool want_rr = true, want_res = false;
-        if (const char *env = getenv("PYITD_FORCE_PATH")) {
-            want_rr = !strcmp(env, "regres");
-            want_res = !strcmp(env, "resident");
-        }
-        pl->regres = want_rr && rr_configure(pl);
-        pl->resident = !pl->regres && want_res && res_configure(pl);
-    }
     pl->tile_cfg = cfg;
     pl->tile = kTileCfgs[cfg].threads * kTileCfgs[cfg].items;
     pl->tiles = (int)((n_samples + pl->tile - 1) / pl->tile);
@@ -522,8 +451,7 @@ extern "C" int64_t pyitd_plan_workspace_bytes(const pyitd_plan *pl) { return pl 
 extern "C" int pyitd_plan_launches(const pyitd_plan *pl) { return pl ? pl->launches : 0; }
 extern "C" int pyitd_plan_path(const pyitd_plan *pl, int *cluster_size) {
     if (!pl) return PYITD_E_INVALID;
-    if (cluster_size) *cluster_size = pl->regres ? pl->rr_cl : (pl->resident ? pl->res_cl : 1);
-    if (pl->regres) return PYITD_PATH_REGRES;
+    if (cluster_size) *cluster_size = pl->resident ? pl->res_cl : 1;
     return pl->resident ? PYITD_PATH_RESIDENT : (pl->stream ? PYITD_PATH_STREAM : PYITD_PATH_LOOKBACK);
 }
 
@@ -558,58 +486,6 @@ static int run_scan(pyitd_plan *pl, const void *x, int *status, int *input_knots
     if (int rc = mark(pl, st)) return rc;
     CU(launch_scan(pl, sp, st));
     pl->launches++;
-    return mark(pl, st);
-}
-
-static int run_regres(pyitd_plan *pl, const void *x, void *rotations, void *baselines, int32_t *n_rows,
-                      int32_t *knot_counts, int32_t *input_knots, int32_t *stop_kind, int32_t *status,
-                      cudaStream_t st) {
-    RegResParams rp = {};
-    const long long span = (long long)pl->rr_cl * kRRWarps * 32 * pl->rr_spl;     // samples a cluster holds
-    if (!pl->res_clusters) {
-        int mc = 0;
-        CU(rr_launch(pl, rp, 0, st, &mc));
-        if (mc < 1) return fail(PYITD_E_CUDA, "no register-resident cluster fits on this device");
-        if (const char *env = getenv("PYITD_RES_CLUSTERS")) {
-            const int v = atoi(env);
-            if (v >= 1 && v < mc) mc = v;
-        }
-        pl->res_clusters = (int)((long long)mc < pl->S ? mc : pl->S);
-        const size_t b_backup = (size_t)pl->res_clusters * span * pl->carry_elem;
-        cudaError_t ce = cudaMalloc(&pl->res_backup, b_backup);
-        if (ce == cudaSuccess) ce = cudaMalloc((void **)&pl->res_kind, (size_t)pl->S * sizeof(int));
-        if (ce != cudaSuccess) {
-            cudaGetLastError();
-            pl->res_clusters = 0;
-            return fail(PYITD_E_NOMEM, std::string("scratch allocation failed: ") + cudaGetErrorString(ce));
-        }
-        pl->ws_bytes = b_backup + (size_t)pl->S * sizeof(int);
-    }
-    pl->launches = 0;
-    pl->events_used = 0;
-    const size_t b_sig = (size_t)pl->S * sizeof(int);
-    CU(cudaMemsetAsync(status, 0, b_sig, st));
-    CU(cudaMemsetAsync(knot_counts, 0, b_sig * pl->rows, st));
-    rp.x = x;
-    rp.rot = rotations;
-    rp.bas = baselines;
-    rp.backup = pl->res_backup;
-    rp.out_sig_stride = (long long)pl->rows * pl->n;
-    rp.backup_stride = span;
-    rp.n_rows = n_rows;
-    rp.knot_counts = knot_counts;
-    rp.input_knots = input_knots;
-    rp.stop_kind = stop_kind ? stop_kind : pl->res_kind;
-    rp.status = status;
-    rp.S = pl->S;
-    rp.n = pl->n;
-    rp.emax = pl->emax;
-    rp.rows = pl->rows;
-    rp.min_extrema = pl->min_extrema;
-    rp.opts = pl->opts;
-    if (int rc = mark(pl, st)) return rc;
-    CU(rr_launch(pl, rp, pl->res_clusters, st, nullptr));
-    pl->launches = 1;
     return mark(pl, st);
 }
 
@@ -678,8 +554,6 @@ extern "C" int pyitd_decompose_device(pyitd_plan *pl, const void *x, void *rotat
     if (!(pl->opts & kOptBaselines)) baselines = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(pl->device));
-    if (pl->regres)
-        return run_regres(pl, x, rotations, baselines, n_rows, knot_counts, input_knots, stop_kind, status, st);
     if (pl->resident)
         return run_resident(pl, x, rotations, baselines, n_rows, knot_counts, input_knots, stop_kind, status, st);
     if (int rc = ensure_workspace(pl)) return rc;
