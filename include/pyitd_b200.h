@@ -86,9 +86,17 @@ PYITD_API int     pyitd_plan_launches(const pyitd_plan *plan);         /* kernel
 #define PYITD_PATH_RESIDENT 2
 PYITD_API int     pyitd_plan_path(const pyitd_plan *plan, int *cluster_size);
 
+/* Stream path only: cut the batch into `groups` contiguous signal ranges (1..16), each with its own launch
+ * chain on an internal stream forked from / joined to the caller's stream, so the last partial wave of one
+ * range's launch overlaps another range's next launch.  Results do not depend on it.  PYITD_GROUPS in the
+ * environment sets the default at plan creation. */
+PYITD_API int     pyitd_plan_set_groups(pyitd_plan *plan, int groups);
+PYITD_API int     pyitd_plan_groups(const pyitd_plan *plan);
+
 /* Measurement aid: with timing enabled every kernel launch of pyitd_decompose_device is bracketed by
  * CUDA events on the launching stream; pyitd_plan_launch_times waits for the last one and returns the
- * number of launches, writing their durations in ms (launch 0 = knot scan, 1.. = one per level). */
+ * number of launches, writing their durations in ms (launch 0 = knot scan, 1.. = one per level).  With
+ * more than one launch group the chains overlap, and ONE duration is returned: the whole call, fork to join. */
 PYITD_API int     pyitd_plan_enable_timing(pyitd_plan *plan, int enable);
 PYITD_API int     pyitd_plan_launch_times(pyitd_plan *plan, float *ms, int capacity);
 

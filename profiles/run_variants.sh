@@ -10,7 +10,8 @@ for ln in sys.stdin:
     ln = ln.strip()
     if ln.startswith('{'):
         d = json.loads(ln); r = d['roofline']
-        print('value %.3f G/s  ms/step %.3f  frac %.3f  kernel %s' % (d['value'] / 1e9, d['ms_per_step'], r['frac'], r['kernel']))
+        print('value %.3f G/s  ms/step %.3f  frac %.3f  groups %s  kernel %s' % (d['value'] / 1e9, d['ms_per_step'], r['frac'], r.get('launch_groups'), r['kernel']))
+        print('   per-level serial ms: ' + ' '.join('%.3f' % l['ms'] for l in r.get('per_level', [])) + '  scan %.3f' % r.get('knot_scan_ms', 0))
     elif ln: print(ln[:300])
 " >> gpurun_out/variants.log
 done

@@ -72,6 +72,10 @@ def lib() -> ctypes.CDLL:
     L.pyitd_plan_launches.argtypes = [vp]
     L.pyitd_plan_path.restype = ci
     L.pyitd_plan_path.argtypes = [vp, ctypes.POINTER(ci)]
+    L.pyitd_plan_set_groups.restype = ci
+    L.pyitd_plan_set_groups.argtypes = [vp, ci]
+    L.pyitd_plan_groups.restype = ci
+    L.pyitd_plan_groups.argtypes = [vp]
     L.pyitd_plan_enable_timing.restype = ci
     L.pyitd_plan_enable_timing.argtypes = [vp, ci]
     L.pyitd_plan_launch_times.restype = ci
@@ -132,6 +136,14 @@ class Plan:
         cl = ctypes.c_int(1)
         code = int(self._L.pyitd_plan_path(self.handle, ctypes.byref(cl)))
         return {0: "lookback", 1: "stream", 2: "resident"}[code], int(cl.value)
+
+    @property
+    def groups(self) -> int:
+        return int(self._L.pyitd_plan_groups(self.handle))
+
+    @groups.setter
+    def groups(self, g: int) -> None:
+        check(self._L.pyitd_plan_set_groups(self.handle, int(g)), "pyitd_plan_set_groups")
 
     def enable_timing(self, on: bool = True) -> None:
         check(self._L.pyitd_plan_enable_timing(self.handle, int(on)), "pyitd_plan_enable_timing")

@@ -31,6 +31,8 @@ static int fail(int code, const std::string &msg) {
             return fail(PYITD_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));   \
     } while (0)
 
+constexpr int kMaxGroups = 16;
+
 struct pyitd_plan {
     int device = 0;
     long long S = 0;          // signals
@@ -61,6 +63,13 @@ struct pyitd_plan {
     int *stop_e = nullptr, *stop_kind = nullptr, *input_knots = nullptr;
     unsigned tag = 0;
     int launches = 0;
+    // stream path: the batch is cut into `groups` signal ranges, each with its own launch chain on its own
+    // stream, so that the tail of one range's level e overlaps the head of another range's level e' (a
+    // grid of equal-length one-CTA-per-signal blocks otherwise idles most SMs for the last partial wave
+    // of every launch)
+    int groups = 1;
+    cudaStream_t gstream[kMaxGroups] = {};
+    cudaEvent_t gfork = nullptr, gjoin[kMaxGroups] = {};
     // optional per-launch CUDA-event timing (bench.py's roofline leg)
     bool timing = false;
     cudaEvent_t *events = nullptr;
@@ -160,12 +169,18 @@ static cudaError_t launch_scan_stream_t(const ScanParams &p, long long ctas, cud
     return cudaGetLastError();
 }
 
-static cudaError_t launch_scan(const pyitd_plan *pl, const ScanParams &p, cudaStream_t st) {
-    if (pl->stream && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0) {
+static bool stream_launchable(const pyitd_plan *pl, const void *in) {
+    return pl->stream && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+}
+
+// nsig: signals of this launch (stream path only: p.sig0 .. p.sig0 + nsig); the look-back path always
+// launches the whole batch
+static cudaError_t launch_scan(const pyitd_plan *pl, const ScanParams &p, cudaStream_t st, long long nsig) {
+    if (stream_launchable(pl, p.x)) {
         switch (pl->dtype) {
-            case PYITD_F64: return launch_scan_stream_t<double, double>(p, pl->S, st);
-            case PYITD_F32_MIXED: return launch_scan_stream_t<float, double>(p, pl->S, st);
-            default: return launch_scan_stream_t<float, float>(p, pl->S, st);
+            case PYITD_F64: return launch_scan_stream_t<double, double>(p, nsig, st);
+            case PYITD_F32_MIXED: return launch_scan_stream_t<float, double>(p, nsig, st);
+            default: return launch_scan_stream_t<float, float>(p, nsig, st);
         }
     }
     const long long ctas = pl->S * pl->tiles;
@@ -176,14 +191,15 @@ static cudaError_t launch_scan(const pyitd_plan *pl, const ScanParams &p, cudaSt
     }
 }
 // first = the launch reads the caller's input (io type) instead of a carry buffer
-static cudaError_t launch_level(const pyitd_plan *pl, const LevelParams &p, bool first, cudaStream_t st) {
-    if (pl->stream && (reinterpret_cast<uintptr_t>(p.in) & 15) == 0) {
+static cudaError_t launch_level(const pyitd_plan *pl, const LevelParams &p, bool first, cudaStream_t st,
+                                long long nsig) {
+    if (stream_launchable(pl, p.in)) {
         switch (pl->dtype) {
-            case PYITD_F64: return launch_stream_t<double, double, double>(p, pl->S, st);
+            case PYITD_F64: return launch_stream_t<double, double, double>(p, nsig, st);
             case PYITD_F32_MIXED:
-                return first ? launch_stream_t<float, double, float>(p, pl->S, st)
-                             : launch_stream_t<double, double, float>(p, pl->S, st);
-            default: return launch_stream_t<float, float, float>(p, pl->S, st);
+                return first ? launch_stream_t<float, double, float>(p, nsig, st)
+                             : launch_stream_t<double, double, float>(p, nsig, st);
+            default: return launch_stream_t<float, float, float>(p, nsig, st);
         }
     }
     const long long ctas = pl->S * pl->tiles;
@@ -360,6 +376,11 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
     if (pl->resident) stream = false;
     if (stream) cfg = 1;                       // both kernels must agree on the 1024-sample tile
     pl->stream = stream;
+    pl->groups = 1;
+    if (const char *env = getenv("PYITD_GROUPS")) {
+        const int v = atoi(env);
+        if (v >= 1 && v <= kMaxGroups) pl->groups = v;
+    }
     pl->tile_cfg = cfg;
     pl->tile = kTileCfgs[cfg].threads * kTileCfgs[cfg].items;
     pl->tiles = (int)((n_samples + pl->tile - 1) / pl->tile);
@@ -440,6 +461,11 @@ extern "C" void pyitd_plan_destroy(pyitd_plan *pl) {
         for (int i = 0; i < pl->n_events; ++i) cudaEventDestroy(pl->events[i]);
         delete[] pl->events;
     }
+    for (int i = 0; i < kMaxGroups; ++i) {
+        if (pl->gstream[i]) cudaStreamDestroy(pl->gstream[i]);
+        if (pl->gjoin[i]) cudaEventDestroy(pl->gjoin[i]);
+    }
+    if (pl->gfork) cudaEventDestroy(pl->gfork);
     cudaFree(pl->res_backup);
     cudaFree(pl->res_kind);
     cudaFree(pl->ws);
@@ -472,7 +498,8 @@ static int mark(pyitd_plan *pl, cudaStream_t st) {
     return 0;
 }
 
-static int run_scan(pyitd_plan *pl, const void *x, int *status, int *input_knots, cudaStream_t st, int kinds = 3) {
+static int run_scan(pyitd_plan *pl, const void *x, int *status, int *input_knots, cudaStream_t st, int kinds = 3,
+                    long long sig0 = 0, long long nsig = -1, bool timed = true) {
     ScanParams sp;
     sp.x = x;
     sp.out = pl->table[0];
@@ -483,10 +510,29 @@ static int run_scan(pyitd_plan *pl, const void *x, int *status, int *input_knots
     sp.n = pl->n;
     sp.tiles = pl->tiles;
     sp.kinds = kinds;
-    if (int rc = mark(pl, st)) return rc;
-    CU(launch_scan(pl, sp, st));
+    sp.sig0 = (int)sig0;
+    if (timed)
+        if (int rc = mark(pl, st)) return rc;
+    CU(launch_scan(pl, sp, st, nsig < 0 ? pl->S : nsig));
     pl->launches++;
-    return mark(pl, st);
+    return timed ? mark(pl, st) : 0;
+}
+
+// signal ranges of the stream path's launch groups
+static int effective_groups(const pyitd_plan *pl, const void *x) {
+    if (!stream_launchable(pl, x)) return 1;
+    int g = pl->groups;
+    if (g > kMaxGroups) g = kMaxGroups;
+    if ((long long)g > pl->S) g = (int)pl->S;
+    return g < 1 ? 1 : g;
+}
+static int ensure_group_streams(pyitd_plan *pl, int g) {
+    if (!pl->gfork) CU(cudaEventCreateWithFlags(&pl->gfork, cudaEventDisableTiming));
+    for (int i = 0; i < g; ++i) {
+        if (!pl->gstream[i]) CU(cudaStreamCreateWithFlags(&pl->gstream[i], cudaStreamNonBlocking));
+        if (!pl->gjoin[i]) CU(cudaEventCreateWithFlags(&pl->gjoin[i], cudaEventDisableTiming));
+    }
+    return 0;
 }
 
 static int run_resident(pyitd_plan *pl, const void *x, void *rotations, void *baselines, int32_t *n_rows,
@@ -567,7 +613,22 @@ extern "C" int pyitd_decompose_device(pyitd_plan *pl, const void *x, void *rotat
     CU(cudaMemsetAsync(n_rows, 0, b_sig, st));
     CU(cudaMemsetAsync(knot_counts, 0, b_sig * pl->rows, st));
 
-    if (int rc = run_scan(pl, x, status, input_knots ? input_knots : pl->input_knots, st)) return rc;
+    // G > 1: fork one launch chain per signal range off the caller's stream and join them at the end; with
+    // timing enabled the two events then bracket the whole call instead of every launch
+    const int G = effective_groups(pl, x);
+    if (G > 1) {
+        if (int rc = ensure_group_streams(pl, G)) return rc;
+        if (int rc = mark(pl, st)) return rc;
+        CU(cudaEventRecord(pl->gfork, st));
+        for (int g = 0; g < G; ++g) CU(cudaStreamWaitEvent(pl->gstream[g], pl->gfork, 0));
+    }
+    auto g_lo = [&](int g) { return pl->S * g / G; };
+    for (int g = 0; g < G; ++g) {
+        cudaStream_t gs = (G > 1) ? pl->gstream[g] : st;
+        if (int rc = run_scan(pl, x, status, input_knots ? input_knots : pl->input_knots, gs, 3, g_lo(g),
+                              g_lo(g + 1) - g_lo(g), G == 1))
+            return rc;
+    }
 
     // one launch per possible extraction + one trailing fix-up launch; signals that stop early
     // cost an immediate CTA exit, so no host sync is needed to learn the level count
@@ -595,12 +656,31 @@ extern "C" int pyitd_decompose_device(pyitd_plan *pl, const void *x, void *rotat
         lp.rows = pl->rows;
         lp.min_extrema = pl->min_extrema;
         lp.opts = pl->opts;
-        CU(launch_level(pl, lp, e == 0, st));
-        pl->launches++;
+        for (int g = 0; g < G; ++g) {
+            lp.sig0 = (int)g_lo(g);
+            CU(launch_level(pl, lp, e == 0, (G > 1) ? pl->gstream[g] : st, g_lo(g + 1) - g_lo(g)));
+            pl->launches++;
+        }
+        if (G == 1)
+            if (int rc = mark(pl, st)) return rc;
+    }
+    if (G > 1) {
+        for (int g = 0; g < G; ++g) {
+            CU(cudaEventRecord(pl->gjoin[g], pl->gstream[g]));
+            CU(cudaStreamWaitEvent(st, pl->gjoin[g], 0));
+        }
         if (int rc = mark(pl, st)) return rc;
     }
     return 0;
 }
+
+extern "C" int pyitd_plan_set_groups(pyitd_plan *pl, int groups) {
+    if (!pl) return fail(PYITD_E_INVALID, "null plan");
+    if (groups < 1 || groups > kMaxGroups) return fail(PYITD_E_INVALID, "groups must be in [1, 16]");
+    pl->groups = groups;
+    return 0;
+}
+extern "C" int pyitd_plan_groups(const pyitd_plan *pl) { return pl ? pl->groups : PYITD_E_INVALID; }
 
 extern "C" int pyitd_plan_enable_timing(pyitd_plan *pl, int enable) {
     if (!pl) return fail(PYITD_E_INVALID, "null plan");
@@ -662,7 +742,7 @@ extern "C" int pyitd_extract_level_device(pyitd_plan *pl, const void *x, void *r
     lp.rows = 1;
     lp.min_extrema = 0;
     lp.opts = 0;
-    CU(launch_level(pl, lp, true, st));
+    CU(launch_level(pl, lp, true, st, pl->S));
     pl->launches++;
     return 0;
 }

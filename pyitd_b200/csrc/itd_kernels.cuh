@@ -197,6 +197,7 @@ struct ScanParams {
     int n;           // samples per signal
     int tiles;
     int kinds;       // 1 valleys, 2 peaks, 3 both (the knot set)
+    int sig0 = 0;    // first signal of this launch (stream kernels: one launch per signal group)
 };
 
 struct LevelParams {
@@ -216,6 +217,7 @@ struct LevelParams {
     int rows;            // emax + 1
     int min_extrema;
     unsigned opts;
+    int sig0 = 0;        // first signal of this launch (stream kernels: one launch per signal group)
 };
 
 // ---------------------------------------------------------------------------------------------

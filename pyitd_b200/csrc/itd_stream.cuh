@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_stream_kernel(const Level
     asm volatile("" : "+r"(sbase));                       // keep it in a register (no S2R re-derivation)
     const unsigned full0 = sbase + (unsigned)offsetof(Smem, full);
 
-    const int sig = blockIdx.x;
+    const int sig = blockIdx.x + p.sig0;
     const int n = p.n, e = p.e, tiles = p.tiles;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long row_off = (long long)sig * p.out_sig_stride;
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) scan_stream_kernel(const ScanPa
     asm volatile("" : "+r"(sbase));
     const unsigned full0 = sbase + (unsigned)offsetof(Smem, full);
 
-    const int sig = blockIdx.x;
+    const int sig = blockIdx.x + p.sig0;
     const int n = p.n, tiles = p.tiles;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {

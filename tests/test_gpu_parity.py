@@ -195,6 +195,26 @@ def test_both_level_kernels_agree_with_oracle(path, monkeypatch):
         pyitd_b200.clear_plan_cache()
 
 
+@pytest.mark.parametrize("groups", [2, 3, 7])
+def test_stream_launch_groups_do_not_change_results(groups, monkeypatch):
+    """The stream path may cut the batch into signal ranges with their own launch chains on internal streams
+    (pyitd_plan_set_groups); every signal must still match the oracle bit for bit, ragged stops included."""
+    monkeypatch.setenv("PYITD_FORCE_PATH", "stream")
+    monkeypatch.setenv("PYITD_GROUPS", str(groups))
+    pyitd_b200.clear_plan_cache()
+    rng = np.random.default_rng(310 + groups)
+    try:
+        from pyitd_b200.itd import get_plan
+        assert get_plan(0, 11, 5000, _capi.F64, 11, 2, _capi.OPT_BASELINES).groups == groups
+        for n in (1024, 5000, 9000):
+            check_against_oracle(_mixed_batch(rng, 11, n), max_iteration=11)
+        check_against_oracle(_mixed_batch(rng, 2, 3000), max_iteration=3)        # fewer signals than groups
+        x = synth.eeg_like(40, 16384, seed=77, device="cuda").cpu().numpy()
+        check_against_oracle(x, max_iteration=11)
+    finally:
+        pyitd_b200.clear_plan_cache()
+
+
 RES_SIZES = (3, 4, 5, 31, 33, 127, 128, 129, 255, 256, 257, 258, 511, 513, 1023, 1024, 1025, 2047, 2049, 4096,
              4097, 7777, 8192, 10004, 16385, 20000)
 
