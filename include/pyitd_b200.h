@@ -88,14 +88,10 @@ PYITD_API int     pyitd_plan_path(const pyitd_plan *plan, int *cluster_size);
 
 /* Stream path only: cut the batch into `groups` contiguous signal ranges (1..16), each with its own launch
  * chain on an internal stream forked from / joined to the caller's stream, so the last partial wave of one
- * range's launch overlaps another range's next launch.  Results do not depend on it.  PYITD_GROUPS in the
- * environment sets the default at plan creation. */
+ * range's launch overlaps another range's next launch.  Results do not depend on it.  The default is 2 for
+ * batches of 1024 signals or more, else 1; PYITD_GROUPS in the environment overrides it at plan creation. */
 PYITD_API int     pyitd_plan_set_groups(pyitd_plan *plan, int groups);
 PYITD_API int     pyitd_plan_groups(const pyitd_plan *plan);
-/* Level-kernel generation of the stream path: 0 = level_stream_kernel (striped lanes, knot tables in HBM),
- * 8 or 4 = level_blk_kernel (that many blocked samples per lane, knots kept as a bit mask only); -1 when the
- * plan does not use the stream path.  PYITD_STREAM_KERNEL=v1|blk8|blk4 overrides the default at plan creation. */
-PYITD_API int     pyitd_plan_stream_kernel(const pyitd_plan *plan);
 
 /* Measurement aid: with timing enabled every kernel launch of pyitd_decompose_device is bracketed by
  * CUDA events on the launching stream; pyitd_plan_launch_times waits for the last one and returns the

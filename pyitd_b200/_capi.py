@@ -76,8 +76,6 @@ def lib() -> ctypes.CDLL:
     L.pyitd_plan_set_groups.argtypes = [vp, ci]
     L.pyitd_plan_groups.restype = ci
     L.pyitd_plan_groups.argtypes = [vp]
-    L.pyitd_plan_stream_kernel.restype = ci
-    L.pyitd_plan_stream_kernel.argtypes = [vp]
     L.pyitd_plan_enable_timing.restype = ci
     L.pyitd_plan_enable_timing.argtypes = [vp, ci]
     L.pyitd_plan_launch_times.restype = ci
@@ -146,11 +144,6 @@ class Plan:
     @groups.setter
     def groups(self, g: int) -> None:
         check(self._L.pyitd_plan_set_groups(self.handle, int(g)), "pyitd_plan_set_groups")
-
-    @property
-    def stream_kernel(self) -> int:
-        """0: level_stream_kernel; 8 / 4: level_blk_kernel with that many samples per lane; -1: not the stream path."""
-        return int(self._L.pyitd_plan_stream_kernel(self.handle))
 
     def enable_timing(self, on: bool = True) -> None:
         check(self._L.pyitd_plan_enable_timing(self.handle, int(on)), "pyitd_plan_enable_timing")

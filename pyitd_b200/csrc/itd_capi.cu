@@ -13,7 +13,6 @@
 
 #include "itd_kernels.cuh"
 #include "itd_stream.cuh"
-#include "itd_blk.cuh"
 #include "itd_resident.cuh"
 
 using namespace pyitd;
@@ -45,8 +44,6 @@ struct pyitd_plan {
     int tile_cfg = 1;         // index into the (THREADS, ITEMS) table
     int tile = 1024, tiles = 0;
     bool stream = false;      // one-CTA-per-signal TMA-pipelined level kernel (itd_stream.cuh)
-    int blk = 0;              // stream path, level kernel generation: 0 = level_stream_kernel (knot tables),
-                              // 8 / 4 = level_blk_kernel with 8 / 4 blocked samples per lane (itd_blk.cuh)
     // whole-decomposition-on-chip kernel (itd_resident.cuh): one cluster per signal, one launch per batch
     bool resident = false;
     int res_cfg = 0;          // 0: 8 warps x 8 samples/lane, 1: 16 warps x 4 samples/lane
@@ -173,37 +170,6 @@ static cudaError_t launch_scan_stream_t(const ScanParams &p, long long ctas, cud
 }
 
 
-// level_blk_kernel: 8 warps; 8 samples per lane -> 2048-sample tiles, 3-stage ring, 2 CTAs per SM;
-//                             4 samples per lane -> 1024-sample tiles, 3-stage ring, 3 CTAs per SM
-template <typename InT, typename CarryT, typename OutT, int IT, bool LAST, bool BAS>
-static cudaError_t launch_blk_v(const LevelParams &p, long long ctas, cudaStream_t st) {
-    constexpr int W = 8, STG = 3, MINB = (IT == 8) ? 2 : 3;
-    auto k = level_blk_kernel<InT, CarryT, OutT, W, IT, STG, MINB, LAST, BAS>;
-    const size_t smem = BlkGeom<InT, CarryT, W, IT, STG>::bytes(p.cur.mstride);
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k<<<(unsigned)ctas, W * 32, smem, st>>>(p);
-    return cudaGetLastError();
-}
-template <typename InT, typename CarryT, typename OutT, int IT>
-static cudaError_t launch_blk_t(const LevelParams &p, long long ctas, cudaStream_t st) {
-    const bool last = (p.e == p.emax), bas = (p.bas != nullptr);
-    if (last) return bas ? launch_blk_v<InT, CarryT, OutT, IT, true, true>(p, ctas, st)
-                         : launch_blk_v<InT, CarryT, OutT, IT, true, false>(p, ctas, st);
-    return bas ? launch_blk_v<InT, CarryT, OutT, IT, false, true>(p, ctas, st)
-               : launch_blk_v<InT, CarryT, OutT, IT, false, false>(p, ctas, st);
-}
-template <int IT>
-static cudaError_t launch_blk_d(int dtype, const LevelParams &p, bool first, long long ctas, cudaStream_t st) {
-    switch (dtype) {
-        case PYITD_F64: return launch_blk_t<double, double, double, IT>(p, ctas, st);
-        case PYITD_F32_MIXED:
-            return first ? launch_blk_t<float, double, float, IT>(p, ctas, st)
-                         : launch_blk_t<double, double, float, IT>(p, ctas, st);
-        default: return launch_blk_t<float, float, float, IT>(p, ctas, st);
-    }
-}
-static bool aligned16(const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
 static bool stream_launchable(const pyitd_plan *pl, const void *in) {
     return pl->stream && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
@@ -228,11 +194,7 @@ static cudaError_t launch_scan(const pyitd_plan *pl, const ScanParams &p, cudaSt
 }
 // first = the launch reads the caller's input (io type) instead of a carry buffer
 static cudaError_t launch_level(const pyitd_plan *pl, const LevelParams &p, bool first, cudaStream_t st,
-                                long long nsig, bool tables = true) {
-    // the blocked kernel needs no knot tables (only the mask) and does 128-bit stores: decompose_device uses
-    // it for every level when the plan says so and the caller's buffers are 16-byte aligned
-    if (!tables && pl->blk && stream_launchable(pl, p.in))
-        return pl->blk == 8 ? launch_blk_d<8>(pl->dtype, p, first, nsig, st) : launch_blk_d<4>(pl->dtype, p, first, nsig, st);
+                                long long nsig) {
     if (stream_launchable(pl, p.in)) {
         switch (pl->dtype) {
             case PYITD_F64: return launch_stream_t<double, double, double>(p, nsig, st);
@@ -416,13 +378,9 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
     if (pl->resident) stream = false;
     if (stream) cfg = 1;                       // both kernels must agree on the 1024-sample tile
     pl->stream = stream;
-    pl->blk = 0;
-    if (const char *env = getenv("PYITD_STREAM_KERNEL")) {
-        const long long mwords = (((n_samples + 31) / 32) + 3) & ~3ll;
-        const int v = !strcmp(env, "blk8") ? 8 : (!strcmp(env, "blk4") ? 4 : 0);
-        if (stream && v && mwords <= kBlkMaxMaskWords) pl->blk = v;
-    }
-    pl->groups = 1;
+    // two launch chains hide most of the partial last wave of every level launch (measured: 17.35 -> 16.56 ms/step
+    // on 4096 x 65536; more groups add nothing)
+    pl->groups = (stream && n_signals >= 1024) ? 2 : 1;
     if (const char *env = getenv("PYITD_GROUPS")) {
         const int v = atoi(env);
         if (v >= 1 && v <= kMaxGroups) pl->groups = v;
@@ -665,8 +623,6 @@ extern "C" int pyitd_decompose_device(pyitd_plan *pl, const void *x, void *rotat
     // G > 1: fork one launch chain per signal range off the caller's stream and join them at the end; with
     // timing enabled the two events then bracket the whole call instead of every launch
     const int G = effective_groups(pl, x);
-    // all levels of a call go through the same kernel generation: the blocked kernel leaves no knot tables behind
-    const bool use_blk = pl->blk && stream_launchable(pl, x) && aligned16(rotations) && (!baselines || aligned16(baselines));
     if (G > 1) {
         if (int rc = ensure_group_streams(pl, G)) return rc;
         if (int rc = mark(pl, st)) return rc;
@@ -709,7 +665,7 @@ extern "C" int pyitd_decompose_device(pyitd_plan *pl, const void *x, void *rotat
         lp.opts = pl->opts;
         for (int g = 0; g < G; ++g) {
             lp.sig0 = (int)g_lo(g);
-            CU(launch_level(pl, lp, e == 0, (G > 1) ? pl->gstream[g] : st, g_lo(g + 1) - g_lo(g), !use_blk));
+            CU(launch_level(pl, lp, e == 0, (G > 1) ? pl->gstream[g] : st, g_lo(g + 1) - g_lo(g)));
             pl->launches++;
         }
         if (G == 1)
@@ -732,7 +688,6 @@ extern "C" int pyitd_plan_set_groups(pyitd_plan *pl, int groups) {
     return 0;
 }
 extern "C" int pyitd_plan_groups(const pyitd_plan *pl) { return pl ? pl->groups : PYITD_E_INVALID; }
-extern "C" int pyitd_plan_stream_kernel(const pyitd_plan *pl) { return pl ? (pl->stream ? pl->blk : -1) : PYITD_E_INVALID; }
 
 extern "C" int pyitd_plan_enable_timing(pyitd_plan *pl, int enable) {
     if (!pl) return fail(PYITD_E_INVALID, "null plan");
