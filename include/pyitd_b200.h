@@ -132,6 +132,23 @@ PYITD_API int pyitd_extract_level_device(pyitd_plan *plan, const void *x, void *
                                int32_t *knot_count, int32_t *status, void *stream);
 
 /*
+ * one sifting level with SUPPLIED knots -- detect the knots once (pyitd_find_knots_device on a
+ * reference channel, or any ascending list), then apply the knot baseline + interpolation of ITD.py:95-119 to
+ * other channels or to updated data.  This is the "retention and reuse of extrema ... along multiple channels"
+ * mode of the reference's C++ port (itd.cpp:41-44; compute_extrema == false at itd.cpp:156-169), on ITD.py's own
+ * interpolant.  With a signal's own knots it equals pyitd_extract_level_device bit for bit.
+ *   knots       [n_knot_rows, knot_capacity] int32, ascending interior indices in [1, n_samples - 2]
+ *   knot_count  [n_knot_rows] int32
+ *   n_knot_rows n_signals (one list per signal) or 1 (one list shared by every signal)
+ *   status      PYITD_ST_BAD_KNOTS when a list is not strictly increasing inside [1, n-2] (that signal is then
+ *               processed with the empty list), PYITD_ST_ZERO_DX / PYITD_ST_NONFINITE as elsewhere
+ */
+#define PYITD_ST_BAD_KNOTS 8
+PYITD_API int pyitd_extract_with_knots_device(pyitd_plan *plan, const void *x, const int32_t *knots,
+                                    int64_t knot_capacity, const int32_t *knot_count, int64_t n_knot_rows,
+                                    void *rotation, void *baseline, int32_t *status, void *stream);
+
+/*
  * Replaces detect_peaks (ITD.py:33-76) and the knot merge around it (ITD.py:87-88, :97).
  *   kinds      PYITD_KNOTS_VALLEYS = detect_peaks(x), PYITD_KNOTS_PEAKS = detect_peaks(-x),
  *              PYITD_KNOTS_BOTH = sort(unique(hstack(both))) = the knot set of one level

@@ -18,7 +18,8 @@
  * Status codes (shared with include/pyitd_b200.h):
  *   0 ok, 1 zero delta-X in a segment (reference raises ZeroDivisionError, ITD.py:116),
  *   2 non-finite input (reference NaN path ITD.py:46-51,64-68 is not supported),
- *   3 signal shorter than 3 samples (undefined in the reference, ITD.py:42-43).
+ *   3 signal shorter than 3 samples (undefined in the reference, ITD.py:42-43),
+ *   8 a supplied knot list is not strictly increasing inside [1, n-2] (extract_with_knots only).
  */
 #define _GNU_SOURCE
 #include <math.h>
@@ -71,20 +72,23 @@ int64_t itd_oracle_find_knots_f32(const float *x, int64_t n, int64_t *idx)
 }
 
 /* ---- one sifting level ------------------------------------------------------------------
- * ITD.py:79-121 itd_baseline_extract.  tau must have room for n entries, knotL for n.
- * Writes rotation R and baseline B (both length n); *K_out = interior knot count of x. */
-int itd_oracle_extract_level_f64(const double *x, int64_t n, double *R, double *B,
-                                 int64_t *tau, double *knotL, int64_t *K_out)
+ * ITD.py:95-119 with the knot list GIVEN: tau[1..K] hold the interior knots (ascending, inside
+ * [1, n-2]); this function adds tau[0] = 0 and tau[K+1] = n-1 (ITD.py:98) and evaluates the knot
+ * baseline, the baseline and the rotation.  With the knots of x itself it is the body of
+ * itd_baseline_extract; with another channel's knots it is the "retain and reuse the extrema ...
+ * along multiple channels" mode of the reference's C++ port (itd.cpp:41-44, compute_extrema ==
+ * false at itd.cpp:156-169) applied to ITD.py's own interpolant.  knotL must have room for K+2. */
+#define ITD_BAD_KNOTS 8
+int itd_oracle_extract_with_knots_f64(const double *x, int64_t n, int64_t *tau, int64_t K,
+                                      double *R, double *B, double *knotL)
 {
     if (n < 3) return ITD_TOO_SHORT;
     for (int64_t i = 0; i < n; ++i)
         if (!isfinite(x[i])) return ITD_NONFINITE;
-
-    /* ITD.py:95-98: tau = [0, knots..., n-1] */
-    int64_t K = itd_oracle_find_knots_f64(x, n, tau + 1);
+    for (int64_t k = 1; k <= K; ++k)
+        if (tau[k] < 1 || tau[k] > n - 2 || (k > 1 && tau[k] <= tau[k - 1])) return ITD_BAD_KNOTS;
     tau[0] = 0;
     tau[K + 1] = n - 1;
-    if (K_out) *K_out = K;
 
     /* ITD.py:100-102: numpy.mean of two samples = (0.0 + a + b) / 2 */
     knotL[0] = ((0.0 + x[0]) + x[1]) / 2.0;
@@ -120,20 +124,34 @@ int itd_oracle_extract_level_f64(const double *x, int64_t n, double *R, double *
     return status;
 }
 
-/* Same operation sequence carried out entirely in IEEE binary32 (the "pure fp32" variant the
- * product exposes as dtype='f32'; there is no such path in the reference, whose signatures are
- * float64 only, ITD.py:33,79).  The knot weight is formed from exact integers in double and
- * rounded once to float, so that index differences above 2^24 stay exact (SURVEY.md section 7). */
-int itd_oracle_extract_level_f32(const float *x, int64_t n, float *R, float *B,
-                                 int64_t *tau, float *knotL, int64_t *K_out)
+/* ITD.py:79-121 itd_baseline_extract.  tau must have room for n entries, knotL for n.
+ * Writes rotation R and baseline B (both length n); *K_out = interior knot count of x. */
+int itd_oracle_extract_level_f64(const double *x, int64_t n, double *R, double *B,
+                                 int64_t *tau, double *knotL, int64_t *K_out)
 {
     if (n < 3) return ITD_TOO_SHORT;
     for (int64_t i = 0; i < n; ++i)
         if (!isfinite(x[i])) return ITD_NONFINITE;
-    int64_t K = itd_oracle_find_knots_f32(x, n, tau + 1);
+    /* ITD.py:87-98: the knots of x itself */
+    int64_t K = itd_oracle_find_knots_f64(x, n, tau + 1);
+    if (K_out) *K_out = K;
+    return itd_oracle_extract_with_knots_f64(x, n, tau, K, R, B, knotL);
+}
+
+/* Same operation sequence carried out entirely in IEEE binary32 (the "pure fp32" variant the
+ * product exposes as dtype='f32'; there is no such path in the reference, whose signatures are
+ * float64 only, ITD.py:33,79).  The knot weight is formed from exact integers in double and
+ * rounded once to float, so that index differences above 2^24 stay exact (SURVEY.md section 7). */
+int itd_oracle_extract_with_knots_f32(const float *x, int64_t n, int64_t *tau, int64_t K,
+                                      float *R, float *B, float *knotL)
+{
+    if (n < 3) return ITD_TOO_SHORT;
+    for (int64_t i = 0; i < n; ++i)
+        if (!isfinite(x[i])) return ITD_NONFINITE;
+    for (int64_t k = 1; k <= K; ++k)
+        if (tau[k] < 1 || tau[k] > n - 2 || (k > 1 && tau[k] <= tau[k - 1])) return ITD_BAD_KNOTS;
     tau[0] = 0;
     tau[K + 1] = n - 1;
-    if (K_out) *K_out = K;
     knotL[0] = ((0.0f + x[0]) + x[1]) / 2.0f;
     knotL[K + 1] = ((0.0f + x[n - 2]) + x[n - 1]) / 2.0f;
     for (int64_t k = 1; k <= K; ++k) {
@@ -158,6 +176,17 @@ int itd_oracle_extract_level_f32(const float *x, int64_t n, float *R, float *B,
     B[n - 1] = 0.0f;
     for (int64_t t = 0; t < n; ++t) R[t] = x[t] - B[t];
     return status;
+}
+
+int itd_oracle_extract_level_f32(const float *x, int64_t n, float *R, float *B,
+                                 int64_t *tau, float *knotL, int64_t *K_out)
+{
+    if (n < 3) return ITD_TOO_SHORT;
+    for (int64_t i = 0; i < n; ++i)
+        if (!isfinite(x[i])) return ITD_NONFINITE;
+    int64_t K = itd_oracle_find_knots_f32(x, n, tau + 1);
+    if (K_out) *K_out = K;
+    return itd_oracle_extract_with_knots_f32(x, n, tau, K, R, B, knotL);
 }
 
 /* ---- level loop -------------------------------------------------------------------------

@@ -29,7 +29,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-ITD_OK, ITD_ZERO_DX, ITD_NONFINITE, ITD_TOO_SHORT = 0, 1, 2, 3
+ITD_OK, ITD_ZERO_DX, ITD_NONFINITE, ITD_TOO_SHORT, ITD_BAD_KNOTS = 0, 1, 2, 3, 8
 
 
 class OracleError(Exception):
@@ -37,7 +37,8 @@ class OracleError(Exception):
 
     def __init__(self, status: int):
         super().__init__({1: "zero delta-X (ZeroDivisionError, ITD.py:116)",
-                          2: "non-finite input", 3: "signal shorter than 3 samples"}.get(status, str(status)))
+                          2: "non-finite input", 3: "signal shorter than 3 samples",
+                          8: "supplied knots are not strictly increasing inside [1, n-2]"}.get(status, str(status)))
         self.status = status
 
 
@@ -65,18 +66,22 @@ def np_find_knots(x: np.ndarray) -> np.ndarray:
     return np.flatnonzero(np_knot_flags(x)).astype(np.int64)
 
 
-def np_extract_level(x: np.ndarray):
-    """One sifting level, ITD.py:79-121.  Returns ``(R, B, knots)``; dtype follows ``x``
-    (float64 = the reference; float32 = the product's pure-fp32 variant, same operation order
-    with the knot weight rounded once from an exact double quotient)."""
+def np_extract_with_knots(x: np.ndarray, knots: np.ndarray):
+    """ITD.py:95-119 with the interior knots GIVEN (ascending, inside [1, n-2]): the body of
+    ``itd_baseline_extract`` when ``knots`` are x's own, and the reference's "reuse the extrema along
+    multiple channels" mode (itd.cpp:41-44, ``compute_extrema=false`` at itd.cpp:156-169) on ITD.py's
+    interpolant when they come from another channel.  Returns ``(R, B)``; dtype follows ``x``."""
     ft = x.dtype.type
     n = x.shape[0]
     if n < 3:
         raise OracleError(ITD_TOO_SHORT)
     if not np.all(np.isfinite(x)):
         raise OracleError(ITD_NONFINITE)
-    flags = np_knot_flags(x)
-    knots = np.flatnonzero(flags).astype(np.int64)
+    knots = np.asarray(knots, dtype=np.int64)
+    if knots.size and (knots[0] < 1 or knots[-1] > n - 2 or np.any(np.diff(knots) <= 0)):
+        raise OracleError(ITD_BAD_KNOTS)
+    flags = np.zeros(n, dtype=bool)
+    flags[knots] = True
     tau = np.concatenate(([0], knots, [n - 1])).astype(np.int64)              # ITD.py:95-98
     X = x[tau]
     L = np.empty(tau.shape[0], dtype=x.dtype)
@@ -99,6 +104,19 @@ def np_extract_level(x: np.ndarray):
     B = L[seg] + v                                                            # ITD.py:115-117
     B[-1] = 0                                                                 # ITD.py:112
     R = x - B                                                                 # ITD.py:119
+    return R, B
+
+
+def np_extract_level(x: np.ndarray):
+    """One sifting level, ITD.py:79-121.  Returns ``(R, B, knots)``; dtype follows ``x``
+    (float64 = the reference; float32 = the product's pure-fp32 variant, same operation order
+    with the knot weight rounded once from an exact double quotient)."""
+    if x.shape[0] < 3:
+        raise OracleError(ITD_TOO_SHORT)
+    if not np.all(np.isfinite(x)):
+        raise OracleError(ITD_NONFINITE)
+    knots = np.flatnonzero(np_knot_flags(x)).astype(np.int64)                 # ITD.py:87-97
+    R, B = np_extract_with_knots(x, knots)
     return R, B, knots
 
 
@@ -167,6 +185,10 @@ def c_lib() -> ctypes.CDLL:
             f = getattr(lib, name)
             f.restype = ci
             f.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+        for name in ("itd_oracle_extract_with_knots_f64", "itd_oracle_extract_with_knots_f32"):
+            f = getattr(lib, name)
+            f.restype = ci
+            f.argtypes = [vp, i64, vp, i64, vp, vp, vp]
         for name in ("itd_oracle_decompose_f64", "itd_oracle_decompose_f32"):
             f = getattr(lib, name)
             f.restype = ci
@@ -212,6 +234,23 @@ def c_extract_level(x: np.ndarray):
     if st != ITD_OK:
         raise OracleError(st)
     return R, B, tau[1:K.value + 1].copy()
+
+
+def c_extract_with_knots(x: np.ndarray, knots: np.ndarray):
+    x = np.ascontiguousarray(x)
+    n = x.shape[0]
+    knots = np.asarray(knots, dtype=np.int64)
+    K = knots.shape[0]
+    R = np.empty_like(x)
+    B = np.empty_like(x)
+    tau = np.empty(K + 2, dtype=np.int64)
+    tau[1:K + 1] = knots
+    L = np.empty(K + 2, dtype=x.dtype)
+    st = getattr(c_lib(), "itd_oracle_extract_with_knots_" + _suffix(x))(
+        _ptr(x), n, _ptr(tau), K, _ptr(R), _ptr(B), _ptr(L))
+    if st != ITD_OK:
+        raise OracleError(st)
+    return R, B
 
 
 def c_decompose(x: np.ndarray, max_iteration: int = 11, min_extrema: int = 2) -> OracleResult:

@@ -6,8 +6,8 @@ C ABI of ``libpyitd_b200.so`` (hand-written sm_100a kernels); there is no CPU fa
 """
 from ._capi import PyITDLibraryError, Plan  # noqa: F401
 from .itd import (ITD, ITDResult, clear_plan_cache, decompose, detect_peaks, extract_level,  # noqa: F401
-                  find_knots, itd_baseline_extract)
+                  extract_with_knots, find_knots, itd_baseline_extract)
 
 __all__ = ["ITD", "ITDResult", "decompose", "detect_peaks", "itd_baseline_extract", "extract_level",
-           "find_knots", "Plan", "PyITDLibraryError", "clear_plan_cache"]
+           "find_knots", "extract_with_knots", "Plan", "PyITDLibraryError", "clear_plan_cache"]
 __version__ = "0.1.0"

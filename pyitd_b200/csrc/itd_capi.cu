@@ -754,6 +754,64 @@ extern "C" int pyitd_extract_level_device(pyitd_plan *pl, const void *x, void *r
     return 0;
 }
 
+extern "C" int pyitd_extract_with_knots_device(pyitd_plan *pl, const void *x, const int32_t *knots,
+                                               int64_t knot_capacity, const int32_t *knot_count, int64_t n_knot_rows,
+                                               void *rotation, void *baseline, int32_t *status, void *stream) {
+    if (!pl || !x || !knots || !knot_count || !rotation || !baseline || !status || knot_capacity < 0)
+        return fail(PYITD_E_INVALID, "null argument");
+    if (n_knot_rows != 1 && n_knot_rows != pl->S)
+        return fail(PYITD_E_INVALID, "n_knot_rows must be 1 (one list shared by every signal) or n_signals");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(pl->device));
+    if (int rc = ensure_workspace(pl)) return rc;
+    pl->launches = 0;
+    const size_t b_sig = (size_t)pl->S * sizeof(int);
+    CU(cudaMemsetAsync(pl->stop_e, 0x7f, b_sig, st));
+    CU(cudaMemsetAsync(status, 0, b_sig, st));
+    const int shared_list = (n_knot_rows == 1 && pl->S != 1) ? 1 : 0;
+    switch (pl->dtype) {
+        case PYITD_F64:
+            table_from_knots_kernel<double, double><<<(unsigned)pl->S, 256, 0, st>>>(
+                x, knots, knot_capacity, knot_count, shared_list, pl->table[0], status, pl->n, pl->tiles, pl->tile);
+            break;
+        case PYITD_F32_MIXED:
+            table_from_knots_kernel<float, double><<<(unsigned)pl->S, 256, 0, st>>>(
+                x, knots, knot_capacity, knot_count, shared_list, pl->table[0], status, pl->n, pl->tiles, pl->tile);
+            break;
+        default:
+            table_from_knots_kernel<float, float><<<(unsigned)pl->S, 256, 0, st>>>(
+                x, knots, knot_capacity, knot_count, shared_list, pl->table[0], status, pl->n, pl->tiles, pl->tile);
+    }
+    CU(cudaGetLastError());
+    pl->launches++;
+    LevelParams lp;
+    lp.in = x;
+    lp.carry_out = pl->carry[0];
+    lp.fix_src = pl->carry[0];
+    lp.rot = rotation;
+    lp.bas = baseline;
+    lp.out_sig_stride = pl->n;
+    lp.cur = pl->table[0];
+    lp.next = pl->table[1];
+    lp.desc = pl->desc;
+    if (int rc = next_tag(pl, st, &lp.tag)) return rc;
+    lp.stop_e = pl->stop_e;
+    lp.stop_kind = pl->stop_kind;
+    lp.n_rows = pl->input_knots;            // scratch: the stop bookkeeping is not reported here
+    lp.knot_counts = pl->input_knots;
+    lp.status = status;
+    lp.n = pl->n;
+    lp.tiles = pl->tiles;
+    lp.e = 0;
+    lp.emax = 0x3fffffff;                   // never the "last" level: row 0 is the plain rotation
+    lp.rows = 1;
+    lp.min_extrema = 0;
+    lp.opts = kOptGivenKnots;
+    CU(launch_level(pl, lp, true, st, pl->S));
+    pl->launches++;
+    return 0;
+}
+
 extern "C" int pyitd_find_knots_device(pyitd_plan *pl, const void *x, int kinds, int32_t *knots,
                                        int64_t knot_capacity, int32_t *knot_count, int32_t *status,
                                        void *stream) {

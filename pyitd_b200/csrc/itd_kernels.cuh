@@ -30,9 +30,11 @@ constexpr int kStopKnots = 1;
 constexpr int kStopIter = 2;
 constexpr int kStZeroDx = 1;
 constexpr int kStNonFinite = 2;
+constexpr int kStBadKnots = 8;
 
 constexpr unsigned kOptBaselines = 1u;
 constexpr unsigned kOptZeroTail = 2u;
+constexpr unsigned kOptGivenKnots = 4u;   // internal: segment ids from the stored flag mask, not from a stencil on x
 
 // ---------------------------------------------------------------------------------------------
 // unfused IEEE arithmetic in the carry type
@@ -430,6 +432,12 @@ __global__ void __launch_bounds__(THREADS) level_kernel(const LevelParams p) {
         const bool f = (t >= 1) && (t <= n - 2) && is_knot(xs[j - 1], xs[j], xs[j + 1]);
         bal[r] = __ballot_sync(0xffffffffu, f);
     }
+    if (p.opts & kOptGivenKnots) {
+        // supplied knots (pyitd_extract_with_knots_device): the table's flag mask is the truth, x's own extrema are not
+        const unsigned *gm = p.cur.mask + (long long)sig * p.cur.mstride + tile * (T / 32);
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) bal[r] = (t0 + r * THREADS + warp * 32 < n) ? gm[r * WARPS + warp] : 0u;
+    }
     if (lane == 0) {
 #pragma unroll
         for (int r = 0; r < ITEMS; ++r) s_wcnt[r * WARPS + warp] = __popc(bal[r]);
@@ -567,6 +575,76 @@ __global__ void export_knots_kernel(const int *tau, const int *kcount, long long
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < lim;
          i += (long long)gridDim.x * blockDim.x)
         dst[i] = src[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// table_from_knots_kernel: the knot table of a level from a SUPPLIED knot list instead of a scan of x
+// (the reference's C++ port keeps and reuses the extrema "along multiple channels", itd.cpp:41-44, with
+// compute_extrema == false at itd.cpp:156-169; here on ITD.py's own interpolant, ITD.py:95-119).
+// One CTA per signal.  knots: [rows, cap] ascending interior indices, rows = S or 1 (shared list).
+// Writes exactly what knot_scan_kernel writes: tau / X_k (with the end knots 0 and n-1, ITD.py:98), the
+// flag mask, the per-tile knot prefix, K and the two end baselines (ITD.py:101-102).  A list that is not
+// strictly increasing inside [1, n-2] is replaced by the empty list and reported as kStBadKnots.
+// ---------------------------------------------------------------------------------------------
+template <typename InT, typename CarryT>
+__global__ void __launch_bounds__(256) table_from_knots_kernel(const void *xin, const int *knots, long long cap,
+                                                               const int *counts, int shared_list, KnotTable out,
+                                                               int *status, int n, int tiles, int tile) {
+    const int sig = blockIdx.x, tid = threadIdx.x;
+    const long long kr = shared_list ? 0 : sig;
+    const InT *x = reinterpret_cast<const InT *>(xin) + (long long)sig * n;
+    const int *kn = knots + kr * cap;
+    int K = counts[kr];
+    bool bad = (K < 0) || ((long long)K > cap) || (K > n - 2);
+    if (bad) K = 0;
+    bool nonfinite = false;
+    for (int t = tid; t < n; t += blockDim.x) nonfinite |= !isfinite((CarryT)x[t]);
+    for (int j = tid; j < K; j += blockDim.x) {
+        const int t = kn[j];
+        bad |= (t < 1) || (t > n - 2) || (j > 0 && t <= kn[j - 1]);
+    }
+    bad = __syncthreads_or(bad ? 1 : 0) != 0;
+    nonfinite = __syncthreads_or(nonfinite ? 1 : 0) != 0;
+    if (bad) K = 0;
+    if (tid == 0 && (bad || nonfinite)) atomicOr(status + sig, (bad ? kStBadKnots : 0) | (nonfinite ? kStNonFinite : 0));
+
+    int *tau = out.tau + (long long)sig * out.kstride;
+    CarryT *xk = reinterpret_cast<CarryT *>(out.xk) + (long long)sig * out.kstride;
+    unsigned *mask = out.mask + (long long)sig * out.mstride;
+    int *tbase = out.tbase + (long long)sig * (tiles + 1);
+    for (long long w = tid; w < out.mstride; w += blockDim.x) mask[w] = 0u;
+    for (int j = tid; j < K; j += blockDim.x) {
+        const int t = kn[j];
+        tau[1 + j] = t;
+        xk[1 + j] = (CarryT)x[t];
+    }
+    if (tid == 0) {
+        const CarryT a0 = (CarryT)x[0], a1 = (CarryT)x[1], z1 = (CarryT)x[n - 2], z0 = (CarryT)x[n - 1];
+        tau[0] = 0;
+        xk[0] = a0;
+        tau[K + 1] = n - 1;
+        xk[K + 1] = z0;
+        out.kcount[sig] = K;
+        CarryT *endl = reinterpret_cast<CarryT *>(out.endl) + 2ll * sig;
+        endl[0] = mean2<CarryT>(a0, a1);
+        endl[1] = mean2<CarryT>(z1, z0);
+    }
+    // knots before each tile: lower bound of the tile's first sample in the list
+    for (int i = tid; i <= tiles; i += blockDim.x) {
+        const long long target = (long long)i * tile;
+        int lo = 0, hi = K;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (kn[mid] < target) lo = mid + 1;
+            else hi = mid;
+        }
+        tbase[i] = (i == tiles) ? K : lo;
+    }
+    __syncthreads();                                   // the mask row is cleared
+    for (int j = tid; j < K; j += blockDim.x) {
+        const int t = kn[j];
+        atomicOr(mask + (t >> 5), 1u << (t & 31));
+    }
 }
 
 template <int THREADS, int ITEMS, typename CarryT>

@@ -229,6 +229,42 @@ def find_knots(x: torch.Tensor, kinds: int = _capi.KNOTS_BOTH, dtype: Optional[s
     return knots, cnt, st
 
 
+def extract_with_knots(x: torch.Tensor, knots: torch.Tensor, knot_count: Optional[torch.Tensor] = None,
+                       dtype: Optional[str] = None):
+    """One sifting level of a CUDA batch ``x[S, N]`` with SUPPLIED knots: detect the
+    knots once (:func:`find_knots` on a reference channel), then apply the knot baseline and the interpolation of
+    ITD.py:95-119 to other channels or to updated data -- the "retain and reuse the extrema ... along multiple
+    channels" mode of the reference's C++ port (itd.cpp:41-44, ``compute_extrema=false`` at itd.cpp:156-169).
+
+    ``knots``: int32 ``[S, cap]`` (one ascending list per signal) or ``[cap]`` / ``[1, cap]`` (one list shared by
+    every signal); ``knot_count``: valid entries per list (default: all ``cap``).
+    Returns ``(rotation, baseline, status)``."""
+    if not (isinstance(x, torch.Tensor) and x.is_cuda):
+        raise TypeError("extract_with_knots expects a CUDA tensor")
+    xt = x if x.dim() == 2 else x.unsqueeze(0)
+    code, io_dtype = _resolve_dtype(xt.dtype, dtype)
+    xt = xt.to(io_dtype).contiguous()
+    S, N = xt.shape
+    kt = knots if knots.dim() == 2 else knots.unsqueeze(0)
+    kt = kt.to(device=xt.device, dtype=torch.int32).contiguous()
+    rows, cap = kt.shape
+    if rows not in (1, S):
+        raise ValueError(f"knots must have 1 or {S} rows, got {rows}")
+    if knot_count is None:
+        kc = torch.full((rows,), cap, dtype=torch.int32, device=xt.device)
+    else:
+        kc = knot_count.to(device=xt.device, dtype=torch.int32).reshape(rows).contiguous()
+    dev = xt.device.index
+    plan = get_plan(dev, S, N, code, 0, 2, 0)
+    R = torch.empty_like(xt)
+    B = torch.empty_like(xt)
+    st = torch.empty(S, dtype=torch.int32, device=xt.device)
+    with torch.cuda.device(dev):
+        plan.extract_with_knots_device(_ptr(xt), _ptr(kt), cap, _ptr(kc), rows, _ptr(R), _ptr(B), _ptr(st),
+                                       torch.cuda.current_stream(dev).cuda_stream)
+    return R, B, st
+
+
 # ---------------------------------------------------------------------------------------------
 # the reference's two module-level functions
 # ---------------------------------------------------------------------------------------------

@@ -215,6 +215,74 @@ def test_stream_launch_groups_do_not_change_results(groups, monkeypatch):
         pyitd_b200.clear_plan_cache()
 
 
+@pytest.mark.parametrize("path", ["stream", "lookback"])
+def test_extract_with_supplied_knots(path, monkeypatch):
+    """SURVEY 8f rank 1 (itd.cpp:41-44, :156-169 compute_extrema=false): knots detected once and reused.
+    (a) a signal's own knots reproduce itd_baseline_extract bit for bit; (b) channel 0's knots applied to every
+    other channel (one shared list) and (c) per-signal lists equal the oracle's ITD.py:95-119 with tau given;
+    (d) a list that is not strictly increasing inside [1, n-2] is reported and replaced by the empty list."""
+    monkeypatch.setenv("PYITD_FORCE_PATH", path)
+    pyitd_b200.clear_plan_cache()
+    rng = np.random.default_rng(330)
+    try:
+        for n in (8, 1000, 4096, 6148):
+            x = rng.standard_normal((7, n)).cumsum(axis=1) + 0.3 * rng.standard_normal((7, n))
+            xg = gpu(x)
+            knots, cnt, st = pyitd_b200.find_knots(xg)
+            # (a) own knots
+            R, B, st2 = pyitd_b200.extract_with_knots(xg, knots, cnt)
+            R0, B0, _, st0 = pyitd_b200.extract_level(xg)
+            assert torch.equal(st2, st0) and torch.equal(R, R0) and torch.equal(B, B0)
+            # (b) channel 0's list shared by all channels
+            k0 = knots[0, : int(cnt[0])]
+            R, B, st3 = pyitd_b200.extract_with_knots(xg, k0)
+            for s in range(7):
+                try:
+                    wr, wb = o.c_extract_with_knots(x[s], k0.cpu().numpy())
+                except o.OracleError as e:
+                    assert int(st3[s]) & e.status
+                    continue
+                assert int(st3[s]) == 0
+                assert R[s].cpu().numpy().tobytes() == wr.tobytes() and B[s].cpu().numpy().tobytes() == wb.tobytes()
+            # (c) per-signal lists: signal s uses the knots of signal (s + 1) % 7
+            perm = [(s + 1) % 7 for s in range(7)]
+            R, B, st4 = pyitd_b200.extract_with_knots(xg, knots[perm], cnt[perm])
+            for s in range(7):
+                kk = knots[perm[s], : int(cnt[perm[s]])].cpu().numpy()
+                try:
+                    wr, wb = o.c_extract_with_knots(x[s], kk)
+                except o.OracleError as e:
+                    assert int(st4[s]) & e.status
+                    continue
+                assert R[s].cpu().numpy().tobytes() == wr.tobytes() and B[s].cpu().numpy().tobytes() == wb.tobytes()
+            # numpy restatement agrees with the C one
+            wr2, wb2 = o.np_extract_with_knots(x[1], k0.cpu().numpy())
+            wr, wb = o.c_extract_with_knots(x[1], k0.cpu().numpy())
+            assert wr.tobytes() == wr2.tobytes() and wb.tobytes() == wb2.tobytes()
+        # (d) invalid lists
+        x = rng.standard_normal((3, 512))
+        bad = torch.tensor([[5, 5, 9, 0], [0, 3, 4, 5], [7, 9, 511, 0]], dtype=torch.int32)
+        R, B, st5 = pyitd_b200.extract_with_knots(gpu(x), bad, torch.tensor([3, 4, 3], dtype=torch.int32))
+        assert [int(v) & _capi.ST_BAD_KNOTS for v in st5.cpu()] == [8, 8, 8]
+        wr, wb = o.c_extract_with_knots(x[0], np.empty(0, dtype=np.int64))       # processed with the empty list
+        assert R[0].cpu().numpy().tobytes() == wr.tobytes()
+        # empty list: the monotone case (two end knots only)
+        R, B, st6 = pyitd_b200.extract_with_knots(gpu(x), torch.zeros((1, 1), dtype=torch.int32),
+                                                  torch.zeros(1, dtype=torch.int32))
+        assert int(st6.abs().max()) == 0
+        for s in range(3):
+            wr, wb = o.c_extract_with_knots(x[s], np.empty(0, dtype=np.int64))
+            assert B[s].cpu().numpy().tobytes() == wb.tobytes()
+        # fp32 I/O around the fp64 arithmetic
+        x32 = rng.standard_normal((4, 3000)).astype(np.float32)
+        kn, c, _ = pyitd_b200.find_knots(gpu(x32), dtype="f32_mixed")
+        R, B, _ = pyitd_b200.extract_with_knots(gpu(x32), kn[0, : int(c[0])], dtype="f32_mixed")
+        wr, wb = o.c_extract_with_knots(x32[2].astype(np.float64), kn[0, : int(c[0])].cpu().numpy())
+        assert R[2].cpu().numpy().tobytes() == wr.astype(np.float32).tobytes()
+    finally:
+        pyitd_b200.clear_plan_cache()
+
+
 RES_SIZES = (3, 4, 5, 31, 33, 127, 128, 129, 255, 256, 257, 258, 511, 513, 1023, 1024, 1025, 2047, 2049, 4096,
              4097, 7777, 8192, 10004, 16385, 20000)
 

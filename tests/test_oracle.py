@@ -144,3 +144,32 @@ def test_reconstruction_invariant():
     x = synth.config1_chirp(n=16384, seed=3)
     r = o.c_decompose(x, 20)
     assert np.max(np.abs(r.rotations.sum(axis=0) - x)) < 1e-14
+
+
+def test_extract_with_knots_restatements():
+    """ITD.py:95-119 with the knot list given: with a signal's own knots it IS the pinned
+    itd_baseline_extract; with another channel's knots the C and numpy restatements agree bit for bit."""
+    rng = np.random.default_rng(77)
+    for n in (3, 8, 100, 5000):
+        x = rng.standard_normal(n)
+        y = np.cumsum(rng.standard_normal(n)) + 0.1 * rng.standard_normal(n)
+        k = o.c_find_knots(x)
+        R, B, _ = o.c_extract_level(x)
+        R2, B2 = o.c_extract_with_knots(x, k)
+        assert R.tobytes() == R2.tobytes() and B.tobytes() == B2.tobytes()
+        try:
+            Ra, Ba = o.c_extract_with_knots(y, k)
+        except o.OracleError as e:
+            with pytest.raises(o.OracleError):
+                o.np_extract_with_knots(y, k)
+            assert e.status == o.ITD_ZERO_DX
+            continue
+        Rn, Bn = o.np_extract_with_knots(y, k)
+        assert Ra.tobytes() == Rn.tobytes() and Ba.tobytes() == Bn.tobytes()
+        assert Ba[-1] == 0.0 and np.array_equal(Ra + Ba, (y - Ba) + Ba)
+    for bad in ([5, 5, 9], [0, 3], [3, 99]):
+        with pytest.raises(o.OracleError) as ei:
+            o.c_extract_with_knots(np.arange(100.0) ** 2, np.array(bad))
+        assert ei.value.status == o.ITD_BAD_KNOTS
+        with pytest.raises(o.OracleError):
+            o.np_extract_with_knots(np.arange(100.0) ** 2, np.array(bad))
