@@ -100,6 +100,11 @@ PYITD_API int     pyitd_plan_groups(const pyitd_plan *plan);
 PYITD_API int     pyitd_plan_enable_timing(pyitd_plan *plan, int enable);
 PYITD_API int     pyitd_plan_launch_times(pyitd_plan *plan, float *ms, int capacity);
 
+/* Measurement aid: a plain streaming kernel with the level kernel's traffic mix -- reads n_doubles float64 from x,
+ * writes n_doubles to y and to z (128-bit accesses, `ctas` blocks of 256 threads, grid-stride).  Its GB/s is the
+ * memory system's practical ceiling for a 1 : 2 read : write stream, next to the copy peak in MEASURED_PEAKS.json. */
+PYITD_API int     pyitd_probe_mixed_traffic(const void *x, void *y, void *z, int64_t n_doubles, int ctas, void *stream);
+
 /*
  * Replaces ITD.itd(data, max_iteration) (ITD.py:351-433) for a batch of independent signals.
  *   x           [n_signals, n_samples]            dtype per plan (device memory)

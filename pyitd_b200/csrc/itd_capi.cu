@@ -689,6 +689,24 @@ extern "C" int pyitd_plan_set_groups(pyitd_plan *pl, int groups) {
 }
 extern "C" int pyitd_plan_groups(const pyitd_plan *pl) { return pl ? pl->groups : PYITD_E_INVALID; }
 
+// measurement aid: the memory system's ceiling for the level kernel's traffic mix (read 1, write 2 streams)
+__global__ void __launch_bounds__(256) mix_probe_kernel(const double2 *__restrict__ x, double2 *__restrict__ y,
+                                                        double2 *__restrict__ z, long long nvec) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        const double2 v = x[i];
+        y[i] = make_double2(v.x - 1.0, v.y - 1.0);
+        z[i] = make_double2(v.x + 1.0, v.y + 1.0);
+    }
+}
+extern "C" int pyitd_probe_mixed_traffic(const void *x, void *y, void *z, int64_t n_doubles, int ctas, void *stream) {
+    if (!x || !y || !z || n_doubles < 2 || ctas < 1) return fail(PYITD_E_INVALID, "bad argument");
+    mix_probe_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>((const double2 *)x, (double2 *)y, (double2 *)z,
+                                                                      n_doubles / 2);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int pyitd_plan_enable_timing(pyitd_plan *pl, int enable) {
     if (!pl) return fail(PYITD_E_INVALID, "null plan");
     CU(cudaSetDevice(pl->device));
