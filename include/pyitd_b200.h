@@ -79,11 +79,13 @@ PYITD_API int64_t pyitd_plan_workspace_bytes(const pyitd_plan *plan);
 PYITD_API int     pyitd_plan_launches(const pyitd_plan *plan);         /* kernel launches of the last call */
 /* Which kernel family pyitd_decompose_* uses for this shape: PYITD_PATH_RESIDENT (signal kept on chip by a
  * thread-block cluster, one launch per batch), PYITD_PATH_STREAM (one CTA per signal, carry in HBM) or
- * PYITD_PATH_LOOKBACK (many CTAs per signal, carry in HBM: long single signals).  *cluster_size (may be NULL)
+ * PYITD_PATH_LOOKBACK (one CTA per tile with a look-back chain, carry in HBM: a handful of signals) or
+ * PYITD_PATH_STRIDED (ONE long signal: persistent CTAs stride over its tiles with the streaming pipeline).  *cluster_size (may be NULL)
  * receives the CTAs per cluster of the resident kernel, else 1. */
 #define PYITD_PATH_LOOKBACK 0
 #define PYITD_PATH_STREAM   1
 #define PYITD_PATH_RESIDENT 2
+#define PYITD_PATH_STRIDED  3
 PYITD_API int     pyitd_plan_path(const pyitd_plan *plan, int *cluster_size);
 
 /* Stream path only: cut the batch into `groups` contiguous signal ranges (1..16), each with its own launch

@@ -13,6 +13,7 @@
 
 #include "itd_kernels.cuh"
 #include "itd_stream.cuh"
+#include "itd_strided.cuh"
 #include "itd_resident.cuh"
 
 using namespace pyitd;
@@ -44,6 +45,8 @@ struct pyitd_plan {
     int tile_cfg = 1;         // index into the (THREADS, ITEMS) table
     int tile = 1024, tiles = 0;
     bool stream = false;      // one-CTA-per-signal TMA-pipelined level kernel (itd_stream.cuh)
+    bool strided = false;     // ONE long signal: persistent blocks stride over its tiles (itd_strided.cuh)
+    int strided_cap = 0;      // test hook: upper bound on the persistent grid (PYITD_STRIDED_CTAS)
     // whole-decomposition-on-chip kernel (itd_resident.cuh): one cluster per signal, one launch per batch
     bool resident = false;
     int res_cfg = 0;          // 0: 8 warps x 8 samples/lane, 1: 16 warps x 4 samples/lane
@@ -171,6 +174,66 @@ static cudaError_t launch_scan_stream_t(const ScanParams &p, long long ctas, cud
 
 
 
+// one long signal: persistent grid of as many blocks as fit on the device (all co-resident: the look-back chain
+// over the tiles needs every block to make progress), block c takes tiles c, c + G, ...
+template <typename InT, typename CarryT, typename OutT, bool LAST, bool BAS>
+static cudaError_t launch_strided_v(const LevelParams &p, int cap, cudaStream_t st) {
+    auto k = level_strided_kernel<InT, CarryT, OutT, kStreamWarps, kStreamItems, kStreamStages, LAST, BAS>;
+    constexpr size_t smem = sizeof(StridedSmem<InT, CarryT, kStreamWarps, kStreamItems, kStreamStages>);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0, dev = 0, sms = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kStreamWarps * 32, smem);
+    if (e != cudaSuccess) return e;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long g = (long long)per_sm * sms;
+    if (g < 1) return cudaErrorLaunchOutOfResources;
+    if (cap > 0 && g > cap) g = cap;
+    if (g > p.tiles) g = p.tiles;
+    k<<<(unsigned)g, kStreamWarps * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+template <typename InT, typename CarryT, typename OutT>
+static cudaError_t launch_strided_t(const LevelParams &p, int cap, cudaStream_t st) {
+    const bool last = (p.e == p.emax), bas = (p.bas != nullptr);
+    if (last) return bas ? launch_strided_v<InT, CarryT, OutT, true, true>(p, cap, st)
+                         : launch_strided_v<InT, CarryT, OutT, true, false>(p, cap, st);
+    return bas ? launch_strided_v<InT, CarryT, OutT, false, true>(p, cap, st)
+               : launch_strided_v<InT, CarryT, OutT, false, false>(p, cap, st);
+}
+
+// the strided path's knot scan: flag words + per-tile counts, then the prefix and the compaction pass
+template <typename InT, typename CarryT>
+static cudaError_t launch_scan_strided_t(const pyitd_plan *pl, const ScanParams &p, cudaStream_t st) {
+    auto k = scan_strided_kernel<InT, CarryT, kStreamWarps, kStreamItems>;
+    constexpr size_t smem = sizeof(ScanStridedSmem<InT, kStreamWarps, kStreamItems>);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0, dev = 0, sms = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kStreamWarps * 32, smem);
+    if (e != cudaSuccess) return e;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long g = (long long)per_sm * sms;
+    if (g < 1) return cudaErrorLaunchOutOfResources;
+    if (pl->strided_cap > 0 && g > pl->strided_cap) g = pl->strided_cap;
+    if (g > p.tiles) g = p.tiles;
+    k<<<(unsigned)g, kStreamWarps * 32, smem, st>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    tile_prefix_scan_kernel<InT, CarryT><<<1, 1024, 0, st>>>(p.out, p.x, p.sig0, p.tiles, p.n, p.input_knots);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int grid = (p.tiles + 255) / 256 < 148 * 8 ? (p.tiles + 255) / 256 : 148 * 8;
+    compact_from_mask_kernel<InT, CarryT><<<grid, 256, 0, st>>>(p.out, p.x, p.sig0, p.n, p.tiles, -1, nullptr);
+    return cudaGetLastError();
+}
+
+static bool strided_launchable_fwd(const pyitd_plan *pl, const void *in) {
+    return pl->strided && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+}
+
 static bool stream_launchable(const pyitd_plan *pl, const void *in) {
     return pl->stream && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
 }
@@ -178,6 +241,13 @@ static bool stream_launchable(const pyitd_plan *pl, const void *in) {
 // nsig: signals of this launch (stream path only: p.sig0 .. p.sig0 + nsig); the look-back path always
 // launches the whole batch
 static cudaError_t launch_scan(const pyitd_plan *pl, const ScanParams &p, cudaStream_t st, long long nsig) {
+    if (strided_launchable_fwd(pl, p.x)) {
+        switch (pl->dtype) {
+            case PYITD_F64: return launch_scan_strided_t<double, double>(pl, p, st);
+            case PYITD_F32_MIXED: return launch_scan_strided_t<float, double>(pl, p, st);
+            default: return launch_scan_strided_t<float, float>(pl, p, st);
+        }
+    }
     if (stream_launchable(pl, p.x)) {
         switch (pl->dtype) {
             case PYITD_F64: return launch_scan_stream_t<double, double>(p, nsig, st);
@@ -195,6 +265,15 @@ static cudaError_t launch_scan(const pyitd_plan *pl, const ScanParams &p, cudaSt
 // first = the launch reads the caller's input (io type) instead of a carry buffer
 static cudaError_t launch_level(const pyitd_plan *pl, const LevelParams &p, bool first, cudaStream_t st,
                                 long long nsig) {
+    if (strided_launchable_fwd(pl, p.in)) {
+        switch (pl->dtype) {
+            case PYITD_F64: return launch_strided_t<double, double, double>(p, pl->strided_cap, st);
+            case PYITD_F32_MIXED:
+                return first ? launch_strided_t<float, double, float>(p, pl->strided_cap, st)
+                             : launch_strided_t<double, double, float>(p, pl->strided_cap, st);
+            default: return launch_strided_t<float, float, float>(p, pl->strided_cap, st);
+        }
+    }
     if (stream_launchable(pl, p.in)) {
         switch (pl->dtype) {
             case PYITD_F64: return launch_stream_t<double, double, double>(p, nsig, st);
@@ -356,7 +435,8 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
     pl->carry_elem = (dtype == PYITD_F32) ? 4 : 8;
     pl->io_elem = (dtype == PYITD_F64) ? 8 : 4;
 
-    int cfg = (n_samples <= 512) ? 0 : 1;
+    // look-back kernels: 512 x 4 tiles measured 15 % faster than 256 x 4 on long signals (profiles/r1/s3/cfg3_tiles.jsonl)
+    int cfg = (n_samples <= 512) ? 0 : ((n_samples >= (1 << 20)) ? 3 : 1);
     if (const char *env = getenv("PYITD_TILE_CFG")) {
         int v = atoi(env);
         if (v >= 0 && v < kNumTileCfgs) cfg = v;
@@ -367,16 +447,22 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
     //   a handful / long / tiny -> many look-back CTAs per signal (lookback)
     // The streaming kernel needs 16-byte aligned rows for its TMA bulk copies.
     const long long stream_tiles = (n_samples + kStreamTile - 1) / kStreamTile;
-    const bool stream_ok = (n_samples % 4 == 0) && stream_tiles <= kStreamMaxTiles;
+    const bool stream_ok_rows = (n_samples % 4 == 0);             // 16-byte aligned rows for the TMA bulk copies
+    const bool stream_ok = stream_ok_rows && stream_tiles <= kStreamMaxTiles;
     bool stream = stream_ok && n_samples >= 2048 && n_signals >= 160;
     bool resident = !stream && n_signals > 16 && n_signals < 160 && n_samples >= 4096;
     if (const char *env = getenv("PYITD_FORCE_PATH")) {
         stream = !strcmp(env, "stream") && stream_ok;
         resident = !strcmp(env, "resident");
     }
+    // one long signal: the streaming pipeline made persistent over its tiles (2.4x the look-back kernel at 2^28)
+    bool strided = !stream && !resident && n_signals == 1 && stream_ok_rows && n_samples >= (1 << 18);
+    if (const char *env = getenv("PYITD_FORCE_PATH")) strided = !strcmp(env, "strided") && n_signals == 1 && stream_ok_rows;
     pl->resident = resident && res_configure(pl);
-    if (pl->resident) stream = false;
-    if (stream) cfg = 1;                       // both kernels must agree on the 1024-sample tile
+    if (pl->resident) stream = strided = false;
+    if (stream || strided) cfg = 1;            // both kernels must agree on the 1024-sample tile
+    pl->strided = strided;
+    if (const char *env = getenv("PYITD_STRIDED_CTAS")) pl->strided_cap = atoi(env);
     pl->stream = stream;
     // two launch chains hide most of the partial last wave of every level launch (measured: 17.35 -> 16.56 ms/step
     // on 4096 x 65536; more groups add nothing)
@@ -485,6 +571,7 @@ extern "C" int pyitd_plan_launches(const pyitd_plan *pl) { return pl ? pl->launc
 extern "C" int pyitd_plan_path(const pyitd_plan *pl, int *cluster_size) {
     if (!pl) return PYITD_E_INVALID;
     if (cluster_size) *cluster_size = pl->resident ? pl->res_cl : 1;
+    if (pl->strided) return PYITD_PATH_STRIDED;
     return pl->resident ? PYITD_PATH_RESIDENT : (pl->stream ? PYITD_PATH_STREAM : PYITD_PATH_LOOKBACK);
 }
 
@@ -523,6 +610,29 @@ static int run_scan(pyitd_plan *pl, const void *x, int *status, int *input_knots
     CU(launch_scan(pl, sp, st, nsig < 0 ? pl->S : nsig));
     pl->launches++;
     return timed ? mark(pl, st) : 0;
+}
+
+static bool strided_launchable(const pyitd_plan *pl, const void *in) {
+    return pl->strided && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+}
+// tile_prefix_kernel + compact_from_mask_kernel on the table the level launch `lp` just produced
+static int run_strided_passes(pyitd_plan *pl, const LevelParams &lp, cudaStream_t st) {
+    const int last = (lp.e == lp.emax) ? 1 : 0;
+    int grid = (pl->tiles + 255) / 256 < 148 * 8 ? (pl->tiles + 255) / 256 : 148 * 8;
+    if (pl->carry_elem == 8) {
+        tile_prefix_kernel<double><<<1, 1024, 0, st>>>(lp.next, lp.sig0, lp.tiles, lp.n, lp.e, lp.rows, lp.min_extrema, last,
+                                                       lp.stop_e, lp.stop_kind, lp.n_rows, lp.knot_counts);
+        CU(cudaGetLastError());
+        compact_from_mask_kernel<double, double><<<grid, 256, 0, st>>>(lp.next, lp.carry_out, lp.sig0, lp.n, lp.tiles, lp.e, lp.stop_e);
+    } else {
+        tile_prefix_kernel<float><<<1, 1024, 0, st>>>(lp.next, lp.sig0, lp.tiles, lp.n, lp.e, lp.rows, lp.min_extrema, last,
+                                                      lp.stop_e, lp.stop_kind, lp.n_rows, lp.knot_counts);
+        CU(cudaGetLastError());
+        compact_from_mask_kernel<float, float><<<grid, 256, 0, st>>>(lp.next, lp.carry_out, lp.sig0, lp.n, lp.tiles, lp.e, lp.stop_e);
+    }
+    CU(cudaGetLastError());
+    pl->launches += 2;
+    return 0;
 }
 
 // signal ranges of the stream path's launch groups
@@ -667,6 +777,10 @@ extern "C" int pyitd_decompose_device(pyitd_plan *pl, const void *x, void *rotat
             lp.sig0 = (int)g_lo(g);
             CU(launch_level(pl, lp, e == 0, (G > 1) ? pl->gstream[g] : st, g_lo(g + 1) - g_lo(g)));
             pl->launches++;
+        }
+        if (strided_launchable(pl, lp.in) && e <= pl->emax) {
+            // the strided level kernel leaves flag words + per-tile counts: prefix / stop rule, then the compaction pass
+            if (int rc = run_strided_passes(pl, lp, st)) return rc;
         }
         if (G == 1)
             if (int rc = mark(pl, st)) return rc;

@@ -363,7 +363,8 @@ def test_default_path_by_shape():
     assert get_plan(0, 64, 65536, _capi.F64, 11, 2, 0).path == ("resident", 4)
     assert get_plan(0, 1, 65536, _capi.F64, 11, 2, 0).path[0] == "lookback"
     assert get_plan(0, 3515, 8192, _capi.F32_MIXED, 7, 2, 0).path[0] == "stream"
-    assert get_plan(0, 1, 1 << 22, _capi.F32, 11, 2, 0).path[0] == "lookback"
+    assert get_plan(0, 1, 1 << 22, _capi.F32, 11, 2, 0).path[0] == "strided"
+    assert get_plan(0, 2, 1 << 22, _capi.F32, 11, 2, 0).path[0] == "lookback"
     pyitd_b200.clear_plan_cache()
 
 
@@ -380,11 +381,61 @@ def test_min_extrema(min_extrema):
     check_against_oracle(_mixed_batch(rng, 6, 3000), max_iteration=11, min_extrema=min_extrema)
 
 
-def test_long_single_signal_multi_cta():
+@pytest.mark.parametrize("path", ["lookback", "strided"])
+def test_long_single_signal_multi_cta(path, monkeypatch):
     # one signal over thousands of tiles: exercises the decoupled look-back chain and deep levels
-    # where almost every tile is knot-free
-    x = synth.long_signal(n=1 << 21, seed=3).double().numpy()
-    check_against_oracle(x[None, :], max_iteration=11)
+    # where almost every tile is knot-free (one CTA per tile / persistent CTAs striding over the tiles)
+    monkeypatch.setenv("PYITD_FORCE_PATH", path)
+    pyitd_b200.clear_plan_cache()
+    try:
+        x = synth.long_signal(n=1 << 21, seed=3).double().numpy()
+        check_against_oracle(x[None, :], max_iteration=11)
+    finally:
+        pyitd_b200.clear_plan_cache()
+
+
+@pytest.mark.parametrize("ctas", [0, 1, 3])
+def test_strided_long_signal_kernel(ctas, monkeypatch):
+    """level_strided_kernel (one long signal, persistent CTAs striding over its tiles, look-back rank bases, halo
+    samples riding with the TMA slice): sizes around the 1024-sample tile, grids of 1 / 3 / all-that-fit CTAs (one,
+    several or hundreds of tiles per CTA), every stop kind, baselines, zero tail, fp32 variants -- bit for bit."""
+    monkeypatch.setenv("PYITD_FORCE_PATH", "strided")
+    if ctas:
+        monkeypatch.setenv("PYITD_STRIDED_CTAS", str(ctas))
+    pyitd_b200.clear_plan_cache()
+    rng = np.random.default_rng(340 + ctas)
+    try:
+        from pyitd_b200.itd import get_plan
+        assert get_plan(0, 1, 4096, _capi.F64, 11, 2, _capi.OPT_BASELINES).path[0] == "strided"
+        for n in (4, 8, 36, 128, 1020, 1024, 1028, 2044, 2048, 2052, 3076, 5120, 10004, 20000):
+            for kind in range(6):
+                x = _mixed_batch(rng, 6, n)[kind:kind + 1]
+                check_against_oracle(x, max_iteration=11)
+        for mi in (0, 1, 4):
+            check_against_oracle(_mixed_batch(rng, 4, 6000)[3:4], max_iteration=mi)
+        check_against_oracle(_mixed_batch(rng, 2, 9000)[1:2], max_iteration=11, min_extrema=5)
+        xz = _mixed_batch(rng, 4, 5000)[3:4]
+        rz = pyitd_b200.decompose(gpu(xz), max_iteration=11, return_baselines=True, zero_tail=True)
+        ref = check_against_oracle(xz, max_iteration=11)
+        nr = int(rz.n_rows[0])
+        assert torch.equal(rz.rotations[0, :nr], ref.rotations[0, :nr])
+        assert float(rz.rotations[0, nr:].abs().max() if nr < rz.rotations.shape[1] else 0) == 0
+        # config 3's generator, 2^20 samples (1024 tiles: 2-3 per CTA at the default grid)
+        x32 = synth.long_signal(n=1 << 20, seed=3).numpy()
+        for dt in ("f32_mixed", "f32"):
+            res = pyitd_b200.decompose(gpu(x32[None, :]), max_iteration=11, dtype=dt, return_baselines=True)
+            want = o.c_decompose(x32.astype(np.float64) if dt == "f32_mixed" else x32, 11)
+            assert res.rows_of(0).cpu().numpy().tobytes() == want.rotations.astype(np.float32).tobytes(), dt
+            assert res.baselines_of(0).cpu().numpy().tobytes() == want.baselines.astype(np.float32).tobytes(), dt
+            assert res.knot_counts[0, : want.rotations.shape[0]].cpu().tolist() == list(want.knot_counts)
+        # supplied knots and the single-level entry go through the same kernel
+        xs = rng.standard_normal((1, 7000)).cumsum(axis=1)
+        kn, c, _ = pyitd_b200.find_knots(gpu(xs))
+        R, B, st = pyitd_b200.extract_with_knots(gpu(xs), kn, c)
+        wr, wb, _ = o.c_extract_level(xs[0])
+        assert R[0].cpu().numpy().tobytes() == wr.tobytes() and B[0].cpu().numpy().tobytes() == wb.tobytes()
+    finally:
+        pyitd_b200.clear_plan_cache()
 
 
 def test_eeg_like_batch_config2_subset():
@@ -557,12 +608,12 @@ def _level1_knots_torch(x):
 
 @pytest.mark.parametrize("dt", ["f32_mixed", "f32"])
 def test_config3_long_signal_fp32_at_oracle_size(dt):
-    """Config 3's generator at 2**22 samples (the oracle needs seconds there): multi-CTA look-back path.
+    """Config 3's generator at 2**22 samples (the oracle needs seconds there): the strided long-signal path.
     f32_mixed must equal float32(reference(float64(x32))) bit for bit; pure f32 equals a binary32 execution."""
     x32 = synth.long_signal(n=1 << 22, seed=3).numpy()
     res = pyitd_b200.decompose(gpu(x32[None, :]), max_iteration=11, dtype=dt)
     from pyitd_b200.itd import get_plan
-    assert get_plan(0, 1, 1 << 22, _capi.F32_MIXED if dt == "f32_mixed" else _capi.F32, 11, 2, 0).path[0] == "lookback"
+    assert get_plan(0, 1, 1 << 22, _capi.F32_MIXED if dt == "f32_mixed" else _capi.F32, 11, 2, 0).path[0] == "strided"
     want = o.c_decompose(x32.astype(np.float64) if dt == "f32_mixed" else x32, 11)
     got = res.rows_of(0).cpu().numpy()
     assert got.shape == want.rotations.shape
