@@ -45,7 +45,7 @@ struct pyitd_plan {
     int tile_cfg = 1;         // index into the (THREADS, ITEMS) table
     int tile = 1024, tiles = 0;
     bool stream = false;      // one-CTA-per-signal TMA-pipelined level kernel (itd_stream.cuh)
-    bool strided = false;     // ONE long signal: persistent blocks stride over its tiles (itd_strided.cuh)
+    bool strided = false;     // a few long signals, one at a time: persistent blocks stride over the tiles (itd_strided.cuh)
     int strided_cap = 0;      // test hook: upper bound on the persistent grid (PYITD_STRIDED_CTAS)
     // whole-decomposition-on-chip kernel (itd_resident.cuh): one cluster per signal, one launch per batch
     bool resident = false;
@@ -242,11 +242,19 @@ static bool stream_launchable(const pyitd_plan *pl, const void *in) {
 // launches the whole batch
 static cudaError_t launch_scan(const pyitd_plan *pl, const ScanParams &p, cudaStream_t st, long long nsig) {
     if (strided_launchable_fwd(pl, p.x)) {
-        switch (pl->dtype) {
-            case PYITD_F64: return launch_scan_strided_t<double, double>(pl, p, st);
-            case PYITD_F32_MIXED: return launch_scan_strided_t<float, double>(pl, p, st);
-            default: return launch_scan_strided_t<float, float>(pl, p, st);
+        // a few long signals: one after the other, each launch fills the device
+        ScanParams q = p;
+        for (long long sg = 0; sg < pl->S; ++sg) {
+            q.sig0 = (int)sg;
+            cudaError_t e;
+            switch (pl->dtype) {
+                case PYITD_F64: e = launch_scan_strided_t<double, double>(pl, q, st); break;
+                case PYITD_F32_MIXED: e = launch_scan_strided_t<float, double>(pl, q, st); break;
+                default: e = launch_scan_strided_t<float, float>(pl, q, st);
+            }
+            if (e != cudaSuccess) return e;
         }
+        return cudaSuccess;
     }
     if (stream_launchable(pl, p.x)) {
         switch (pl->dtype) {
@@ -266,13 +274,21 @@ static cudaError_t launch_scan(const pyitd_plan *pl, const ScanParams &p, cudaSt
 static cudaError_t launch_level(const pyitd_plan *pl, const LevelParams &p, bool first, cudaStream_t st,
                                 long long nsig) {
     if (strided_launchable_fwd(pl, p.in)) {
-        switch (pl->dtype) {
-            case PYITD_F64: return launch_strided_t<double, double, double>(p, pl->strided_cap, st);
-            case PYITD_F32_MIXED:
-                return first ? launch_strided_t<float, double, float>(p, pl->strided_cap, st)
-                             : launch_strided_t<double, double, float>(p, pl->strided_cap, st);
-            default: return launch_strided_t<float, float, float>(p, pl->strided_cap, st);
+        LevelParams q = p;
+        for (long long sg = 0; sg < pl->S; ++sg) {
+            q.sig0 = (int)sg;
+            cudaError_t e;
+            switch (pl->dtype) {
+                case PYITD_F64: e = launch_strided_t<double, double, double>(q, pl->strided_cap, st); break;
+                case PYITD_F32_MIXED:
+                    e = first ? launch_strided_t<float, double, float>(q, pl->strided_cap, st)
+                              : launch_strided_t<double, double, float>(q, pl->strided_cap, st);
+                    break;
+                default: e = launch_strided_t<float, float, float>(q, pl->strided_cap, st);
+            }
+            if (e != cudaSuccess) return e;
         }
+        return cudaSuccess;
     }
     if (stream_launchable(pl, p.in)) {
         switch (pl->dtype) {
@@ -456,8 +472,8 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
         resident = !strcmp(env, "resident");
     }
     // one long signal: the streaming pipeline made persistent over its tiles (2.4x the look-back kernel at 2^28)
-    bool strided = !stream && !resident && n_signals == 1 && stream_ok_rows && n_samples >= (1 << 18);
-    if (const char *env = getenv("PYITD_FORCE_PATH")) strided = !strcmp(env, "strided") && n_signals == 1 && stream_ok_rows;
+    bool strided = !stream && !resident && n_signals <= 16 && stream_ok_rows && n_samples >= (1 << 18);
+    if (const char *env = getenv("PYITD_FORCE_PATH")) strided = !strcmp(env, "strided") && n_signals <= 64 && stream_ok_rows;
     pl->resident = resident && res_configure(pl);
     if (pl->resident) stream = strided = false;
     if (stream || strided) cfg = 1;            // both kernels must agree on the 1024-sample tile
@@ -619,19 +635,22 @@ static bool strided_launchable(const pyitd_plan *pl, const void *in) {
 static int run_strided_passes(pyitd_plan *pl, const LevelParams &lp, cudaStream_t st) {
     const int last = (lp.e == lp.emax) ? 1 : 0;
     int grid = (pl->tiles + 255) / 256 < 148 * 8 ? (pl->tiles + 255) / 256 : 148 * 8;
+    for (long long sg = 0; sg < pl->S; ++sg) {
+    const int sig0 = (int)sg;
     if (pl->carry_elem == 8) {
-        tile_prefix_kernel<double><<<1, 1024, 0, st>>>(lp.next, lp.sig0, lp.tiles, lp.n, lp.e, lp.rows, lp.min_extrema, last,
+        tile_prefix_kernel<double><<<1, 1024, 0, st>>>(lp.next, sig0, lp.tiles, lp.n, lp.e, lp.rows, lp.min_extrema, last,
                                                        lp.stop_e, lp.stop_kind, lp.n_rows, lp.knot_counts);
         CU(cudaGetLastError());
-        compact_from_mask_kernel<double, double><<<grid, 256, 0, st>>>(lp.next, lp.carry_out, lp.sig0, lp.n, lp.tiles, lp.e, lp.stop_e);
+        compact_from_mask_kernel<double, double><<<grid, 256, 0, st>>>(lp.next, lp.carry_out, sig0, lp.n, lp.tiles, lp.e, lp.stop_e);
     } else {
-        tile_prefix_kernel<float><<<1, 1024, 0, st>>>(lp.next, lp.sig0, lp.tiles, lp.n, lp.e, lp.rows, lp.min_extrema, last,
+        tile_prefix_kernel<float><<<1, 1024, 0, st>>>(lp.next, sig0, lp.tiles, lp.n, lp.e, lp.rows, lp.min_extrema, last,
                                                       lp.stop_e, lp.stop_kind, lp.n_rows, lp.knot_counts);
         CU(cudaGetLastError());
-        compact_from_mask_kernel<float, float><<<grid, 256, 0, st>>>(lp.next, lp.carry_out, lp.sig0, lp.n, lp.tiles, lp.e, lp.stop_e);
+        compact_from_mask_kernel<float, float><<<grid, 256, 0, st>>>(lp.next, lp.carry_out, sig0, lp.n, lp.tiles, lp.e, lp.stop_e);
     }
     CU(cudaGetLastError());
     pl->launches += 2;
+    }
     return 0;
 }
 

@@ -364,7 +364,8 @@ def test_default_path_by_shape():
     assert get_plan(0, 1, 65536, _capi.F64, 11, 2, 0).path[0] == "lookback"
     assert get_plan(0, 3515, 8192, _capi.F32_MIXED, 7, 2, 0).path[0] == "stream"
     assert get_plan(0, 1, 1 << 22, _capi.F32, 11, 2, 0).path[0] == "strided"
-    assert get_plan(0, 2, 1 << 22, _capi.F32, 11, 2, 0).path[0] == "lookback"
+    assert get_plan(0, 2, 1 << 22, _capi.F32, 11, 2, 0).path[0] == "strided"
+    assert get_plan(0, 2, 1 << 16, _capi.F32, 11, 2, 0).path[0] == "lookback"
     pyitd_b200.clear_plan_cache()
 
 
@@ -428,6 +429,8 @@ def test_strided_long_signal_kernel(ctas, monkeypatch):
             assert res.rows_of(0).cpu().numpy().tobytes() == want.rotations.astype(np.float32).tobytes(), dt
             assert res.baselines_of(0).cpu().numpy().tobytes() == want.baselines.astype(np.float32).tobytes(), dt
             assert res.knot_counts[0, : want.rotations.shape[0]].cpu().tolist() == list(want.knot_counts)
+        # a few long signals: one after the other through the same launches
+        check_against_oracle(_mixed_batch(rng, 3, 6148), max_iteration=11)
         # supplied knots and the single-level entry go through the same kernel
         xs = rng.standard_normal((1, 7000)).cumsum(axis=1)
         kn, c, _ = pyitd_b200.find_knots(gpu(xs))
