@@ -104,8 +104,11 @@ PYITD_API int     pyitd_plan_launch_times(pyitd_plan *plan, float *ms, int capac
 
 /* Measurement aid: a plain streaming kernel with the level kernel's traffic mix -- reads n_doubles float64 from x,
  * writes n_doubles to y and to z (128-bit accesses, `ctas` blocks of 256 threads, grid-stride).  Its GB/s is the
- * memory system's practical ceiling for a 1 : 2 read : write stream, next to the copy peak in MEASURED_PEAKS.json. */
-PYITD_API int     pyitd_probe_mixed_traffic(const void *x, void *y, void *z, int64_t n_doubles, int ctas, void *stream);
+ * memory system's practical ceiling for a 1 : 2 read : write stream, next to the copy peak in MEASURED_PEAKS.json.
+ * chunk_doubles == 0: grid-stride; > 0: every block streams its own contiguous ranges of that many doubles (the
+ * access pattern of one CTA per signal). */
+PYITD_API int     pyitd_probe_mixed_traffic(const void *x, void *y, void *z, int64_t n_doubles, int ctas,
+                                            int64_t chunk_doubles, void *stream);
 
 /*
  * Replaces ITD.itd(data, max_iteration) (ITD.py:351-433) for a batch of independent signals.

@@ -10,17 +10,18 @@ x = torch.randn(n, dtype=torch.float64, device="cuda")
 y = torch.empty_like(x); z = torch.empty_like(x)
 st = torch.cuda.current_stream().cuda_stream
 out = {}
-for ctas in (148 * 4, 148 * 8, 148 * 16, 148 * 32):
+for ctas, chunk in ((148 * 4, 0), (148 * 8, 0), (148 * 16, 0), (148 * 32, 0),
+                    (444, 65536), (888, 65536), (1184, 65536), (4096, 65536), (444, 1024), (1184, 1024)):
     for _ in range(3):
-        _capi.check(L.pyitd_probe_mixed_traffic(x.data_ptr(), y.data_ptr(), z.data_ptr(), n, ctas, st), "probe")
+        _capi.check(L.pyitd_probe_mixed_traffic(x.data_ptr(), y.data_ptr(), z.data_ptr(), n, ctas, chunk, st), "probe")
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10):
-        L.pyitd_probe_mixed_traffic(x.data_ptr(), y.data_ptr(), z.data_ptr(), n, ctas, st)
+        L.pyitd_probe_mixed_traffic(x.data_ptr(), y.data_ptr(), z.data_ptr(), n, ctas, chunk, st)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
-    out[ctas] = {"ms": ms, "GBps": 24.0 * n / ms / 1e6}
+    out[f"{ctas}x256 chunk {chunk}"] = {"ms": ms, "GBps": 24.0 * n / ms / 1e6}
 # plain copy for reference (1 : 1)
 for _ in range(3):
     y.copy_(x)

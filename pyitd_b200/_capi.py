@@ -77,7 +77,7 @@ def lib() -> ctypes.CDLL:
     L.pyitd_plan_groups.restype = ci
     L.pyitd_plan_groups.argtypes = [vp]
     L.pyitd_probe_mixed_traffic.restype = ci
-    L.pyitd_probe_mixed_traffic.argtypes = [vp, vp, vp, i64, ci, vp]
+    L.pyitd_probe_mixed_traffic.argtypes = [vp, vp, vp, i64, ci, i64, vp]
     L.pyitd_plan_enable_timing.restype = ci
     L.pyitd_plan_enable_timing.argtypes = [vp, ci]
     L.pyitd_plan_launch_times.restype = ci

@@ -822,20 +822,34 @@ extern "C" int pyitd_plan_set_groups(pyitd_plan *pl, int groups) {
 }
 extern "C" int pyitd_plan_groups(const pyitd_plan *pl) { return pl ? pl->groups : PYITD_E_INVALID; }
 
-// measurement aid: the memory system's ceiling for the level kernel's traffic mix (read 1, write 2 streams)
+// measurement aid: the memory system's ceiling for the level kernel's traffic mix (read 1, write 2 streams).
+// chunk_vec == 0: grid-stride (neighbouring blocks touch neighbouring addresses); chunk_vec > 0: block b streams its own
+// contiguous range of chunk_vec vectors, then the range of block b + gridDim.x, ... (the one-CTA-per-signal access pattern)
 __global__ void __launch_bounds__(256) mix_probe_kernel(const double2 *__restrict__ x, double2 *__restrict__ y,
-                                                        double2 *__restrict__ z, long long nvec) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-        const double2 v = x[i];
-        y[i] = make_double2(v.x - 1.0, v.y - 1.0);
-        z[i] = make_double2(v.x + 1.0, v.y + 1.0);
+                                                        double2 *__restrict__ z, long long nvec, long long chunk_vec) {
+    if (chunk_vec == 0) {
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+            const double2 v = x[i];
+            y[i] = make_double2(v.x - 1.0, v.y - 1.0);
+            z[i] = make_double2(v.x + 1.0, v.y + 1.0);
+        }
+    } else {
+        for (long long c0 = (long long)blockIdx.x * chunk_vec; c0 < nvec; c0 += (long long)gridDim.x * chunk_vec) {
+            const long long c1 = (c0 + chunk_vec < nvec) ? c0 + chunk_vec : nvec;
+            for (long long i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+                const double2 v = x[i];
+                y[i] = make_double2(v.x - 1.0, v.y - 1.0);
+                z[i] = make_double2(v.x + 1.0, v.y + 1.0);
+            }
+        }
     }
 }
-extern "C" int pyitd_probe_mixed_traffic(const void *x, void *y, void *z, int64_t n_doubles, int ctas, void *stream) {
-    if (!x || !y || !z || n_doubles < 2 || ctas < 1) return fail(PYITD_E_INVALID, "bad argument");
+extern "C" int pyitd_probe_mixed_traffic(const void *x, void *y, void *z, int64_t n_doubles, int ctas, int64_t chunk_doubles,
+                                         void *stream) {
+    if (!x || !y || !z || n_doubles < 2 || ctas < 1 || chunk_doubles < 0) return fail(PYITD_E_INVALID, "bad argument");
     mix_probe_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>((const double2 *)x, (double2 *)y, (double2 *)z,
-                                                                      n_doubles / 2);
+                                                                      n_doubles / 2, chunk_doubles / 2);
     CU(cudaGetLastError());
     return 0;
 }
