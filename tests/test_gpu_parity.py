@@ -529,6 +529,48 @@ def test_repeated_calls_reuse_the_plan_and_stay_exact():
             assert torch.equal(first.rows_of(s), again.rows_of(s))
 
 
+@pytest.mark.parametrize("path,S", [("stream", 5), ("strided", 1), ("strided", 3)])
+def test_input_pointer_that_is_not_16_byte_aligned(path, S, monkeypatch):
+    """The TMA bulk copies of the stream / strided kernels need 16-byte aligned rows.  A caller's x that is only
+    8-byte aligned must still decompose exactly: the scan and the first level fall back to the look-back kernels
+    (which leave complete knot tables), later levels read the library's own aligned carry."""
+    from pyitd_b200.itd import get_plan
+    monkeypatch.setenv("PYITD_FORCE_PATH", path)
+    monkeypatch.setenv("PYITD_GROUPS", "2")
+    pyitd_b200.clear_plan_cache()
+    rng = np.random.default_rng(350)
+    try:
+        n = 5000
+        x = _mixed_batch(rng, 6, n)[:S] if S > 1 else _mixed_batch(rng, 6, n)[3:4]
+        buf = torch.zeros(S * n + 1, dtype=torch.float64, device="cuda")
+        buf[1:] = torch.from_numpy(x).reshape(-1).cuda()
+        assert (buf.data_ptr() + 8) % 16 == 8
+        plan = get_plan(0, S, n, _capi.F64, 11, 2, _capi.OPT_BASELINES)
+        assert plan.path[0] == path
+        rows = plan.rows
+        rot = torch.empty((S, rows, n), dtype=torch.float64, device="cuda")
+        bas = torch.empty_like(rot)
+        ints = [torch.empty(S, dtype=torch.int32, device="cuda") for _ in range(4)]
+        counts = torch.empty((S, rows), dtype=torch.int32, device="cuda")
+        plan.decompose_device(buf.data_ptr() + 8, rot.data_ptr(), bas.data_ptr(), ints[0].data_ptr(), counts.data_ptr(),
+                              ints[1].data_ptr(), ints[2].data_ptr(), ints[3].data_ptr(),
+                              torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        for s in range(S):
+            try:
+                want = o.c_decompose(x[s], 11)
+            except o.OracleError as e:
+                assert int(ints[3][s]) & e.status
+                continue
+            nr = int(ints[0][s])
+            assert rot[s, :nr].cpu().numpy().tobytes() == want.rotations.tobytes(), s
+            nb = want.baselines.shape[0]
+            assert bas[s, :nb].cpu().numpy().tobytes() == want.baselines.tobytes(), s
+            assert int(ints[1][s]) == want.input_knots
+    finally:
+        pyitd_b200.clear_plan_cache()
+
+
 # ---------------------------------------------------------------------------------------------
 # fp32 variants
 # ---------------------------------------------------------------------------------------------
