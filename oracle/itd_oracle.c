@@ -393,3 +393,78 @@ int itd_oracle_decompose_batch_f32(const float *x, int64_t nsig, int64_t n, int 
                    n_rows, knot_counts, status, 0};
     return run_batch(&j, nthreads);
 }
+
+/* ==== SURVEY.md 8f rank 2: the time-domain cubic-spline baseline variant =====================
+ * numba_accelerated_itd.py:183-211 itd_baseline_extract_modified(x) -> baseline and
+ * MEITD.py:303-338 itd_baseline_extract(data) -> (rotation, baseline): same knots (the stencil of
+ * matlab_detect_peaks on x and -x, numba_accelerated_itd.py:17-59 == ITD.py:33-76), same knot
+ * baseline loop (numba_accelerated_itd.py:168-178 == ITD.py:106-110), but
+ *   - the end knots are the mean of the odd-reflected pad (numba_accelerated_itd.py:199-203,
+ *     MEITD.py:323-325): L_0 = ((2 x[0] - x[1]) + x[0]) / 2, L_{K+1} = (x[n-1] + (2 x[n-1] - x[n-2])) / 2;
+ *   - the baseline is the cubic spline through (tau_k, L_k), k = 0..K+1, evaluated at every sample
+ *     0..n-1 (custom_splrep / numba_splev, numba_accelerated_itd.py:70-165, :207-209).
+ * The spline itself lives in a THIRD-PARTY dependency: scipy.interpolate.splrep(x, y, k=3) with the
+ * default s = 0 (no weights), i.e. FITPACK curfit/fpcurf (scipy 1.18.1 in this image; the reference's
+ * environment.yml pins none): the interpolating cubic spline with not-a-knot end conditions (FITPACK
+ * places no knot at x[1] and x[m-2]).  Its published definition is restated here through the
+ * second-derivative ("moment") equations, Thomas-solved:
+ *      mu_i M_{i-1} + 2 M_i + lam_i M_{i+1} = 6 [(y_{i+1}-y_i)/h_i - (y_i-y_{i-1})/h_{i-1}] / (h_{i-1}+h_i),
+ *      not-a-knot: (M_1-M_0)/h_0 = (M_2-M_1)/h_1 and the mirror image at the right end.
+ * FITPACK solves the same interpolation problem by Givens rotations on the B-spline collocation
+ * matrix, so the two agree to rounding, not bit for bit: tests/test_oracle.py pins this function to
+ * the reference's output (tests/golden/spline_*.npz) at 1e-12 relative L2 (measured 2e-16 .. 4e-15).
+ * Needs K + 2 >= 4 points (splrep raises TypeError "m > k must hold" otherwise): status 16. */
+#define ITD_FEW_KNOTS 16
+int itd_oracle_spline_level_f64(const double *x, int64_t n, double *R, double *B, int64_t *K_out)
+{
+    if (n < 3) return ITD_TOO_SHORT;
+    for (int64_t i = 0; i < n; ++i)
+        if (!isfinite(x[i])) return ITD_NONFINITE;
+    int64_t *tau = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 2));
+    int64_t K = itd_oracle_find_knots_f64(x, n, tau + 1);
+    if (K_out) *K_out = K;
+    if (K < 2) { free(tau); return ITD_FEW_KNOTS; }
+    tau[0] = 0;
+    tau[K + 1] = n - 1;
+    const int64_t P = K + 2;
+    double *y = (double *)malloc(sizeof(double) * (size_t)P * 4);
+    double *M = y + P, *cp = M + P, *dp = cp + P;
+    y[0] = ((2.0 * x[0] - x[1]) + x[0]) / 2.0;
+    y[K + 1] = (x[n - 1] + (2.0 * x[n - 1] - x[n - 2])) / 2.0;
+    for (int64_t k = 1; k <= K; ++k) {
+        double w = (double)(tau[k] - tau[k - 1]) / (double)(tau[k + 1] - tau[k - 1]);
+        double d = x[tau[k + 1]] - x[tau[k - 1]];
+        y[k] = 0.5 * (x[tau[k - 1]] + w * d) + 0.5 * x[tau[k]];
+    }
+    /* rows i = 1..K of the moment equations, the two end rows with M_0 / M_{K+1} eliminated */
+    for (int64_t i = 1; i <= K; ++i) {
+        double h0 = (double)(tau[i] - tau[i - 1]), h1 = (double)(tau[i + 1] - tau[i]);
+        double a = h0 / (h0 + h1), c = h1 / (h0 + h1), b = 2.0;
+        double d = 6.0 * ((y[i + 1] - y[i]) / h1 - (y[i] - y[i - 1]) / h0) / (h0 + h1);
+        if (i == 1) { double r = h0 / h1; b += a * (1.0 + r); c -= a * r; a = 0.0; }
+        if (i == K) { double r = h1 / h0; b += c * (1.0 + r); a -= c * r; c = 0.0; }
+        if (i == 1) { cp[i] = c / b; dp[i] = d / b; }
+        else { double m = b - a * cp[i - 1]; cp[i] = c / m; dp[i] = (d - a * dp[i - 1]) / m; }
+    }
+    M[K] = dp[K];
+    for (int64_t i = K - 1; i >= 1; --i) M[i] = dp[i] - cp[i] * M[i + 1];
+    {
+        double r0 = (double)(tau[1] - tau[0]) / (double)(tau[2] - tau[1]);
+        double rK = (double)(tau[K + 1] - tau[K]) / (double)(tau[K] - tau[K - 1]);
+        M[0] = (1.0 + r0) * M[1] - r0 * M[2];
+        M[K + 1] = (1.0 + rK) * M[K] - rK * M[K - 1];
+    }
+    for (int64_t j = 0; j <= K; ++j) {
+        double h = (double)(tau[j + 1] - tau[j]);
+        double c1 = (y[j + 1] - y[j]) / h - h * (2.0 * M[j] + M[j + 1]) / 6.0;
+        double c2 = M[j] / 2.0, c3 = (M[j + 1] - M[j]) / (6.0 * h);
+        int64_t t1 = (j == K) ? n : tau[j + 1];          /* the last segment includes sample n-1 */
+        for (int64_t t = tau[j]; t < t1; ++t) {
+            double u = (double)(t - tau[j]);
+            B[t] = y[j] + u * (c1 + u * (c2 + u * c3));
+        }
+    }
+    for (int64_t t = 0; t < n; ++t) R[t] = x[t] - B[t];  /* MEITD.py:335 */
+    free(y); free(tau);
+    return ITD_OK;
+}

@@ -29,7 +29,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-ITD_OK, ITD_ZERO_DX, ITD_NONFINITE, ITD_TOO_SHORT, ITD_BAD_KNOTS = 0, 1, 2, 3, 8
+ITD_OK, ITD_ZERO_DX, ITD_NONFINITE, ITD_TOO_SHORT, ITD_BAD_KNOTS, ITD_FEW_KNOTS = 0, 1, 2, 3, 8, 16
 
 
 class OracleError(Exception):
@@ -38,7 +38,8 @@ class OracleError(Exception):
     def __init__(self, status: int):
         super().__init__({1: "zero delta-X (ZeroDivisionError, ITD.py:116)",
                           2: "non-finite input", 3: "signal shorter than 3 samples",
-                          8: "supplied knots are not strictly increasing inside [1, n-2]"}.get(status, str(status)))
+                          8: "supplied knots are not strictly increasing inside [1, n-2]",
+                          16: "fewer than 2 interior knots (splrep: m > k must hold)"}.get(status, str(status)))
         self.status = status
 
 
@@ -120,6 +121,62 @@ def np_extract_level(x: np.ndarray):
     return R, B, knots
 
 
+def np_spline_level(x: np.ndarray):
+    """SURVEY 8f rank 2 -- one level of the cubic-spline baseline variant: ``itd_baseline_extract``
+    of MEITD.py:303-338 (returns rotation and baseline) == ``itd_baseline_extract_modified`` of
+    numba_accelerated_itd.py:183-211 (returns the baseline).  Knots and knot baseline as in ITD.py; end
+    knots = mean of the odd-reflected pad (MEITD.py:323-325); baseline = ``splev(arange(n),
+    splrep(tau, L, k=3))`` (MEITD.py:330-333), scipy's FITPACK interpolating spline with not-a-knot
+    ends, restated through the moment equations (see oracle/itd_oracle.c).  float64 only.
+    Returns ``(R, B, knots)``."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = x.shape[0]
+    if n < 3:
+        raise OracleError(ITD_TOO_SHORT)
+    if not np.all(np.isfinite(x)):
+        raise OracleError(ITD_NONFINITE)
+    knots = np_find_knots(x)
+    K = knots.shape[0]
+    if K < 2:
+        raise OracleError(ITD_FEW_KNOTS)
+    tau = np.concatenate(([0], knots, [n - 1])).astype(np.int64)
+    X = x[tau]
+    y = np.empty(K + 2)
+    y[0] = ((2.0 * x[0] - x[1]) + x[0]) / 2.0
+    y[-1] = (x[-1] + (2.0 * x[-1] - x[-2])) / 2.0
+    w = (tau[1:-1] - tau[:-2]) / (tau[2:] - tau[:-2])
+    y[1:-1] = 0.5 * (X[:-2] + w * (X[2:] - X[:-2])) + 0.5 * X[1:-1]
+    h = np.diff(tau).astype(np.float64)
+    a = h[:-1] / (h[:-1] + h[1:])
+    c = h[1:] / (h[:-1] + h[1:])
+    b = np.full(K, 2.0)
+    d = 6.0 * ((y[2:] - y[1:-1]) / h[1:] - (y[1:-1] - y[:-2]) / h[:-1]) / (h[:-1] + h[1:])
+    r0, rK = h[0] / h[1], h[K] / h[K - 1]
+    b[0] += a[0] * (1.0 + r0); c[0] -= a[0] * r0; a[0] = 0.0
+    b[K - 1] += c[K - 1] * (1.0 + rK); a[K - 1] -= c[K - 1] * rK; c[K - 1] = 0.0
+    cp = np.empty(K); dp = np.empty(K)
+    cp[0] = c[0] / b[0]; dp[0] = d[0] / b[0]
+    for i in range(1, K):
+        m = b[i] - a[i] * cp[i - 1]
+        cp[i] = c[i] / m
+        dp[i] = (d[i] - a[i] * dp[i - 1]) / m
+    M = np.empty(K + 2)
+    M[K] = dp[K - 1]
+    for i in range(K - 2, -1, -1):
+        M[i + 1] = dp[i] - cp[i] * M[i + 2]
+    M[0] = (1.0 + r0) * M[1] - r0 * M[2]
+    M[K + 1] = (1.0 + rK) * M[K] - rK * M[K - 1]
+    t = np.arange(n)
+    seg = np.minimum(np.searchsorted(tau, t, side="right") - 1, K)
+    u = (t - tau[seg]).astype(np.float64)
+    hj = h[seg]
+    c1 = (y[seg + 1] - y[seg]) / hj - hj * (2.0 * M[seg] + M[seg + 1]) / 6.0
+    c2 = M[seg] / 2.0
+    c3 = (M[seg + 1] - M[seg]) / (6.0 * hj)
+    B = y[seg] + u * (c1 + u * (c2 + u * c3))
+    return x - B, B, knots
+
+
 @dataclass
 class OracleResult:
     rotations: np.ndarray        # (n_rows, N): proper rotations then the final trend row
@@ -198,6 +255,8 @@ def c_lib() -> ctypes.CDLL:
             f.restype = ci
             f.argtypes = [vp, i64, i64, ci, ci, vp, vp, vp, vp, vp, ci]
         lib.itd_oracle_max_threads.restype = ci
+        lib.itd_oracle_spline_level_f64.restype = ci
+        lib.itd_oracle_spline_level_f64.argtypes = [vp, i64, vp, vp, vp]
         _LIB = lib
     return _LIB
 
@@ -251,6 +310,18 @@ def c_extract_with_knots(x: np.ndarray, knots: np.ndarray):
     if st != ITD_OK:
         raise OracleError(st)
     return R, B
+
+
+def c_spline_level(x: np.ndarray):
+    """C restatement of the spline-baseline level (see np_spline_level).  Returns ``(R, B, K)``."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    R = np.empty_like(x)
+    B = np.empty_like(x)
+    K = ctypes.c_int64(0)
+    st = c_lib().itd_oracle_spline_level_f64(_ptr(x), x.shape[0], _ptr(R), _ptr(B), ctypes.byref(K))
+    if st != ITD_OK:
+        raise OracleError(st)
+    return R, B, int(K.value)
 
 
 def c_decompose(x: np.ndarray, max_iteration: int = 11, min_extrema: int = 2) -> OracleResult:
