@@ -159,6 +159,25 @@ PYITD_API int pyitd_extract_with_knots_device(pyitd_plan *plan, const void *x, c
                                     void *rotation, void *baseline, int32_t *status, void *stream);
 
 /*
+ * one level of the cubic-spline baseline variant -- replaces
+ * itd_baseline_extract(data) -> (rotation, baseline) of MEITD.py:303-338 and
+ * itd_baseline_extract_modified(x) -> baseline of numba_accelerated_itd.py:183-211.  Knots and knot baseline as in
+ * ITD.py, end knots from the odd-reflected pad (MEITD.py:323-325), baseline = the interpolating cubic spline with
+ * not-a-knot ends through (tau_k, L_k) (scipy splrep(k=3) + splev in the reference, MEITD.py:330-333), evaluated at
+ * every sample including the last; rotation = x - baseline (MEITD.py:335).  PYITD_F64 and PYITD_F32_MIXED plans.
+ *   rotation   [n_signals, n_samples] or NULL (the numba variant returns the baseline only)
+ *   baseline   [n_signals, n_samples]
+ *   knot_count [n_signals] int32 = interior knots of x
+ *   min_knots  signals with fewer interior knots get baseline = x, rotation = 0 (10 in numba_accelerated_itd.py:
+ *              188-191; values below 2 act as 2)
+ *   status     PYITD_ST_FEW_KNOTS when a signal has fewer than 2 interior knots (the reference's splrep raises
+ *              TypeError "m > k must hold"); PYITD_ST_NONFINITE as elsewhere
+ */
+#define PYITD_ST_FEW_KNOTS 16
+PYITD_API int pyitd_extract_spline_device(pyitd_plan *plan, const void *x, void *rotation, void *baseline,
+                                int32_t *knot_count, int32_t *status, int min_knots, void *stream);
+
+/*
  * Replaces detect_peaks (ITD.py:33-76) and the knot merge around it (ITD.py:87-88, :97).
  *   kinds      PYITD_KNOTS_VALLEYS = detect_peaks(x), PYITD_KNOTS_PEAKS = detect_peaks(-x),
  *              PYITD_KNOTS_BOTH = sort(unique(hstack(both))) = the knot set of one level

@@ -8,6 +8,9 @@ from ._capi import PyITDLibraryError, Plan  # noqa: F401
 from .itd import (ITD, ITDResult, clear_plan_cache, decompose, detect_peaks, extract_level,  # noqa: F401
                   extract_with_knots, find_knots, itd_baseline_extract)
 
-__all__ = ["ITD", "ITDResult", "decompose", "detect_peaks", "itd_baseline_extract", "extract_level",
+from .spline import extract_spline, itd_baseline_extract_modified, itd_baseline_extract_spline  # noqa: F401
+
+__all__ = ["extract_spline", "itd_baseline_extract_spline", "itd_baseline_extract_modified",
+           "ITD", "ITDResult", "decompose", "detect_peaks", "itd_baseline_extract", "extract_level",
            "find_knots", "extract_with_knots", "Plan", "PyITDLibraryError", "clear_plan_cache"]
 __version__ = "0.1.0"

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libpyitd_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "pyitd_b200.h")
 
 F64, F32_MIXED, F32 = 0, 1, 2
-ST_ZERO_DX, ST_NONFINITE, ST_TOO_SHORT, ST_BAD_KNOTS = 1, 2, 4, 8
+ST_ZERO_DX, ST_NONFINITE, ST_TOO_SHORT, ST_BAD_KNOTS, ST_FEW_KNOTS = 1, 2, 4, 8, 16
 STOP_KNOTS, STOP_ITER = 1, 2
 OPT_BASELINES, OPT_ZERO_TAIL = 1, 2
 KNOTS_VALLEYS, KNOTS_PEAKS, KNOTS_BOTH = 1, 2, 3
@@ -90,6 +90,8 @@ def lib() -> ctypes.CDLL:
     L.pyitd_extract_level_device.argtypes = [vp] * 7
     L.pyitd_extract_with_knots_device.restype = ci
     L.pyitd_extract_with_knots_device.argtypes = [vp, vp, vp, i64, vp, i64, vp, vp, vp, vp]
+    L.pyitd_extract_spline_device.restype = ci
+    L.pyitd_extract_spline_device.argtypes = [vp, vp, vp, vp, vp, vp, ci, vp]
     L.pyitd_find_knots_device.restype = ci
     L.pyitd_find_knots_device.argtypes = [vp, vp, ci, vp, i64, vp, vp, vp]
     _lib = L
@@ -190,6 +192,10 @@ class Plan:
         check(self._L.pyitd_extract_with_knots_device(self.handle, x, knots, capacity, knot_count, n_knot_rows,
                                                       rotation, baseline, status, stream),
               "pyitd_extract_with_knots_device")
+
+    def extract_spline_device(self, x, rotation, baseline, knot_count, status, min_knots, stream) -> None:
+        check(self._L.pyitd_extract_spline_device(self.handle, x, rotation, baseline, knot_count, status,
+                                                  int(min_knots), stream), "pyitd_extract_spline_device")
 
     def find_knots_device(self, x, kinds, knots, capacity, knot_count, status, stream) -> None:
         check(self._L.pyitd_find_knots_device(self.handle, x, kinds, knots, capacity, knot_count, status,

@@ -15,6 +15,7 @@
 #include "itd_stream.cuh"
 #include "itd_strided.cuh"
 #include "itd_resident.cuh"
+#include "itd_spline.cuh"
 
 using namespace pyitd;
 
@@ -975,6 +976,54 @@ extern "C" int pyitd_extract_with_knots_device(pyitd_plan *pl, const void *x, co
     CU(launch_level(pl, lp, true, st, pl->S));
     pl->launches++;
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// spline-baseline variant: knot scan, truncated-PCR coefficient pass, evaluation pass
+// ---------------------------------------------------------------------------------------------
+template <typename InT, typename CarryT, typename OutT>
+static cudaError_t launch_spline_t(const SplineParams &p, long long S, cudaStream_t st) {
+    auto k = spline_level_kernel<InT, CarryT, OutT>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplineSmem));
+    if (e != cudaSuccess) return e;
+    k<<<(unsigned)(S * p.parts), kSplThreads, sizeof(SplineSmem), st>>>(p);
+    return cudaGetLastError();
+}
+
+extern "C" int pyitd_extract_spline_device(pyitd_plan *pl, const void *x, void *rotation, void *baseline,
+                                           int32_t *knot_count, int32_t *status, int min_knots, void *stream) {
+    if (!pl || !x || !baseline || !knot_count || !status) return fail(PYITD_E_INVALID, "null argument");
+    if (pl->dtype == PYITD_F32)
+        return fail(PYITD_E_INVALID, "the spline variant computes in float64: use a PYITD_F64 or PYITD_F32_MIXED plan");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(pl->device));
+    if (int rc = ensure_workspace(pl)) return rc;
+    pl->launches = 0;
+    pl->events_used = 0;
+    CU(cudaMemsetAsync(status, 0, (size_t)pl->S * sizeof(int), st));
+    if (int rc = run_scan(pl, x, status, knot_count, st)) return rc;
+    SplineParams sp;
+    sp.x = x;
+    sp.rot = rotation;
+    sp.bas = baseline;
+    sp.tab = pl->table[0];
+    sp.status = status;
+    sp.n = pl->n;
+    sp.tiles = pl->tiles;
+    sp.tile = pl->tile;
+    sp.min_knots = min_knots < 2 ? 2 : min_knots;
+    // one CTA per signal walks its knot windows when there are enough signals to fill the device (4 CTAs per SM),
+    // else the windows of a signal are spread over several CTAs
+    const long long max_parts = ((long long)pl->n + kSplUseful - 1) / kSplUseful;
+    long long parts = (148ll * 8 + pl->S - 1) / pl->S;
+    if (parts > max_parts) parts = max_parts;
+    if (parts < 1) parts = 1;
+    sp.parts = (int)parts;
+    // event timing: launch 0 = knot scan, 1 = spline level kernel
+    if (pl->dtype == PYITD_F64) CU((launch_spline_t<double, double, double>(sp, pl->S, st)));
+    else CU((launch_spline_t<float, double, float>(sp, pl->S, st)));
+    pl->launches++;
+    return mark(pl, st);
 }
 
 extern "C" int pyitd_find_knots_device(pyitd_plan *pl, const void *x, int kinds, int32_t *knots,

@@ -1,0 +1,283 @@
+// itd_spline.cuh -- SURVEY.md 8f rank 2: one level of the cubic-spline baseline variant of ITD.
+//
+// Reference (paths relative to /root/reference): itd_baseline_extract of MEITD.py:303-338 (rotation and
+// baseline) and itd_baseline_extract_modified of numba_accelerated_itd.py:183-211 (baseline only).  Knots and
+// the knot baseline L_k are those of ITD.py (same stencil, same Frei-Osorio formula); the end knots are the
+// mean of the odd-reflected pad (MEITD.py:323-325); the baseline is the interpolating cubic spline with
+// not-a-knot ends through (tau_k, L_k) -- scipy.interpolate.splrep(k=3, s=0) + splev in the reference
+// (MEITD.py:330-333) -- evaluated at every sample.
+//
+// ONE kernel after the ordinary knot scan (which leaves tau / X_k / flag mask / per-tile prefix):
+//
+//   spline_level_kernel  walks a signal in WINDOWS of 896 knots.  Per window:
+//     1. the knot slice (tau, X) plus 64 halo knots either side is staged in shared memory; one thread per knot
+//        rebuilds L_k, 1/h_k and the segment slopes;
+//     2. the tridiagonal moment system  mu_i M_{i-1} + 2 M_i + lam_i M_{i+1} = d_i  is solved by TRUNCATED
+//        PARALLEL CYCLIC REDUCTION in shared memory.  The rows are strictly diagonally dominant (off-diagonal
+//        sum <= 1/2 of the diagonal), so after s reduction steps the remaining coupling to rows 2^s away is
+//        below (1/2)^(2^s): at most six steps (reach 63 knots, residual coupling < 5.5e-20) decouple every row.
+//        A window therefore depends on no other window: the solve is streaming and embarrassingly parallel in
+//        the knot index, unlike the sequential Thomas sweep of the CPU restatement (or FITPACK's QR sweep);
+//     3. the four power coefficients of the window's segments stay in shared memory and the samples of those
+//        segments are evaluated straight from them: segment id = prefix popcount of the flag mask, Horner,
+//        R = x - B, one coalesced load and two coalesced stores per sample.
+//
+// HBM traffic per sample: x read by the scan and by this kernel (2 s), R and B written (2 s); per knot 12 B of
+// (tau, X_k) written by the scan and read here.  Spline coefficients never leave the chip.
+// No tensor cores: nothing is a contraction.
+#pragma once
+
+#include "itd_kernels.cuh"
+
+namespace pyitd {
+
+constexpr int kStFewKnots = 16;
+constexpr int kSplSlots = 1024;                       // rows of one PCR window held in shared memory
+constexpr int kSplHalo = 64;                          // >= 1 + 2 + 4 + 8 + 16 + 32
+constexpr int kSplUseful = kSplSlots - 2 * kSplHalo;  // rows a window is responsible for
+constexpr int kSplThreads = 256;
+constexpr int kSplSteps = 6;
+
+struct SplineParams {
+    const void *x;       // [S, N] input type
+    void *rot;           // [S, N] output type or null
+    void *bas;           // [S, N] output type
+    KnotTable tab;       // of x, from the knot scan
+    int *status;
+    int n, tiles, tile;  // tile = samples per tbase entry
+    int min_knots;       // signals with fewer interior knots keep B = x, R = 0 (numba_accelerated_itd.py:188-191)
+    int parts;           // CTAs per signal
+};
+
+struct SplineSmem {
+    // knot-indexed arrays: entry m is knot k = base - 2 + m of the window (base = unknown index of PCR slot 0)
+    int ts[kSplSlots + 4];        // tau_k
+    double xs[kSplSlots + 4];     // X_k, then the segment slope (L_{k+1} - L_k) / h_k, then the coefficient c1
+    double ys[kSplSlots + 4];     // L_k (= coefficient c0)
+    double ih[kSplSlots + 4];     // 1 / h_k, h_k = tau_{k+1} - tau_k
+    // slot-indexed (slot q = entry m - 2): PCR rows with a unit diagonal; afterwards r = M, a = c2, c = c3
+    double a[kSplSlots], c[kSplSlots], r[kSplSlots];
+};
+
+// 1 / b to ~1 ulp: MUFU seed (about 20 bits) + two Newton steps.  The spline solve is held to 1e-9 against the
+// reference's FITPACK solve, not to bit equality, so the ~40-instruction IEEE division is not needed here.
+__device__ __forceinline__ double fast_rcp(double b) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(b));
+    double e = __fma_rn(-b, x, 1.0);
+    x = __fma_rn(x, e, x);
+    e = __fma_rn(-b, x, 1.0);
+    return __fma_rn(x, e, x);
+}
+
+template <typename InT, typename CarryT, typename OutT>
+__global__ void __launch_bounds__(kSplThreads, 4) spline_level_kernel(const SplineParams p) {
+    extern __shared__ __align__(16) unsigned char spl_smem_raw[];
+    SplineSmem &sm = *reinterpret_cast<SplineSmem *>(spl_smem_raw);
+    const int sig = blockIdx.x / p.parts, part = blockIdx.x % p.parts;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = p.tab.kcount[sig];
+    const int n = p.n;
+    const InT *x = reinterpret_cast<const InT *>(p.x) + (long long)sig * n;
+    OutT *rot = p.rot ? reinterpret_cast<OutT *>(p.rot) + (long long)sig * n : nullptr;
+    OutT *bas = reinterpret_cast<OutT *>(p.bas) + (long long)sig * n;
+
+    if (K < 2 || K < p.min_knots) {
+        // numba_accelerated_itd.py:188-191: too few extrema -> the input is returned as the baseline; with fewer than
+        // two knots the reference's splrep raises (m > k must hold): reported through the status word
+        if (part == 0 && tid == 0 && K < 2) atomicOr(p.status + sig, kStFewKnots);
+        for (int t = part * kSplThreads + tid; t < n; t += p.parts * kSplThreads) {
+            bas[t] = (OutT)__ldg(x + t);
+            if (rot) rot[t] = (OutT)0;
+        }
+        return;
+    }
+    const int *tau = p.tab.tau + (long long)sig * p.tab.kstride;
+    const CarryT *xk = reinterpret_cast<const CarryT *>(p.tab.xk) + (long long)sig * p.tab.kstride;
+    const unsigned *mask = p.tab.mask + (long long)sig * p.tab.mstride;
+    const int *tbase = p.tab.tbase + (long long)sig * (p.tiles + 1);
+
+    // end knots: mean of the odd-reflected pad (MEITD.py:323-325): pad = 2 * edge - neighbour
+    const double x0 = (double)__ldg(x), x1 = (double)__ldg(x + 1);
+    const double xn1 = (double)__ldg(x + n - 1), xn2 = (double)__ldg(x + n - 2);
+    const double y_first = __dmul_rn(__dadd_rn(__dsub_rn(__dmul_rn(2.0, x0), x1), x0), 0.5);
+    const double y_last = __dmul_rn(__dadd_rn(xn1, __dsub_rn(__dmul_rn(2.0, xn1), xn2)), 0.5);
+    constexpr int M = kSplSlots + 4;
+
+    for (int win = part; win * kSplUseful < K; win += p.parts) {
+        // PCR slot q holds unknown (interior knot) i = base + q = knot entry m = q + 2; rows outside [1, K] are
+        // identity rows
+        const int base = 1 + win * kSplUseful - kSplHalo;
+        __syncthreads();                                   // previous window's readers are done
+        for (int m = tid; m < M; m += kSplThreads) {
+            const int k = base - 2 + m;
+            const bool in = (k >= 0 && k <= K + 1);
+            sm.ts[m] = in ? __ldg(tau + k) : 0;
+            sm.xs[m] = in ? (double)__ldg(xk + k) : 0.0;
+        }
+        __syncthreads();
+        for (int m = tid; m < M; m += kSplThreads) {
+            const int k = base - 2 + m;
+            double y = 0.0, ih = 0.0;
+            if (k == 0) y = y_first;
+            else if (k == K + 1) y = y_last;
+            else if (k >= 1 && k <= K) {
+                // L_k of ITD.py:106-110
+                const double w = (double)(sm.ts[m] - sm.ts[m - 1]) * fast_rcp((double)(sm.ts[m + 1] - sm.ts[m - 1]));
+                y = 0.5 * (sm.xs[m - 1] + w * (sm.xs[m + 1] - sm.xs[m - 1])) + 0.5 * sm.xs[m];
+            }
+            if (k >= 0 && k <= K) ih = fast_rcp((double)(sm.ts[m + 1] - sm.ts[m]));
+            sm.ys[m] = y;
+            sm.ih[m] = ih;
+        }
+        __syncthreads();
+        for (int m = tid; m < M - 1; m += kSplThreads)     // slopes overwrite X_k, which nobody reads any more
+            sm.xs[m] = (sm.ys[m + 1] - sm.ys[m]) * sm.ih[m];
+        __syncthreads();
+        // rows of the moment equations  mu M_{i-1} + 2 M_i + lam M_{i+1} = 6 (s_i - s_{i-1}) / (h_{i-1} + h_i),
+        // normalised to a unit diagonal; the end rows carry the not-a-knot conditions (M_0, M_{K+1} eliminated)
+        for (int q = tid; q < kSplSlots; q += kSplThreads) {
+            const int i = base + q, m = q + 2;
+            double a = 0.0, c = 0.0, r = 0.0;
+            if (i >= 1 && i <= K) {
+                const double h0 = (double)(sm.ts[m] - sm.ts[m - 1]);       // tau_i - tau_{i-1}
+                const double h1 = (double)(sm.ts[m + 1] - sm.ts[m]);       // tau_{i+1} - tau_i
+                const double ihs = fast_rcp(h0 + h1);
+                a = h0 * ihs;
+                c = h1 * ihs;
+                r = 6.0 * (sm.xs[m] - sm.xs[m - 1]) * ihs;
+                double inv = 0.5;
+                if (i == 1 || i == K) {
+                    double b = 2.0;
+                    if (i == 1) {
+                        const double rho = h0 * sm.ih[m];
+                        b += a * (1.0 + rho);
+                        c -= a * rho;
+                        a = 0.0;
+                    }
+                    if (i == K) {
+                        const double rho = h1 * sm.ih[m - 1];
+                        b += c * (1.0 + rho);
+                        a -= c * rho;
+                        c = 0.0;
+                    }
+                    inv = fast_rcp(b);
+                }
+                a *= inv;
+                c *= inv;
+                r *= inv;
+            }
+            sm.a[q] = a;
+            sm.c[q] = c;
+            sm.r[q] = r;
+        }
+        __syncthreads();
+        // truncated parallel cyclic reduction, in place through registers; stops as soon as every remaining
+        // coupling is below 1e-13 -- four orders of magnitude inside the 1e-9 parity
+        // tolerance -- which takes five steps on evenly spaced knots and at most six ((1/2)^(2^s) bound)
+#pragma unroll 1
+        for (int s = 0; s < kSplSteps; ++s) {
+            const int d = 1 << s;
+            double na[4], nc[4], nr[4];
+            bool big = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int q = tid + j * kSplThreads;
+                const double k1 = sm.a[q], k2 = sm.c[q];
+                double am = 0.0, cm = 0.0, rm = 0.0, ap = 0.0, cp = 0.0, rp = 0.0;
+                if (q - d >= 0) { am = sm.a[q - d]; cm = sm.c[q - d]; rm = sm.r[q - d]; }
+                if (q + d < kSplSlots) { ap = sm.a[q + d]; cp = sm.c[q + d]; rp = sm.r[q + d]; }
+                const double inv = fast_rcp(1.0 - k1 * cm - k2 * ap);
+                na[j] = -(k1 * am) * inv;
+                nc[j] = -(k2 * cp) * inv;
+                nr[j] = (sm.r[q] - k1 * rm - k2 * rp) * inv;
+                big |= (fabs(na[j]) > 1e-13) || (fabs(nc[j]) > 1e-13);
+            }
+            const int more = __syncthreads_or(big);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int q = tid + j * kSplThreads;
+                sm.a[q] = na[j];
+                sm.c[q] = nc[j];
+                sm.r[q] = nr[j];
+            }
+            __syncthreads();
+            if (!more) break;
+        }
+        // M_i = r[i] on the decoupled rows (slots [halo - 1, slots - halo] are exact to < 5.5e-20 relative).
+        // Segments of this window: j = j_lo .. j_hi; the coefficients replace dead arrays in place
+        // (c1 over the slope of the same segment, c2 / c3 over a / c of the same slot).
+        const int j_lo = (win == 0) ? 0 : win * kSplUseful + 1;
+        const int j_hi = min(K, win * kSplUseful + kSplUseful);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int q = tid + jj * kSplThreads;
+            const int slot = kSplHalo - 1 + q;
+            const int j = base + slot, m = slot + 2;
+            if (q > kSplUseful || j < j_lo || j > j_hi) continue;
+            const double h = (double)(sm.ts[m + 1] - sm.ts[m]);
+            double Mj, Mj1;
+            if (j == 0) {
+                const double rho = h * sm.ih[m + 1];                       // h_0 / h_1
+                Mj = (1.0 + rho) * sm.r[slot + 1] - rho * sm.r[slot + 2];
+            } else {
+                Mj = sm.r[slot];
+            }
+            if (j == K) {
+                const double rho = h * sm.ih[m - 1];                       // h_K / h_{K-1}
+                Mj1 = (1.0 + rho) * sm.r[slot] - rho * sm.r[slot - 1];
+            } else {
+                Mj1 = sm.r[slot + 1];
+            }
+            const double sixth = 1.0 / 6.0;
+            sm.xs[m] = sm.xs[m] - h * (2.0 * Mj + Mj1) * sixth;            // only this thread touches xs[m], a / c[slot]
+            sm.a[slot] = 0.5 * Mj;
+            sm.c[slot] = (Mj1 - Mj) * sm.ih[m] * sixth;
+        }
+        __syncthreads();
+
+        // evaluation of the window's samples: [tau_{j_lo}, tau_{j_hi + 1}), plus sample n-1 in the last window.
+        // Blocks of 256 samples aligned to 256: one sample per thread, one flag word per warp.
+        const int t_lo = sm.ts[j_lo - (base - 2)];
+        const int t_hi = (j_hi == K) ? n : sm.ts[j_hi + 1 - (base - 2)];
+        constexpr int UN = 4;                              // blocks in flight per thread
+        for (int tb = (t_lo & ~(kSplThreads - 1)); tb < t_hi; tb += UN * kSplThreads) {
+            double xv[UN];
+            int mm[UN], tt[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int tw = tb + u * kSplThreads + warp * 32;   // first sample of this warp's flag word
+                tt[u] = -1;
+                xv[u] = 0.0;
+                mm[u] = 2;
+                if (tw >= t_hi || tw + 31 < t_lo) continue;        // warp-uniform
+                // interior knots before the word: per-tile prefix + the words of the tile before it
+                const int wword = tw >> 5;
+                const int tile = tw / p.tile;
+                int cnt = 0;
+                for (int w = ((tile * p.tile) >> 5) + lane; w < wword; w += 32) cnt += __popc(__ldg(mask + w));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                const int t = tw + lane;
+                if (t < t_lo || t >= t_hi) continue;
+                xv[u] = (double)__ldg(x + t);
+                const unsigned mw = __ldg(mask + wword);
+                int j = __ldg(tbase + tile) + cnt + __popc(mw & (0xffffffffu >> (31 - lane)));   // interior knots <= t
+                if (j > K) j = K;
+                mm[u] = j - (base - 2);
+                tt[u] = t;
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                if (tt[u] < 0) continue;
+                const int m = mm[u], t = tt[u];
+                const double uu = (double)(t - sm.ts[m]);
+                const double b = sm.ys[m] + uu * (sm.xs[m] + uu * (sm.a[m - 2] + uu * sm.c[m - 2]));
+                __stcs(bas + t, (OutT)b);
+                if (rot) __stcs(rot + t, (OutT)(xv[u] - b));       // MEITD.py:335
+            }
+        }
+    }
+}
+
+}  // namespace pyitd
