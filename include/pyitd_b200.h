@@ -178,6 +178,32 @@ PYITD_API int pyitd_extract_spline_device(pyitd_plan *plan, const void *x, void 
                                 int32_t *knot_count, int32_t *status, int min_knots, void *stream);
 
 /*
+ * the 2-D "crossways" ensemble ITD of siftED2D.ipynb (code cell 1, raw JSON :233-278).
+ *
+ * pyitd_crossways_device replaces crossways_itd_baseline_extract(data) for a batch of images: the spline baseline
+ * (pyitd_extract_spline_device, min_knots = 10 in the notebook) along every row, along every column, then along the
+ * rows of the column result and the columns of the row result; out = (lengthwise + crosswise) / 2.
+ *   row_plan   plan for (n_images * height) signals of width samples
+ *   col_plan   plan for (n_images * width) signals of height samples   (same dtype and device)
+ *   images,out [n_images, height, width] C-contiguous, plan dtype
+ *   scratch    pyitd_crossways_scratch_bytes(...) bytes of device memory
+ *
+ * pyitd_ensemble2d_device replaces retrieve_statistical_image_component(data) with the noise draws SUPPLIED
+ * (the notebook draws them from numba's unseeded generator): members data + v_e and data - v_e for e < draws,
+ * crossways on each, lowpass = mean over e of the pair means.  totalextract2d = [data - lowpass, lowpass].
+ *   image [height, width]; noise [draws, height, width]; lowpass [height, width]
+ *   row_plan / col_plan sized for n_images = 2 * draws; scratch pyitd_ensemble2d_scratch_bytes(...) bytes
+ * Non-finite input is not supported (no status is reported here).
+ */
+PYITD_API int64_t pyitd_crossways_scratch_bytes(const pyitd_plan *row_plan, int64_t n_images, int64_t height, int64_t width);
+PYITD_API int pyitd_crossways_device(pyitd_plan *row_plan, pyitd_plan *col_plan, const void *images, void *out, void *scratch,
+                           int64_t n_images, int64_t height, int64_t width, int min_knots, void *stream);
+PYITD_API int64_t pyitd_ensemble2d_scratch_bytes(const pyitd_plan *row_plan, int64_t draws, int64_t height, int64_t width);
+PYITD_API int pyitd_ensemble2d_device(pyitd_plan *row_plan, pyitd_plan *col_plan, const void *image, const void *noise,
+                            void *lowpass, void *scratch, int64_t draws, int64_t height, int64_t width, int min_knots,
+                            void *stream);
+
+/*
  * Replaces detect_peaks (ITD.py:33-76) and the knot merge around it (ITD.py:87-88, :97).
  *   kinds      PYITD_KNOTS_VALLEYS = detect_peaks(x), PYITD_KNOTS_PEAKS = detect_peaks(-x),
  *              PYITD_KNOTS_BOTH = sort(unique(hstack(both))) = the knot set of one level

@@ -177,6 +177,51 @@ def np_spline_level(x: np.ndarray):
     return x - B, B, knots
 
 
+# --------------------------------------------------------------------------------------------
+# 2-D crossways ensemble ITD (siftED2D.ipynb code cell 1, raw JSON :233-278)
+# --------------------------------------------------------------------------------------------
+def spline_baseline_min10(x: np.ndarray, level=None) -> np.ndarray:
+    """The notebook's 1-D ``itd_baseline_extract`` (== numba_accelerated_itd.py:183-211): the spline baseline,
+    or the input itself when it has fewer than 10 extrema."""
+    level = level or c_spline_level
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    if np_find_knots(x).shape[0] < 10:
+        return x.copy()
+    return level(x)[1]
+
+
+def crossways(data: np.ndarray, level=None) -> np.ndarray:
+    """``crossways_itd_baseline_extract`` (siftED2D.ipynb cell 1): rows, columns, rows of the column result,
+    columns of the row result, mean of the two."""
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    H, W = data.shape
+    lengthwise = np.zeros((H, W))
+    crosswise = np.zeros((H, W))
+    for r in range(H):
+        lengthwise[r, :] = spline_baseline_min10(data[r, :], level)
+    for c in range(W):
+        crosswise[:, c] = spline_baseline_min10(data[:, c], level)
+    for r in range(H):
+        crosswise[r, :] = spline_baseline_min10(crosswise[r, :], level)
+    for c in range(W):
+        lengthwise[:, c] = spline_baseline_min10(lengthwise[:, c], level)
+    return (lengthwise + crosswise) / 2.0
+
+
+def ensemble2d(data: np.ndarray, noise: np.ndarray, level=None) -> np.ndarray:
+    """``retrieve_statistical_image_component`` (siftED2D.ipynb cell 1) with the noise draws ``noise[e]`` given
+    instead of drawn: members ``v + data`` and ``v * -1 + data``, crossways on each, pair means, mean over draws
+    accumulated in draw order.  Returns the low-pass image; ``totalextract2d`` is ``[data - lowpass, lowpass]``."""
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    draws = noise.shape[0]
+    x = np.zeros_like(data)
+    for e in range(draws):
+        a = crossways(noise[e] + data, level)
+        b = crossways((noise[e] * -1) + data, level)
+        x += (a + b) / 2.0
+    return x / (draws * 1.0)
+
+
 @dataclass
 class OracleResult:
     rotations: np.ndarray        # (n_rows, N): proper rotations then the final trend row

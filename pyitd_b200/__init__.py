@@ -10,7 +10,11 @@ from .itd import (ITD, ITDResult, clear_plan_cache, decompose, detect_peaks, ext
 
 from .spline import extract_spline, itd_baseline_extract_modified, itd_baseline_extract_spline  # noqa: F401
 
-__all__ = ["extract_spline", "itd_baseline_extract_spline", "itd_baseline_extract_modified",
+from .sift2d import (crossways_batch, crossways_itd_baseline_extract, retrieve_statistical_image_component,  # noqa: F401
+                     totalextract2d)
+
+__all__ = ["crossways_batch", "crossways_itd_baseline_extract", "retrieve_statistical_image_component", "totalextract2d",
+           "extract_spline", "itd_baseline_extract_spline", "itd_baseline_extract_modified",
            "ITD", "ITDResult", "decompose", "detect_peaks", "itd_baseline_extract", "extract_level",
            "find_knots", "extract_with_knots", "Plan", "PyITDLibraryError", "clear_plan_cache"]
 __version__ = "0.1.0"

@@ -92,6 +92,14 @@ def lib() -> ctypes.CDLL:
     L.pyitd_extract_with_knots_device.argtypes = [vp, vp, vp, i64, vp, i64, vp, vp, vp, vp]
     L.pyitd_extract_spline_device.restype = ci
     L.pyitd_extract_spline_device.argtypes = [vp, vp, vp, vp, vp, vp, ci, vp]
+    L.pyitd_crossways_scratch_bytes.restype = i64
+    L.pyitd_crossways_scratch_bytes.argtypes = [vp, i64, i64, i64]
+    L.pyitd_crossways_device.restype = ci
+    L.pyitd_crossways_device.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, ci, vp]
+    L.pyitd_ensemble2d_scratch_bytes.restype = i64
+    L.pyitd_ensemble2d_scratch_bytes.argtypes = [vp, i64, i64, i64]
+    L.pyitd_ensemble2d_device.restype = ci
+    L.pyitd_ensemble2d_device.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, ci, vp]
     L.pyitd_find_knots_device.restype = ci
     L.pyitd_find_knots_device.argtypes = [vp, vp, ci, vp, i64, vp, vp, vp]
     _lib = L

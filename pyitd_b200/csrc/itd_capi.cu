@@ -16,6 +16,7 @@
 #include "itd_strided.cuh"
 #include "itd_resident.cuh"
 #include "itd_spline.cuh"
+#include "itd_sift2d.cuh"
 
 using namespace pyitd;
 
@@ -990,16 +991,11 @@ static cudaError_t launch_spline_t(const SplineParams &p, long long S, cudaStrea
     return cudaGetLastError();
 }
 
-extern "C" int pyitd_extract_spline_device(pyitd_plan *pl, const void *x, void *rotation, void *baseline,
-                                           int32_t *knot_count, int32_t *status, int min_knots, void *stream) {
-    if (!pl || !x || !baseline || !knot_count || !status) return fail(PYITD_E_INVALID, "null argument");
+static int run_spline(pyitd_plan *pl, const void *x, void *rotation, void *baseline, int32_t *knot_count,
+                      int32_t *status, int min_knots, cudaStream_t st) {
     if (pl->dtype == PYITD_F32)
         return fail(PYITD_E_INVALID, "the spline variant computes in float64: use a PYITD_F64 or PYITD_F32_MIXED plan");
-    cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(pl->device));
     if (int rc = ensure_workspace(pl)) return rc;
-    pl->launches = 0;
-    pl->events_used = 0;
     CU(cudaMemsetAsync(status, 0, (size_t)pl->S * sizeof(int), st));
     if (int rc = run_scan(pl, x, status, knot_count, st)) return rc;
     SplineParams sp;
@@ -1024,6 +1020,122 @@ extern "C" int pyitd_extract_spline_device(pyitd_plan *pl, const void *x, void *
     else CU((launch_spline_t<float, double, float>(sp, pl->S, st)));
     pl->launches++;
     return mark(pl, st);
+}
+
+extern "C" int pyitd_extract_spline_device(pyitd_plan *pl, const void *x, void *rotation, void *baseline,
+                                           int32_t *knot_count, int32_t *status, int min_knots, void *stream) {
+    if (!pl || !x || !baseline || !knot_count || !status) return fail(PYITD_E_INVALID, "null argument");
+    CU(cudaSetDevice(pl->device));
+    pl->launches = 0;
+    pl->events_used = 0;
+    return run_spline(pl, x, rotation, baseline, knot_count, status, min_knots, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2-D crossways ensemble ITD: row passes, column passes as row passes on the transposed batch
+// ---------------------------------------------------------------------------------------------
+struct Sift2dShape {
+    long long B;
+    int H, W;
+};
+static int sift2d_check(const pyitd_plan *rp, const pyitd_plan *cp, long long B, long long H, long long W) {
+    if (!rp || !cp) return fail(PYITD_E_INVALID, "null plan");
+    if (B < 1 || H < 3 || W < 3) return fail(PYITD_E_INVALID, "images must be at least 3 x 3");
+    if (rp->S != B * H || rp->n != W) return fail(PYITD_E_INVALID, "row plan must be (n_images * height) signals of width samples");
+    if (cp->S != B * W || cp->n != H) return fail(PYITD_E_INVALID, "column plan must be (n_images * width) signals of height samples");
+    if (rp->dtype != cp->dtype || rp->device != cp->device) return fail(PYITD_E_INVALID, "row and column plans differ in dtype or device");
+    if (rp->dtype == PYITD_F32) return fail(PYITD_E_INVALID, "use PYITD_F64 or PYITD_F32_MIXED plans");
+    if (B > 65535) return fail(PYITD_E_INVALID, "at most 65535 images per call");
+    return 0;
+}
+template <typename T>
+static int sift2d_transpose(const void *in, void *out, Sift2dShape sh, int H, int W, cudaStream_t st) {
+    dim3 grid((W + kTrTile - 1) / kTrTile, (H + kTrTile - 1) / kTrTile, (unsigned)sh.B);
+    transpose_batch_kernel<T><<<grid, dim3(32, 8), 0, st>>>((const T *)in, (T *)out, H, W);
+    CU(cudaGetLastError());
+    return 0;
+}
+// scratch: 3 buffers of B*H*W elements; out may alias none of them
+template <typename T>
+static int sift2d_crossways(pyitd_plan *rp, pyitd_plan *cp, const void *x, void *out, void *scratch, Sift2dShape sh,
+                            int min_knots, cudaStream_t st) {
+    const size_t elems = (size_t)sh.B * sh.H * sh.W;
+    T *b0 = (T *)scratch, *b1 = b0 + elems, *b2 = b1 + elems;
+    if (int rc = ensure_workspace(rp)) return rc;
+    if (int rc = ensure_workspace(cp)) return rc;
+    int *rk = rp->input_knots, *rs = rp->stop_kind, *ck = cp->input_knots, *cs = cp->stop_kind;   // per-signal scratch
+    // lengthwise[r, :] = base(data[r, :])
+    if (int rc = run_spline(rp, x, nullptr, b0, rk, rs, min_knots, st)) return rc;
+    // crosswise[:, c] = base(data[:, c])   (kept transposed in b2)
+    if (int rc = sift2d_transpose<T>(x, b1, sh, sh.H, sh.W, st)) return rc;
+    if (int rc = run_spline(cp, b1, nullptr, b2, ck, cs, min_knots, st)) return rc;
+    // crosswise[r, :] = base(crosswise[r, :])
+    if (int rc = sift2d_transpose<T>(b2, b1, sh, sh.W, sh.H, st)) return rc;
+    if (int rc = run_spline(rp, b1, nullptr, b2, rk, rs, min_knots, st)) return rc;
+    // lengthwise[:, c] = base(lengthwise[:, c])   (comes back transposed in b0)
+    if (int rc = sift2d_transpose<T>(b0, b1, sh, sh.H, sh.W, st)) return rc;
+    if (int rc = run_spline(cp, b1, nullptr, b0, ck, cs, min_knots, st)) return rc;
+    // (lengthwise + crosswise) / 2
+    dim3 grid((sh.W + kTrTile - 1) / kTrTile, (sh.H + kTrTile - 1) / kTrTile, (unsigned)sh.B);
+    transpose_average_kernel<T><<<grid, dim3(32, 8), 0, st>>>(b0, b2, (T *)out, sh.H, sh.W);
+    CU(cudaGetLastError());
+    rp->launches += 4;
+    return 0;
+}
+
+extern "C" int64_t pyitd_crossways_scratch_bytes(const pyitd_plan *rp, int64_t n_images, int64_t height, int64_t width) {
+    if (!rp) return 0;
+    return (int64_t)(3 * (size_t)n_images * (size_t)height * (size_t)width * rp->io_elem);
+}
+
+extern "C" int pyitd_crossways_device(pyitd_plan *rp, pyitd_plan *cp, const void *images, void *out, void *scratch,
+                                      int64_t n_images, int64_t height, int64_t width, int min_knots, void *stream) {
+    if (!images || !out || !scratch) return fail(PYITD_E_INVALID, "null argument");
+    if (int rc = sift2d_check(rp, cp, n_images, height, width)) return rc;
+    CU(cudaSetDevice(rp->device));
+    rp->launches = cp->launches = 0;
+    rp->events_used = cp->events_used = 0;
+    const Sift2dShape sh = {n_images, (int)height, (int)width};
+    if (rp->dtype == PYITD_F64) return sift2d_crossways<double>(rp, cp, images, out, scratch, sh, min_knots, (cudaStream_t)stream);
+    return sift2d_crossways<float>(rp, cp, images, out, scratch, sh, min_knots, (cudaStream_t)stream);
+}
+
+extern "C" int64_t pyitd_ensemble2d_scratch_bytes(const pyitd_plan *rp, int64_t draws, int64_t height, int64_t width) {
+    if (!rp) return 0;
+    return (int64_t)(5 * (size_t)(2 * draws) * (size_t)height * (size_t)width * rp->io_elem);
+}
+
+template <typename T>
+static int sift2d_ensemble(pyitd_plan *rp, pyitd_plan *cp, const void *image, const void *noise, void *lowpass, void *scratch,
+                           int draws, int H, int W, int min_knots, cudaStream_t st) {
+    const long long hw = (long long)H * W;
+    const size_t elems = (size_t)(2 * draws) * (size_t)hw;
+    T *members = (T *)scratch, *result = members + elems, *cw_scratch = result + elems;
+    const unsigned grid = (unsigned)((hw + 255) / 256);
+    ensemble_members_kernel<T><<<grid, 256, 0, st>>>((const T *)image, (const T *)noise, members, hw, draws);
+    CU(cudaGetLastError());
+    const Sift2dShape sh = {2ll * draws, H, W};
+    if (int rc = sift2d_crossways<T>(rp, cp, members, result, cw_scratch, sh, min_knots, st)) return rc;
+    ensemble_mean_kernel<T><<<grid, 256, 0, st>>>(result, (T *)lowpass, hw, draws);
+    CU(cudaGetLastError());
+    rp->launches += 2;
+    return 0;
+}
+
+extern "C" int pyitd_ensemble2d_device(pyitd_plan *rp, pyitd_plan *cp, const void *image, const void *noise, void *lowpass,
+                                       void *scratch, int64_t draws, int64_t height, int64_t width, int min_knots,
+                                       void *stream) {
+    if (!image || !noise || !lowpass || !scratch) return fail(PYITD_E_INVALID, "null argument");
+    if (draws < 1) return fail(PYITD_E_INVALID, "draws must be >= 1");
+    if (int rc = sift2d_check(rp, cp, 2 * draws, height, width)) return rc;
+    CU(cudaSetDevice(rp->device));
+    rp->launches = cp->launches = 0;
+    rp->events_used = cp->events_used = 0;
+    if (rp->dtype == PYITD_F64)
+        return sift2d_ensemble<double>(rp, cp, image, noise, lowpass, scratch, (int)draws, (int)height, (int)width, min_knots,
+                                       (cudaStream_t)stream);
+    return sift2d_ensemble<float>(rp, cp, image, noise, lowpass, scratch, (int)draws, (int)height, (int)width, min_knots,
+                                  (cudaStream_t)stream);
 }
 
 extern "C" int pyitd_find_knots_device(pyitd_plan *pl, const void *x, int kinds, int32_t *knots,

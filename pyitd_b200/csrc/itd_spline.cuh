@@ -13,7 +13,7 @@
 //     1. the knot slice (tau, X) plus 64 halo knots either side is staged in shared memory; one thread per knot
 //        rebuilds L_k, 1/h_k and the segment slopes;
 //     2. the tridiagonal moment system  mu_i M_{i-1} + 2 M_i + lam_i M_{i+1} = d_i  is solved by TRUNCATED
-//        PARALLEL CYCLIC REDUCTION in shared memory.  The rows are strictly diagonally dominant (off-diagonal
+//        CYCLIC REDUCTION in shared memory (two plain levels, then parallel cyclic reduction on the quarter).  The rows are strictly diagonally dominant (off-diagonal
 //        sum <= 1/2 of the diagonal), so after s reduction steps the remaining coupling to rows 2^s away is
 //        below (1/2)^(2^s): at most six steps (reach 63 knots, residual coupling < 5.5e-20) decouple every row.
 //        A window therefore depends on no other window: the solve is streaming and embarrassingly parallel in
@@ -56,8 +56,11 @@ struct SplineSmem {
     double ys[kSplSlots + 4];     // L_k (= coefficient c0)
     double ih[kSplSlots + 4];     // 1 / h_k, h_k = tau_{k+1} - tau_k
     // slot-indexed (slot q = entry m - 2): PCR rows with a unit diagonal; afterwards r = M, a = c2, c = c3
-    double a[kSplSlots], c[kSplSlots], r[kSplSlots];
+    // (stored at padded positions P(q) = q + q / 16 so that strides of 1, 2 and 4 rows are bank-conflict free)
+    double a[kSplSlots + kSplSlots / 16], c[kSplSlots + kSplSlots / 16], r[kSplSlots + kSplSlots / 16];
 };
+
+__device__ __forceinline__ int P(int q) { return q + (q >> 4); }
 
 // 1 / b to ~1 ulp: MUFU seed (about 20 bits) + two Newton steps.  The spline solve is held to 1e-9 against the
 // reference's FITPACK solve, not to bit equality, so the ~40-instruction IEEE division is not needed here.
@@ -95,7 +98,6 @@ __global__ void __launch_bounds__(kSplThreads, 4) spline_level_kernel(const Spli
     const int *tau = p.tab.tau + (long long)sig * p.tab.kstride;
     const CarryT *xk = reinterpret_cast<const CarryT *>(p.tab.xk) + (long long)sig * p.tab.kstride;
     const unsigned *mask = p.tab.mask + (long long)sig * p.tab.mstride;
-    const int *tbase = p.tab.tbase + (long long)sig * (p.tiles + 1);
 
     // end knots: mean of the odd-reflected pad (MEITD.py:323-325): pad = 2 * edge - neighbour
     const double x0 = (double)__ldg(x), x1 = (double)__ldg(x + 1);
@@ -167,43 +169,62 @@ __global__ void __launch_bounds__(kSplThreads, 4) spline_level_kernel(const Spli
                 c *= inv;
                 r *= inv;
             }
-            sm.a[q] = a;
-            sm.c[q] = c;
-            sm.r[q] = r;
+            sm.a[P(q)] = a;
+            sm.c[P(q)] = c;
+            sm.r[P(q)] = r;
         }
         __syncthreads();
-        // truncated parallel cyclic reduction, in place through registers; stops as soon as every remaining
-        // coupling is below 1e-13 -- four orders of magnitude inside the 1e-9 parity
-        // tolerance -- which takes five steps on evenly spaced knots and at most six ((1/2)^(2^s) bound)
-#pragma unroll 1
-        for (int s = 0; s < kSplSteps; ++s) {
-            const int d = 1 << s;
-            double na[4], nc[4], nr[4];
-            bool big = false;
+        // Truncated cyclic reduction.  Two forward levels of plain cyclic reduction (rows 2i from their odd
+        // neighbours, then rows 4i) leave 256 rows, one per thread; up to four steps of PARALLEL cyclic reduction
+        // on those (distances 4, 8, 16, 32) decouple them -- it stops as soon as every remaining coupling is below
+        // 1e-13, four orders of magnitude inside the 1e-9 parity tolerance (worst case (1/2)^64 after all six
+        // levels) -- and two back-substitution levels return the odd rows.  1792 row updates per window instead of
+        // the 6144 of six full PCR steps.  The rows live at padded positions P(q): conflict-free for strides 1, 2, 4.
+        auto reduce_row = [&](int q, int d, double &na, double &nc, double &nr) {
+            const double k1 = sm.a[P(q)], k2 = sm.c[P(q)];
+            double am = 0.0, cm = 0.0, rm = 0.0, ap = 0.0, cp = 0.0, rp = 0.0;
+            if (q - d >= 0) { am = sm.a[P(q - d)]; cm = sm.c[P(q - d)]; rm = sm.r[P(q - d)]; }
+            if (q + d < kSplSlots) { ap = sm.a[P(q + d)]; cp = sm.c[P(q + d)]; rp = sm.r[P(q + d)]; }
+            const double inv = fast_rcp(__fma_rn(-k1, cm, __fma_rn(-k2, ap, 1.0)));
+            na = -(k1 * am) * inv;
+            nc = -(k2 * cp) * inv;
+            nr = __fma_rn(-k1, rm, __fma_rn(-k2, rp, sm.r[P(q)])) * inv;
+        };
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int q = tid + j * kSplThreads;
-                const double k1 = sm.a[q], k2 = sm.c[q];
-                double am = 0.0, cm = 0.0, rm = 0.0, ap = 0.0, cp = 0.0, rp = 0.0;
-                if (q - d >= 0) { am = sm.a[q - d]; cm = sm.c[q - d]; rm = sm.r[q - d]; }
-                if (q + d < kSplSlots) { ap = sm.a[q + d]; cp = sm.c[q + d]; rp = sm.r[q + d]; }
-                const double inv = fast_rcp(1.0 - k1 * cm - k2 * ap);
-                na[j] = -(k1 * am) * inv;
-                nc[j] = -(k2 * cp) * inv;
-                nr[j] = (sm.r[q] - k1 * rm - k2 * rp) * inv;
-                big |= (fabs(na[j]) > 1e-13) || (fabs(nc[j]) > 1e-13);
-            }
-            const int more = __syncthreads_or(big);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int q = tid + j * kSplThreads;
-                sm.a[q] = na[j];
-                sm.c[q] = nc[j];
-                sm.r[q] = nr[j];
-            }
-            __syncthreads();
-            if (!more) break;
+        for (int j = 0; j < 2; ++j) {                      // level 1: rows 2i (their odd neighbours are not written)
+            const int q = 2 * (tid + j * kSplThreads);
+            double na, nc, nr;
+            reduce_row(q, 1, na, nc, nr);
+            sm.a[P(q)] = na; sm.c[P(q)] = nc; sm.r[P(q)] = nr;
         }
+        __syncthreads();
+        {
+            const int q = 4 * tid;                         // level 2: rows 4i from rows 4i +- 2
+            double na, nc, nr;
+            reduce_row(q, 2, na, nc, nr);
+            sm.a[P(q)] = na; sm.c[P(q)] = nc; sm.r[P(q)] = nr;
+            __syncthreads();
+#pragma unroll 1
+            for (int s = 0; s < 4; ++s) {                  // PCR among the rows 4i, in place through registers
+                reduce_row(q, 4 << s, na, nc, nr);
+                const int more = __syncthreads_or((fabs(na) > 1e-13) || (fabs(nc) > 1e-13));
+                sm.a[P(q)] = na; sm.c[P(q)] = nc; sm.r[P(q)] = nr;
+                __syncthreads();
+                if (!more) break;
+            }
+            // back-substitution: rows 4i + 2 from the solved rows 4i, 4i + 4 (unit diagonal: M = r - a M- - c M+)
+            const int q2 = q + 2;
+            const double mp = (q2 + 2 < kSplSlots) ? sm.r[P(q2 + 2)] : 0.0;
+            sm.r[P(q2)] = __fma_rn(-sm.a[P(q2)], sm.r[P(q2 - 2)], __fma_rn(-sm.c[P(q2)], mp, sm.r[P(q2)]));
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {                      // odd rows from their solved even neighbours
+            const int q = 2 * (tid + j * kSplThreads) + 1;
+            const double mp = (q + 1 < kSplSlots) ? sm.r[P(q + 1)] : 0.0;
+            sm.r[P(q)] = __fma_rn(-sm.a[P(q)], sm.r[P(q - 1)], __fma_rn(-sm.c[P(q)], mp, sm.r[P(q)]));
+        }
+        __syncthreads();
         // M_i = r[i] on the decoupled rows (slots [halo - 1, slots - halo] are exact to < 5.5e-20 relative).
         // Segments of this window: j = j_lo .. j_hi; the coefficients replace dead arrays in place
         // (c1 over the slope of the same segment, c2 / c3 over a / c of the same slot).
@@ -219,63 +240,65 @@ __global__ void __launch_bounds__(kSplThreads, 4) spline_level_kernel(const Spli
             double Mj, Mj1;
             if (j == 0) {
                 const double rho = h * sm.ih[m + 1];                       // h_0 / h_1
-                Mj = (1.0 + rho) * sm.r[slot + 1] - rho * sm.r[slot + 2];
+                Mj = (1.0 + rho) * sm.r[P(slot + 1)] - rho * sm.r[P(slot + 2)];
             } else {
-                Mj = sm.r[slot];
+                Mj = sm.r[P(slot)];
             }
             if (j == K) {
                 const double rho = h * sm.ih[m - 1];                       // h_K / h_{K-1}
-                Mj1 = (1.0 + rho) * sm.r[slot] - rho * sm.r[slot - 1];
+                Mj1 = (1.0 + rho) * sm.r[P(slot)] - rho * sm.r[P(slot - 1)];
             } else {
-                Mj1 = sm.r[slot + 1];
+                Mj1 = sm.r[P(slot + 1)];
             }
             const double sixth = 1.0 / 6.0;
             sm.xs[m] = sm.xs[m] - h * (2.0 * Mj + Mj1) * sixth;            // only this thread touches xs[m], a / c[slot]
-            sm.a[slot] = 0.5 * Mj;
-            sm.c[slot] = (Mj1 - Mj) * sm.ih[m] * sixth;
+            sm.a[P(slot)] = 0.5 * Mj;
+            sm.c[P(slot)] = (Mj1 - Mj) * sm.ih[m] * sixth;
         }
         __syncthreads();
 
         // evaluation of the window's samples: [tau_{j_lo}, tau_{j_hi + 1}), plus sample n-1 in the last window.
-        // Blocks of 256 samples aligned to 256: one sample per thread, one flag word per warp.
+        // Four blocks of 256 samples per iteration (one sample per thread and block, one flag word per warp and
+        // block).  Segment id of sample t = j_lo + flagged samples in (t_lo, t]: every warp keeps the running count
+        // itself from one 128-byte load of the iteration's 32 flag words and a shuffle scan -- no shared memory,
+        // no barrier, four independent x loads in flight per thread.
         const int t_lo = sm.ts[j_lo - (base - 2)];
         const int t_hi = (j_hi == K) ? n : sm.ts[j_hi + 1 - (base - 2)];
-        constexpr int UN = 4;                              // blocks in flight per thread
-        for (int tb = (t_lo & ~(kSplThreads - 1)); tb < t_hi; tb += UN * kSplThreads) {
+        constexpr int UN = 4;
+        int run = j_lo;
+        for (int tb = (t_lo & ~(UN * kSplThreads - 1)); tb < t_hi; tb += UN * kSplThreads) {
             double xv[UN];
-            int mm[UN], tt[UN];
 #pragma unroll
             for (int u = 0; u < UN; ++u) {
-                const int tw = tb + u * kSplThreads + warp * 32;   // first sample of this warp's flag word
-                tt[u] = -1;
-                xv[u] = 0.0;
-                mm[u] = 2;
-                if (tw >= t_hi || tw + 31 < t_lo) continue;        // warp-uniform
-                // interior knots before the word: per-tile prefix + the words of the tile before it
-                const int wword = tw >> 5;
-                const int tile = tw / p.tile;
-                int cnt = 0;
-                for (int w = ((tile * p.tile) >> 5) + lane; w < wword; w += 32) cnt += __popc(__ldg(mask + w));
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-                const int t = tw + lane;
-                if (t < t_lo || t >= t_hi) continue;
-                xv[u] = (double)__ldg(x + t);
-                const unsigned mw = __ldg(mask + wword);
-                int j = __ldg(tbase + tile) + cnt + __popc(mw & (0xffffffffu >> (31 - lane)));   // interior knots <= t
-                if (j > K) j = K;
-                mm[u] = j - (base - 2);
-                tt[u] = t;
+                const int t = tb + u * kSplThreads + tid;
+                xv[u] = (t >= t_lo && t < t_hi) ? (double)__ldg(x + t) : 0.0;
             }
+            const int wi = (tb >> 5) + lane;               // lane l holds flag word l of the iteration
+            unsigned word = (wi < p.tab.mstride) ? __ldg(mask + wi) : 0u;
+            if (wi * 32 <= t_lo) word = (wi * 32 + 31 <= t_lo) ? 0u : (word & ~(0xffffffffu >> (31 - (t_lo & 31))));
+            const int c = __popc(word);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int excl = incl - c;
 #pragma unroll
             for (int u = 0; u < UN; ++u) {
-                if (tt[u] < 0) continue;
-                const int m = mm[u], t = tt[u];
+                const int src = u * (kSplThreads / 32) + warp;
+                const unsigned mw = __shfl_sync(0xffffffffu, word, src);
+                const int before = __shfl_sync(0xffffffffu, excl, src);
+                const int t = tb + u * kSplThreads + tid;
+                if (t < t_lo || t >= t_hi) continue;
+                const int j = run + before + __popc(mw & (0xffffffffu >> (31 - lane)));
+                const int m = j - (base - 2);
                 const double uu = (double)(t - sm.ts[m]);
-                const double b = sm.ys[m] + uu * (sm.xs[m] + uu * (sm.a[m - 2] + uu * sm.c[m - 2]));
+                const double b = sm.ys[m] + uu * (sm.xs[m] + uu * (sm.a[P(m - 2)] + uu * sm.c[P(m - 2)]));
                 __stcs(bas + t, (OutT)b);
                 if (rot) __stcs(rot + t, (OutT)(xv[u] - b));       // MEITD.py:335
             }
+            run += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
 }
