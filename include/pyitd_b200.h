@@ -204,6 +204,28 @@ PYITD_API int pyitd_ensemble2d_device(pyitd_plan *row_plan, pyitd_plan *col_plan
                             void *stream);
 
 /*
+ * post-decomposition analytics on rows that are still in device memory (no plan needed).
+ *
+ * pyitd_wpe_device replaces weighted_permutation_entropy(time_series, order=3, normalize) (MEITD.py:79-128), which the
+ * reference evaluates per rotation (MEITD.py:346, :374, :547), for every row of a matrix.
+ *   rows        [n_rows_total, n_samples], dtype PYITD_F64 (double) or any other value (float)
+ *   valid_rows  NULL, or [n_rows_total / rows_per_signal] int32 (e.g. n_rows of pyitd_decompose_device): rows whose
+ *               index inside their signal is >= valid_rows[signal] get NaN
+ *   out         [n_rows_total] float64
+ * The reference accumulates the weighted counts sequentially in float64; the kernel reduces them in parallel with a
+ * double-double combine, so results agree to ~1e-14 relative, not bit for bit.
+ *
+ * pyitd_column_fsum_device replaces shewchuk(a) (helperfunctions.py:2-9) and shewchuk_sum (ITD.py:475-481):
+ * column_sums[s, t] = math.fsum(rows[s, :valid, t]) -- exactly rounded, bit-identical to CPython's fsum -- and
+ * totals[s] (may be NULL) = their sum over t in double-double arithmetic (within 1 ulp of math.fsum).
+ *   rows [n_signals, rows_per_signal, n_samples]; rows_per_signal <= 64; n_signals <= 65535
+ */
+PYITD_API int pyitd_wpe_device(const void *rows, int64_t n_rows_total, int64_t n_samples, int dtype, int order,
+                     int normalize, const int32_t *valid_rows, int64_t rows_per_signal, double *out, void *stream);
+PYITD_API int pyitd_column_fsum_device(const void *rows, int64_t n_signals, int64_t rows_per_signal, int64_t n_samples,
+                             int dtype, const int32_t *valid_rows, double *column_sums, double *totals, void *stream);
+
+/*
  * Replaces detect_peaks (ITD.py:33-76) and the knot merge around it (ITD.py:87-88, :97).
  *   kinds      PYITD_KNOTS_VALLEYS = detect_peaks(x), PYITD_KNOTS_PEAKS = detect_peaks(-x),
  *              PYITD_KNOTS_BOTH = sort(unique(hstack(both))) = the knot set of one level

@@ -468,3 +468,102 @@ int itd_oracle_spline_level_f64(const double *x, int64_t n, double *R, double *B
     free(y); free(tau);
     return ITD_OK;
 }
+
+/* ==== SURVEY.md 8f rank 4: post-decomposition analytics ========================================
+ * (a) weighted permutation entropy of order 3, MEITD.py:79-128 (used per rotation at MEITD.py:346,
+ *     :374, :547): windows (x[i], x[i+1], x[i+2]); pattern = stable argsort of the window (numpy's
+ *     quicksort is an insertion sort below 16 elements, MEITD.py:106); hash = sum idx_k 3^k (:108);
+ *     weight = population variance of the window (:107) = (((d0^2 + d1^2) + d2^2) / 3 with
+ *     d = x - ((a + b) + c) / 3; weighted counts are accumulated per pattern in window order (:113-117);
+ *     p = counts / sum(counts) over the patterns that occur, in ascending hash order (:122);
+ *     pe = -sum p log2 p (:123), divided by log2(3!) when normalised (:124-125).                 */
+double itd_oracle_wpe3_f64(const double *x, int64_t n, int normalize)
+{
+    /* ascending hash order of the six permutations: (2,1,0)=5 (1,2,0)=7 (2,0,1)=11 (0,2,1)=15 (1,0,2)=19 (0,1,2)=21 */
+    double wc[6] = {0, 0, 0, 0, 0, 0};
+    int64_t cnt[6] = {0, 0, 0, 0, 0, 0};
+    for (int64_t i = 0; i + 2 < n; ++i) {
+        double a = x[i], b = x[i + 1], c = x[i + 2];
+        int slot;
+        /* stable argsort of (a, b, c): ties keep index order */
+        if (a <= b) {
+            if (b <= c) slot = 5;            /* (0,1,2) -> 21 */
+            else if (a <= c) slot = 3;       /* (0,2,1) -> 15 */
+            else slot = 2;                   /* (2,0,1) -> 11 */
+        } else {
+            if (a <= c) slot = 4;            /* (1,0,2) -> 19 */
+            else if (b <= c) slot = 1;       /* (1,2,0) -> 7  */
+            else slot = 0;                   /* (2,1,0) -> 5  */
+        }
+        double mean = ((a + b) + c) / 3.0;
+        double d0 = a - mean, d1 = b - mean, d2 = c - mean;
+        double w = ((d0 * d0 + d1 * d1) + d2 * d2) / 3.0;
+        wc[slot] += w;
+        cnt[slot] += 1;
+    }
+    double total = 0.0;
+    int first = 1;
+    for (int k = 0; k < 6; ++k)
+        if (cnt[k]) { total = first ? wc[k] : total + wc[k]; first = 0; }
+    double acc = 0.0;
+    first = 1;
+    for (int k = 0; k < 6; ++k)
+        if (cnt[k]) {
+            double p = wc[k] / total;
+            double term = p * log2(p);
+            acc = first ? term : acc + term;
+            first = 0;
+        }
+    double pe = -acc;
+    if (normalize) pe /= log2(6.0);
+    return pe;
+}
+
+/* (b) exactly rounded column sums of the output rows, helperfunctions.py:2-9 shewchuk(a) == the inner loop of
+ *     ITD.py:475-481 shewchuk_sum: s[t] = math.fsum(rows[:, t]).  math.fsum is restated (CPython's algorithm:
+ *     a non-overlapping expansion grown by two-sums, rounded once with the half-even correction).         */
+static double fsum_exact(const double *v, int64_t count, int64_t stride)
+{
+    double partials[64];
+    int np_ = 0;
+    for (int64_t r = 0; r < count; ++r) {
+        double xx = v[r * stride];
+        int i = 0;
+        for (int j = 0; j < np_; ++j) {
+            double y = partials[j];
+            if (fabs(xx) < fabs(y)) { double t = xx; xx = y; y = t; }
+            double hi = xx + y;
+            double lo = y - (hi - xx);
+            if (lo != 0.0) partials[i++] = lo;
+            xx = hi;
+        }
+        partials[i] = xx;
+        np_ = i + 1;
+    }
+    double hi = 0.0;
+    if (np_ > 0) {
+        int n2 = np_;
+        hi = partials[--n2];
+        double lo = 0.0;
+        while (n2 > 0) {
+            double xx = hi;
+            double y = partials[--n2];
+            hi = xx + y;
+            double yr = hi - xx;
+            lo = y - yr;
+            if (lo != 0.0) break;
+        }
+        if (n2 > 0 && ((lo < 0.0 && partials[n2 - 1] < 0.0) || (lo > 0.0 && partials[n2 - 1] > 0.0))) {
+            double y = lo * 2.0;
+            double xx = hi + y;
+            double yr = xx - hi;
+            if (y == yr) hi = xx;
+        }
+    }
+    return hi;
+}
+
+void itd_oracle_column_fsum_f64(const double *rows, int64_t n_rows, int64_t n, double *out)
+{
+    for (int64_t t = 0; t < n; ++t) out[t] = fsum_exact(rows + t, n_rows > 64 ? 64 : n_rows, n);
+}

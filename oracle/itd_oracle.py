@@ -222,6 +222,56 @@ def ensemble2d(data: np.ndarray, noise: np.ndarray, level=None) -> np.ndarray:
     return x / (draws * 1.0)
 
 
+# --------------------------------------------------------------------------------------------
+# post-decomposition analytics
+# --------------------------------------------------------------------------------------------
+def c_wpe3(x: np.ndarray, normalize: bool = True) -> float:
+    """``weighted_permutation_entropy(x, order=3, normalize)`` of MEITD.py:79-128 (see itd_oracle.c)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    return float(c_lib().itd_oracle_wpe3_f64(_ptr(x), x.shape[0], int(bool(normalize))))
+
+
+def np_wpe3(x: np.ndarray, normalize: bool = True) -> float:
+    """numpy restatement of the same function (vectorised pattern / weight computation, sequential sums)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = x.shape[0]
+    if n < 3:
+        return -0.0
+    a, b, c = x[:-2], x[1:-1], x[2:]
+    slot = np.where(a <= b, np.where(b <= c, 5, np.where(a <= c, 3, 2)), np.where(a <= c, 4, np.where(b <= c, 1, 0)))
+    mean = ((a + b) + c) / 3.0
+    w = (((a - mean) ** 2 + (b - mean) ** 2) + (c - mean) ** 2) / 3.0
+    wc = []
+    for k in range(6):
+        sel = w[slot == k]
+        if sel.shape[0]:
+            acc = 0.0
+            for v in sel.tolist():          # MEITD.py:113-117 accumulates in window order
+                acc += v
+            wc.append(acc)
+    total = wc[0]
+    for v in wc[1:]:
+        total += v
+    acc = None
+    with np.errstate(all="ignore"):
+        for v in wc:
+            p = np.float64(v) / np.float64(total)
+            term = float(p * np.log2(p))
+            acc = term if acc is None else acc + term
+    pe = -acc
+    if normalize:
+        pe /= float(np.log2(6.0))
+    return pe
+
+
+def c_column_fsum(rows: np.ndarray) -> np.ndarray:
+    """``shewchuk(a)`` of helperfunctions.py:2-9 (== inner loop of ITD.py:475-481): exactly rounded column sums."""
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    out = np.empty(rows.shape[1])
+    c_lib().itd_oracle_column_fsum_f64(_ptr(rows), rows.shape[0], rows.shape[1], _ptr(out))
+    return out
+
+
 @dataclass
 class OracleResult:
     rotations: np.ndarray        # (n_rows, N): proper rotations then the final trend row
@@ -300,6 +350,10 @@ def c_lib() -> ctypes.CDLL:
             f.restype = ci
             f.argtypes = [vp, i64, i64, ci, ci, vp, vp, vp, vp, vp, ci]
         lib.itd_oracle_max_threads.restype = ci
+        lib.itd_oracle_wpe3_f64.restype = ctypes.c_double
+        lib.itd_oracle_wpe3_f64.argtypes = [vp, i64, ci]
+        lib.itd_oracle_column_fsum_f64.restype = None
+        lib.itd_oracle_column_fsum_f64.argtypes = [vp, i64, i64, vp]
         lib.itd_oracle_spline_level_f64.restype = ci
         lib.itd_oracle_spline_level_f64.argtypes = [vp, i64, vp, vp, vp]
         _LIB = lib

@@ -13,7 +13,11 @@ from .spline import extract_spline, itd_baseline_extract_modified, itd_baseline_
 from .sift2d import (crossways_batch, crossways_itd_baseline_extract, retrieve_statistical_image_component,  # noqa: F401
                      totalextract2d)
 
-__all__ = ["crossways_batch", "crossways_itd_baseline_extract", "retrieve_statistical_image_component", "totalextract2d",
+from .analytics import (column_fsum, reconstruction_error, shewchuk, shewchuk_sum, weighted_permutation_entropy,  # noqa: F401
+                        wpe_rows)
+
+__all__ = ["wpe_rows", "weighted_permutation_entropy", "column_fsum", "shewchuk", "shewchuk_sum", "reconstruction_error",
+           "crossways_batch", "crossways_itd_baseline_extract", "retrieve_statistical_image_component", "totalextract2d",
            "extract_spline", "itd_baseline_extract_spline", "itd_baseline_extract_modified",
            "ITD", "ITDResult", "decompose", "detect_peaks", "itd_baseline_extract", "extract_level",
            "find_knots", "extract_with_knots", "Plan", "PyITDLibraryError", "clear_plan_cache"]

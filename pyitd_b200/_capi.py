@@ -100,6 +100,10 @@ def lib() -> ctypes.CDLL:
     L.pyitd_ensemble2d_scratch_bytes.argtypes = [vp, i64, i64, i64]
     L.pyitd_ensemble2d_device.restype = ci
     L.pyitd_ensemble2d_device.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, ci, vp]
+    L.pyitd_wpe_device.restype = ci
+    L.pyitd_wpe_device.argtypes = [vp, i64, i64, ci, ci, ci, vp, i64, vp, vp]
+    L.pyitd_column_fsum_device.restype = ci
+    L.pyitd_column_fsum_device.argtypes = [vp, i64, i64, i64, ci, vp, vp, vp, vp]
     L.pyitd_find_knots_device.restype = ci
     L.pyitd_find_knots_device.argtypes = [vp, vp, ci, vp, i64, vp, vp, vp]
     _lib = L

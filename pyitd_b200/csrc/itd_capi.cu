@@ -17,6 +17,7 @@
 #include "itd_resident.cuh"
 #include "itd_spline.cuh"
 #include "itd_sift2d.cuh"
+#include "itd_analytics.cuh"
 
 using namespace pyitd;
 
@@ -1136,6 +1137,48 @@ extern "C" int pyitd_ensemble2d_device(pyitd_plan *rp, pyitd_plan *cp, const voi
                                        (cudaStream_t)stream);
     return sift2d_ensemble<float>(rp, cp, image, noise, lowpass, scratch, (int)draws, (int)height, (int)width, min_knots,
                                   (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// post-decomposition analytics; no plan: these kernels need no workspace
+// ---------------------------------------------------------------------------------------------
+extern "C" int pyitd_wpe_device(const void *rows, int64_t n_rows_total, int64_t n_samples, int dtype, int order,
+                                int normalize, const int32_t *valid_rows, int64_t rows_per_signal, double *out,
+                                void *stream) {
+    if (!rows || !out) return fail(PYITD_E_INVALID, "null argument");
+    if (order != 3) return fail(PYITD_E_INVALID, "only order 3 is implemented (the only order the reference uses)");
+    if (n_rows_total < 1 || n_rows_total > 0x7fffffffll || n_samples < 0) return fail(PYITD_E_INVALID, "bad shape");
+    if (valid_rows && rows_per_signal < 1) return fail(PYITD_E_INVALID, "rows_per_signal must be >= 1 with valid_rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == PYITD_F64)
+        wpe3_kernel<double><<<(unsigned)n_rows_total, 256, 0, st>>>((const double *)rows, n_samples, valid_rows,
+                                                                    (int)rows_per_signal, normalize, out);
+    else
+        wpe3_kernel<float><<<(unsigned)n_rows_total, 256, 0, st>>>((const float *)rows, n_samples, valid_rows,
+                                                                   (int)rows_per_signal, normalize, out);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pyitd_column_fsum_device(const void *rows, int64_t n_signals, int64_t rows_per_signal, int64_t n_samples,
+                                        int dtype, const int32_t *valid_rows, double *column_sums, double *totals,
+                                        void *stream) {
+    if (!rows || !column_sums) return fail(PYITD_E_INVALID, "null argument");
+    if (n_signals < 1 || n_signals > 65535 || n_samples < 1) return fail(PYITD_E_INVALID, "bad shape (at most 65535 signals per call)");
+    if (rows_per_signal < 1 || rows_per_signal > kFsumMaxRows)
+        return fail(PYITD_E_INVALID, "rows_per_signal must be in [1, 64]");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)((n_samples + 255) / 256), (unsigned)n_signals);
+    if (dtype == PYITD_F64)
+        column_fsum_kernel<double><<<grid, 256, 0, st>>>((const double *)rows, (int)rows_per_signal, n_samples, valid_rows, column_sums);
+    else
+        column_fsum_kernel<float><<<grid, 256, 0, st>>>((const float *)rows, (int)rows_per_signal, n_samples, valid_rows, column_sums);
+    CU(cudaGetLastError());
+    if (totals) {
+        dd_total_kernel<<<(unsigned)n_signals, 256, 0, st>>>(column_sums, n_samples, totals);
+        CU(cudaGetLastError());
+    }
+    return 0;
 }
 
 extern "C" int pyitd_find_knots_device(pyitd_plan *pl, const void *x, int kinds, int32_t *knots,
