@@ -123,12 +123,12 @@ __global__ void __launch_bounds__(kSplThreads, 4) spline_level_kernel(const Spli
             double y = 0.0, ih = 0.0;
             if (k == 0) y = y_first;
             else if (k == K + 1) y = y_last;
-            else if (k >= 1 && k <= K) {
-                // L_k of ITD.py:106-110
+            else if (k >= 1 && k <= K && m >= 1 && m <= M - 2) {
+                // L_k of ITD.py:106-110 (the two outermost entries have no neighbour in the slice and are never used)
                 const double w = (double)(sm.ts[m] - sm.ts[m - 1]) * fast_rcp((double)(sm.ts[m + 1] - sm.ts[m - 1]));
                 y = 0.5 * (sm.xs[m - 1] + w * (sm.xs[m + 1] - sm.xs[m - 1])) + 0.5 * sm.xs[m];
             }
-            if (k >= 0 && k <= K) ih = fast_rcp((double)(sm.ts[m + 1] - sm.ts[m]));
+            if (k >= 0 && k <= K && m <= M - 2) ih = fast_rcp((double)(sm.ts[m + 1] - sm.ts[m]));
             sm.ys[m] = y;
             sm.ih[m] = ih;
         }
