@@ -57,34 +57,44 @@ __global__ void __launch_bounds__(256) wpe3_kernel(const InT *__restrict__ rows,
     }
     const InT *x = rows + r * n;
     double wc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    int cnt[6] = {0, 0, 0, 0, 0, 0};
-    for (long long i = threadIdx.x; i + 2 < n; i += blockDim.x) {
-        const double a = (double)__ldg(x + i), b = (double)__ldg(x + i + 1), c = (double)__ldg(x + i + 2);
-        // ascending hash order of MEITD.py:108: (2,1,0) (1,2,0) (2,0,1) (0,2,1) (1,0,2) (0,1,2)
-        const int slot = (a <= b) ? ((b <= c) ? 5 : ((a <= c) ? 3 : 2)) : ((a <= c) ? 4 : ((b <= c) ? 1 : 0));
-        const double mean = div3(__dadd_rn(__dadd_rn(a, b), c));
-        const double d0 = __dsub_rn(a, mean), d1 = __dsub_rn(b, mean), d2 = __dsub_rn(c, mean);
-        const double w = div3(__dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2)));
+    unsigned seen = 0;                                     // bit k: pattern k occurred
+    constexpr int UN = 4;                                  // windows in flight per thread (12 loads)
+    const long long nwin = n - 2;
+    for (long long i0 = threadIdx.x; i0 < nwin; i0 += (long long)UN * blockDim.x) {
+        double a[UN], b[UN], c[UN];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            wc[k] = __dadd_rn(wc[k], (slot == k) ? w : 0.0);
-            cnt[k] += (slot == k);
+        for (int u = 0; u < UN; ++u) {
+            const long long i = i0 + (long long)u * blockDim.x;
+            const bool in = i < nwin;
+            a[u] = in ? (double)__ldg(x + i) : 0.0;
+            b[u] = in ? (double)__ldg(x + i + 1) : 0.0;
+            c[u] = in ? (double)__ldg(x + i + 2) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            if (i0 + (long long)u * blockDim.x >= nwin) break;
+            // ascending hash order of MEITD.py:108: (2,1,0) (1,2,0) (2,0,1) (0,2,1) (1,0,2) (0,1,2)
+            const int slot = (a[u] <= b[u]) ? ((b[u] <= c[u]) ? 5 : ((a[u] <= c[u]) ? 3 : 2))
+                                            : ((a[u] <= c[u]) ? 4 : ((b[u] <= c[u]) ? 1 : 0));
+            const double mean = div3(__dadd_rn(__dadd_rn(a[u], b[u]), c[u]));
+            const double d0 = __dsub_rn(a[u], mean), d1 = __dsub_rn(b[u], mean), d2 = __dsub_rn(c[u], mean);
+            const double w = div3(__dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2)));
+            seen |= 1u << slot;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) wc[k] = __dadd_rn(wc[k], (slot == k) ? w : 0.0);
         }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         dd v = {wc[k], 0.0};
-        int c = cnt[k];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            v = dd_add(v, dd_shfl_xor(v, o));
-            c += __shfl_xor_sync(0xffffffffu, c, o);
-        }
+        for (int o = 16; o > 0; o >>= 1) v = dd_add(v, dd_shfl_xor(v, o));
+        const int c = __any_sync(0xffffffffu, (seen >> k) & 1u);
         if (lane == 0) {
             s_hi[warp][k] = v.hi;
             s_lo[warp][k] = v.lo;
-            s_cnt[warp][k] = c > 0;
+            s_cnt[warp][k] = c;
         }
     }
     __syncthreads();
@@ -132,19 +142,26 @@ __global__ void __launch_bounds__(256) column_fsum_kernel(const InT *__restrict_
     const InT *col = rows + s * R * n + t;
     double partials[kFsumMaxRows];
     int np = 0;
-    for (int r = 0; r < nr; ++r) {
-        double x = (double)__ldg(col + (long long)r * n);
-        int i = 0;
-        for (int j = 0; j < np; ++j) {
-            double y = partials[j];
-            if (fabs(x) < fabs(y)) { const double tmp = x; x = y; y = tmp; }
-            const double hi = __dadd_rn(x, y);
-            const double lo = __dsub_rn(y, __dsub_rn(hi, x));
-            if (lo != 0.0) partials[i++] = lo;
-            x = hi;
+    for (int r0 = 0; r0 < nr; r0 += 8) {
+        double v[8];                                       // eight independent loads in flight, then the expansion
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (r0 + u < nr) ? (double)__ldg(col + (long long)(r0 + u) * n) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (r0 + u >= nr) break;
+            double x = v[u];
+            int i = 0;
+            for (int j = 0; j < np; ++j) {
+                double y = partials[j];
+                if (fabs(x) < fabs(y)) { const double tmp = x; x = y; y = tmp; }
+                const double hi = __dadd_rn(x, y);
+                const double lo = __dsub_rn(y, __dsub_rn(hi, x));
+                if (lo != 0.0) partials[i++] = lo;
+                x = hi;
+            }
+            partials[i] = x;
+            np = i + 1;
         }
-        partials[i] = x;
-        np = i + 1;
     }
     double hi = 0.0;
     if (np > 0) {
