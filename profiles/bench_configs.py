@@ -41,6 +41,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own log lines (e.g. the "NCCL version" banner) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     codes = {"f64": _capi.F64, "f32_mixed": _capi.F32_MIXED, "f32": _capi.F32}
 
