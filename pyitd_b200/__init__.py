@@ -8,6 +8,8 @@ from ._capi import PyITDLibraryError, Plan  # noqa: F401
 from .itd import (ITD, ITDResult, clear_plan_cache, decompose, detect_peaks, extract_level,  # noqa: F401
                   extract_with_knots, find_knots, itd_baseline_extract)
 
+from . import torch_ops  # noqa: F401  (torch.ops.pyitd.*: torch_ops.load())
+
 from .spline import extract_spline, itd_baseline_extract_modified, itd_baseline_extract_spline  # noqa: F401
 
 from .sift2d import (crossways_batch, crossways_itd_baseline_extract, retrieve_statistical_image_component,  # noqa: F401
