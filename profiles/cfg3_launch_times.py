@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pyitd_b200
 from pyitd_b200 import _capi, synth
 from pyitd_b200.itd import clear_plan_cache, get_plan
-N = 1 << 28
+N = 1 << int(os.environ.get('PYITD_CFG3_LOG2N', '28'))
 dev = torch.device("cuda", 0)
 x = synth.long_signal(n=N, seed=3, device="cuda").unsqueeze(0).contiguous()
 out = {}
@@ -22,7 +22,7 @@ for path in sys.argv[1:] or ["strided", "lookback"]:
     def step():
         plan.decompose_device(x.data_ptr(), rot.data_ptr(), None, ints[0].data_ptr(), counts.data_ptr(), ints[1].data_ptr(),
                               ints[2].data_ptr(), ints[3].data_ptr(), st)
-    for _ in range(2):
+    for _ in range(int(os.environ.get('PYITD_CFG3_WARM', '2'))):
         step()
     plan.enable_timing(True)
     step()

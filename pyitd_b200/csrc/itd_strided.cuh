@@ -555,56 +555,47 @@ template <typename SrcT, typename CarryT>
 __global__ void __launch_bounds__(256) compact_from_mask_kernel(KnotTable next, const void *carry_in, int sig, int n,
                                                                 int tiles, int e_guard, const int *stop_e) {
     constexpr int T = 1024;
-    __shared__ unsigned s_w[32];
-    __shared__ int s_pre[32];
     if (stop_e && stop_e[sig] < e_guard) return;            // the level kernel of e_guard never ran (stop_e null: scan pass)
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5);
     const SrcT *carry = reinterpret_cast<const SrcT *>(carry_in) + (long long)sig * n;
     const unsigned *mask = next.mask + (long long)sig * next.mstride;
     const int *tb = next.tbase + (long long)sig * (tiles + 1);
-    int *tau = next.tau + (long long)sig * next.kstride;
-    CarryT *xk = reinterpret_cast<CarryT *>(next.xk) + (long long)sig * next.kstride;
-    __shared__ int s_list[256];
-    __shared__ int s_n;
-    // a block looks at 256 tiles at a time (one coalesced read of their counts) and works through the non-empty ones:
-    // on a deep level almost every tile is knot-free
-    for (int ib = blockIdx.x * 256; ib < tiles; ib += gridDim.x * 256) {
-        __syncthreads();
-        if (tid == 0) s_n = 0;
-        __syncthreads();
-        {
-            const int i = ib + tid;
-            if (i < tiles && tb[i + 1] - tb[i] > 0) s_list[atomicAdd(&s_n, 1)] = i;
-        }
-        __syncthreads();
-        const int m = s_n;
-        for (int j = 0; j < m; ++j) {
-            const int i = s_list[j];
+    int *tau = next.tau + (long long)sig * next.kstride + 1;
+    CarryT *xk = reinterpret_cast<CarryT *>(next.xk) + (long long)sig * next.kstride + 1;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // a WARP owns 32 consecutive tiles at a time (one coalesced read of their prefix entries) and works through the
+    // non-empty ones with no block barrier: on a deep level almost every tile is knot-free, on a dense one every warp
+    // streams its tiles with independent loads in flight
+    for (int ib = gwarp * 32; ib < tiles; ib += nwarps * 32) {
+        const int i_l = ib + lane;
+        const int base_l = (i_l < tiles) ? tb[i_l] : 0;
+        const int cnt_l = (i_l < tiles) ? tb[i_l + 1] - base_l : 0;
+        unsigned live = __ballot_sync(0xffffffffu, cnt_l > 0);
+        while (live) {
+            const int j = __ffs(live) - 1;
+            live &= live - 1;
+            const int i = ib + j;
             const int t0 = i * T;
-            const int base = tb[i];
+            const int base = __shfl_sync(0xffffffffu, base_l, j);
             const int nwords = (min(T, n - t0) + 31) >> 5;
-            __syncthreads();                                 // s_w / s_pre of the previous tile are consumed
-            if (warp == 0) {
-                const unsigned w = (lane < nwords) ? mask[(t0 >> 5) + lane] : 0u;
-                int incl = __popc(w);
+            const unsigned word = (lane < nwords) ? mask[(t0 >> 5) + lane] : 0u;
+            int incl = __popc(word);
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                s_w[lane] = w;
-                s_pre[lane] = incl - __popc(w);
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int word = r * 8 + warp;
-                const unsigned w = s_w[word];
+            const int pre = base + incl - __popc(word);               // rank of the first knot of this lane's word
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                const unsigned w = __shfl_sync(0xffffffffu, word, r);
+                const int pr = __shfl_sync(0xffffffffu, pre, r);
                 if ((w >> lane) & 1u) {
-                    const int t = t0 + word * 32 + lane;
-                    const int rank = base + s_pre[word] + __popc(w & ((1u << lane) - 1u));
-                    tau[1 + rank] = t;
-                    xk[1 + rank] = (CarryT)carry[t];
+                    const int t = t0 + r * 32 + lane;
+                    const int rank = pr + __popc(w & lt_mask);
+                    tau[rank] = t;
+                    xk[rank] = (CarryT)carry[t];
                 }
             }
         }
