@@ -206,6 +206,12 @@ static cudaError_t launch_strided_t(const LevelParams &p, int cap, cudaStream_t 
                : launch_strided_v<InT, CarryT, OutT, false, false>(p, cap, st);
 }
 
+// compaction pass: a warp owns a group of 32 tiles, 8 warps per block, as many blocks as there are groups (at most 8 per SM x 4 rounds)
+static int compact_grid(int tiles) {
+    const int groups = (tiles + 31) / 32, blocks = (groups + 7) / 8;
+    return blocks < 148 * 32 ? blocks : 148 * 32;
+}
+
 // the strided path's knot scan: flag words + per-tile counts, then the prefix and the compaction pass
 template <typename InT, typename CarryT>
 static cudaError_t launch_scan_strided_t(const pyitd_plan *pl, const ScanParams &p, cudaStream_t st) {
@@ -228,8 +234,7 @@ static cudaError_t launch_scan_strided_t(const pyitd_plan *pl, const ScanParams 
     tile_prefix_scan_kernel<InT, CarryT><<<1, 1024, 0, st>>>(p.out, p.x, p.sig0, p.tiles, p.n, p.input_knots);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const int grid = (p.tiles + 255) / 256 < 148 * 8 ? (p.tiles + 255) / 256 : 148 * 8;
-    compact_from_mask_kernel<InT, CarryT><<<grid, 256, 0, st>>>(p.out, p.x, p.sig0, p.n, p.tiles, -1, nullptr);
+    compact_from_mask_kernel<InT, CarryT><<<compact_grid(p.tiles), 256, 0, st>>>(p.out, p.x, p.sig0, p.n, p.tiles, -1, nullptr);
     return cudaGetLastError();
 }
 
@@ -247,6 +252,9 @@ static cudaError_t launch_scan(const pyitd_plan *pl, const ScanParams &p, cudaSt
     if (strided_launchable_fwd(pl, p.x)) {
         // a few long signals: one after the other, each launch fills the device
         ScanParams q = p;
+        // the per-group knot sums start from zero (a single-level call leaves its level kernel's sums unconsumed)
+        cudaError_t ze = cudaMemsetAsync(p.out.gsum, 0, (size_t)pl->S * (size_t)p.out.gstride * sizeof(int), st);
+        if (ze != cudaSuccess) return ze;
         for (long long sg = 0; sg < pl->S; ++sg) {
             q.sig0 = (int)sg;
             cudaError_t e;
@@ -519,7 +527,9 @@ static int ensure_workspace(pyitd_plan *pl) {
     const size_t b_sig = align_up((size_t)pl->S * sizeof(int));
     const size_t b_endl = align_up((size_t)pl->S * 2 * pl->carry_elem);
     const size_t b_desc = align_up((size_t)pl->S * pl->tiles * sizeof(unsigned long long));
-    size_t total = 2 * b_carry + 2 * (b_tau + b_xk + b_tbase + b_sig + b_endl + b_mask) + b_desc + 3 * b_sig;
+    const long long gstride = pl->strided ? ((((long long)pl->tiles + 31) / 32 + 1 + 3) & ~3ll) : 0;
+    const size_t b_group = align_up((size_t)pl->S * (size_t)gstride * sizeof(int));
+    size_t total = 2 * b_carry + 2 * (b_tau + b_xk + b_tbase + b_sig + b_endl + b_mask) + b_desc + 3 * b_sig + 2 * b_group;
     pl->ws_bytes = total;
     cudaError_t ce = cudaMalloc(&pl->ws, total);
     if (ce != cudaSuccess) {
@@ -545,6 +555,14 @@ static int ensure_workspace(pyitd_plan *pl) {
     pl->stop_e = (int *)take(b_sig);
     pl->stop_kind = (int *)take(b_sig);
     pl->input_knots = (int *)take(b_sig);
+    {
+        int *gsum = (int *)take(b_group), *gbase = (int *)take(b_group);
+        for (int i = 0; i < 2; ++i) {
+            pl->table[i].gsum = pl->strided ? gsum : nullptr;
+            pl->table[i].gbase = pl->strided ? gbase : nullptr;
+            pl->table[i].gstride = gstride;
+        }
+    }
     // the mask rows are padded to 4 words: the padding (and everything else) starts out as "no knot"
     ce = cudaMemset(pl->table[0].mask, 0, b_mask);
     if (ce == cudaSuccess) ce = cudaMemset(pl->table[1].mask, 0, b_mask);
@@ -637,7 +655,7 @@ static bool strided_launchable(const pyitd_plan *pl, const void *in) {
 // tile_prefix_kernel + compact_from_mask_kernel on the table the level launch `lp` just produced
 static int run_strided_passes(pyitd_plan *pl, const LevelParams &lp, cudaStream_t st) {
     const int last = (lp.e == lp.emax) ? 1 : 0;
-    int grid = (pl->tiles + 255) / 256 < 148 * 8 ? (pl->tiles + 255) / 256 : 148 * 8;
+    const int grid = compact_grid(pl->tiles);
     for (long long sg = 0; sg < pl->S; ++sg) {
     const int sig0 = (int)sg;
     if (pl->carry_elem == 8) {

@@ -187,6 +187,11 @@ struct KnotTable {
     unsigned *mask;  // [S, mstride] knot flags, bit (t & 31) of word (t >> 5)
     long long kstride;   // entries per signal in tau/xk: N rounded up to 4, + 4 (16-byte aligned rows)
     long long mstride;   // words per signal in mask: ceil(N/32) rounded up to 4
+    // strided path only (itd_strided.cuh), shared by both tables: knots per GROUP of 32 tiles, accumulated by the level /
+    // scan kernel with one reduction per non-empty tile, and the groups' exclusive prefix (tile_prefix_kernel)
+    int *gsum;           // [S, gstride]  zero between uses (the prefix kernel clears what it read)
+    int *gbase;          // [S, gstride]
+    long long gstride;
 };
 
 struct ScanParams {

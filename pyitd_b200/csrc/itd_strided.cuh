@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_strided_kernel(const Leve
     CarryT *nxk = reinterpret_cast<CarryT *>(p.next.xk) + (long long)sig * p.next.kstride;
     unsigned *nmask0 = p.next.mask + (long long)sig * p.next.mstride + warp * ITEMS + lane;
     int *ntbase = p.next.tbase + (long long)sig * (tiles + 1);
+    int *ngsum = p.next.gsum + (long long)sig * p.next.gstride;
     CarryT *nendl = reinterpret_cast<CarryT *>(p.next.endl) + 2ll * sig;
     LS *ls = sm.ls[warp];
     const unsigned le_mask = 0xffffffffu >> (31 - lane);
@@ -309,7 +310,8 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_strided_kernel(const Leve
             int tot = 0;
 #pragma unroll
             for (int w = 0; w < WARPS; ++w) tot += sm.cnt[k & 1][w];
-            ntbase[i] = tot;                             // tile_prefix_kernel turns counts into the exclusive prefix
+            ntbase[i] = tot;                             // the compaction pass turns counts into the exclusive prefix
+            if (tot) atomicAdd(ngsum + (i >> 5), tot);   // knots per group of 32 tiles (tile_prefix_kernel scans these)
         }
     };
 
@@ -381,6 +383,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) scan_strided_kernel(const ScanP
     CarryT *nxk = reinterpret_cast<CarryT *>(p.out.xk) + (long long)sig * p.out.kstride;
     unsigned *nmask0 = p.out.mask + (long long)sig * p.out.mstride + warp * ITEMS + lane;
     int *ntbase = p.out.tbase + (long long)sig * (tiles + 1);
+    int *ngsum = p.out.gsum + (long long)sig * p.out.gstride;
     CarryT *nendl = reinterpret_cast<CarryT *>(p.out.endl) + 2ll * sig;
     bool bad = false;
 
@@ -444,6 +447,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) scan_strided_kernel(const ScanP
 #pragma unroll
             for (int w = 0; w < WARPS; ++w) tot += sm.cnt[k & 1][w];
             ntbase[i] = tot;
+            if (tot) atomicAdd(ngsum + (i >> 5), tot);
         }
     };
     for (int k = 0; k < my_tiles; ++k) {
@@ -456,33 +460,68 @@ __global__ void __launch_bounds__(WARPS * 32, 4) scan_strided_kernel(const ScanP
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.status + sig, kStNonFinite);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Exclusive prefix of the per-GROUP knot sums gsum[0 .. groups) into gbase by ONE block of 1024 threads; gsum is
+// cleared on the way (it is accumulated again by the next level kernel); returns the total (valid in every thread).
+// A group is 32 tiles, so 2^28 samples are 8192 groups: eight entries per thread.  Warp w owns a contiguous run; a
+// lane takes four consecutive entries per round.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_group_prefix_1024(int *gsum, int *gbase, const int groups) {
+    __shared__ int s_warp[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rounds = (groups + 32 * 128 - 1) / (32 * 128);          // rounds of 128 entries per warp
+    const int w0 = warp * rounds * 128;                                 // first entry of this warp's run
+    auto load4 = [&](const int r, int (&v)[4]) {
+        const int i0 = w0 + r * 128 + lane * 4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (i0 + u < groups) ? gsum[i0 + u] : 0;
+    };
+    int sum = 0;
+    for (int r = 0; r < rounds; ++r) {
+        int v[4];
+        load4(r, v);
+        sum += v[0] + v[1] + v[2] + v[3];
+    }
+    sum = __reduce_add_sync(0xffffffffu, sum);
+    if (lane == 0) s_warp[warp] = sum;
+    __syncthreads();
+    const int wt = s_warp[lane];
+    const int total = __reduce_add_sync(0xffffffffu, wt);
+    int run = __reduce_add_sync(0xffffffffu, (lane < warp) ? wt : 0);   // knots before this warp's run
+    for (int r = 0; r < rounds; ++r) {
+        int v[4];
+        load4(r, v);
+        const int mine = v[0] + v[1] + v[2] + v[3];
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int ex = run + incl - mine;
+        const int i0 = w0 + r * 128 + lane * 4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + u < groups) {
+                gbase[i0 + u] = ex;
+                gsum[i0 + u] = 0;
+            }
+            ex += v[u];
+        }
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    return total;
+}
+
 // tile_prefix for the scan pass: no stop rule; the closing knot carries x[n-1]; K is the input's knot count
 template <typename InT, typename CarryT>
 __global__ void __launch_bounds__(1024) tile_prefix_scan_kernel(KnotTable out, const void *xin, int sig, int tiles, int n,
                                                                 int *input_knots) {
-    __shared__ int s_part[1024];
     const int tid = threadIdx.x;
     int *tb = out.tbase + (long long)sig * (tiles + 1);
-    const int per = (tiles + 1023) / 1024;
-    const int lo = min(tid * per, tiles), hi = min(lo + per, tiles);
-    int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += tb[i];
-    s_part[tid] = sum;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const int v = (tid >= o) ? s_part[tid - o] : 0;
-        __syncthreads();
-        s_part[tid] += v;
-        __syncthreads();
-    }
-    int run = s_part[tid] - sum;
-    for (int i = lo; i < hi; ++i) {
-        const int c = tb[i];
-        tb[i] = run;
-        run += c;
-    }
-    if (tid == 1023) {
-        const int K = s_part[1023];
+    const int K = block_group_prefix_1024(out.gsum + (long long)sig * out.gstride, out.gbase + (long long)sig * out.gstride,
+                                          (tiles + 31) >> 5);
+    if (tid == 0) {
         const InT *x = reinterpret_cast<const InT *>(xin) + (long long)sig * n;
         int *tau = out.tau + (long long)sig * out.kstride;
         CarryT *xk = reinterpret_cast<CarryT *>(out.xk) + (long long)sig * out.kstride;
@@ -495,38 +534,20 @@ __global__ void __launch_bounds__(1024) tile_prefix_scan_kernel(KnotTable out, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// tile_prefix_kernel: per-tile knot counts -> exclusive prefix (in place), K, the closing knot (ITD.py:98),
-// what ITD.py:403 prints and the stop rule (ITD.py:404, :418).  One block; a thread owns a run of tiles.
+// tile_prefix_kernel: per-group knot sums -> exclusive prefix over the groups, K, the closing knot (ITD.py:98),
+// what ITD.py:403 prints and the stop rule (ITD.py:404, :418).  One block.  (The per-tile prefix inside a group is
+// finished by the warp of compact_from_mask_kernel that owns the group.)
 // ---------------------------------------------------------------------------------------------
 template <typename CarryT>
 __global__ void __launch_bounds__(1024) tile_prefix_kernel(KnotTable next, int sig, int tiles, int n, int e, int rows,
                                                            int min_extrema, int last, int *stop_e, int *stop_kind,
                                                            int *n_rows, int *knot_counts) {
-    __shared__ int s_part[1024];
     const int tid = threadIdx.x;
     if (e > stop_e[sig]) return;                          // the level kernel did nothing either
     int *tb = next.tbase + (long long)sig * (tiles + 1);
-    const int per = (tiles + 1023) / 1024;
-    const int lo = min(tid * per, tiles), hi = min(lo + per, tiles);
-    int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += tb[i];
-    s_part[tid] = sum;
-    __syncthreads();
-    // inclusive scan of the 1024 partial sums (Hillis-Steele; once per level)
-    for (int o = 1; o < 1024; o <<= 1) {
-        const int v = (tid >= o) ? s_part[tid - o] : 0;
-        __syncthreads();
-        s_part[tid] += v;
-        __syncthreads();
-    }
-    int run = s_part[tid] - sum;
-    for (int i = lo; i < hi; ++i) {
-        const int c = tb[i];
-        tb[i] = run;
-        run += c;
-    }
-    if (tid == 1023) {
-        const int Kn = s_part[1023];
+    const int Kn = block_group_prefix_1024(next.gsum + (long long)sig * next.gstride,
+                                           next.gbase + (long long)sig * next.gstride, (tiles + 31) >> 5);
+    if (tid == 0) {
         int *ntau = next.tau + (long long)sig * next.kstride;
         CarryT *nxk = reinterpret_cast<CarryT *>(next.xk) + (long long)sig * next.kstride;
         tb[tiles] = Kn;
@@ -554,48 +575,71 @@ __global__ void __launch_bounds__(1024) tile_prefix_kernel(KnotTable next, int s
 template <typename SrcT, typename CarryT>
 __global__ void __launch_bounds__(256) compact_from_mask_kernel(KnotTable next, const void *carry_in, int sig, int n,
                                                                 int tiles, int e_guard, const int *stop_e) {
-    constexpr int T = 1024;
+    constexpr int T = 1024, CH = 16;                          // CH flag words (512 samples) of loads in flight per lane
     if (stop_e && stop_e[sig] < e_guard) return;            // the level kernel of e_guard never ran (stop_e null: scan pass)
     const int lane = threadIdx.x & 31;
     const int gwarp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5);
-    const SrcT *carry = reinterpret_cast<const SrcT *>(carry_in) + (long long)sig * n;
-    const unsigned *mask = next.mask + (long long)sig * next.mstride;
-    const int *tb = next.tbase + (long long)sig * (tiles + 1);
-    int *tau = next.tau + (long long)sig * next.kstride + 1;
-    CarryT *xk = reinterpret_cast<CarryT *>(next.xk) + (long long)sig * next.kstride + 1;
+    const SrcT *__restrict__ carry = reinterpret_cast<const SrcT *>(carry_in) + (long long)sig * n;
+    const unsigned *__restrict__ mask = next.mask + (long long)sig * next.mstride;
+    int *tb = next.tbase + (long long)sig * (tiles + 1);
+    const int *__restrict__ gbase = next.gbase + (long long)sig * next.gstride;
+    int *__restrict__ tau = next.tau + (long long)sig * next.kstride + 1;
+    CarryT *__restrict__ xk = reinterpret_cast<CarryT *>(next.xk) + (long long)sig * next.kstride + 1;
     const unsigned lt_mask = (1u << lane) - 1u;
-    // a WARP owns 32 consecutive tiles at a time (one coalesced read of their prefix entries) and works through the
-    // non-empty ones with no block barrier: on a deep level almost every tile is knot-free, on a dense one every warp
-    // streams its tiles with independent loads in flight
-    for (int ib = gwarp * 32; ib < tiles; ib += nwarps * 32) {
-        const int i_l = ib + lane;
-        const int base_l = (i_l < tiles) ? tb[i_l] : 0;
-        const int cnt_l = (i_l < tiles) ? tb[i_l + 1] - base_l : 0;
+    const int groups = (tiles + 31) >> 5;
+    // a WARP owns a group of 32 consecutive tiles: it finishes their exclusive knot prefix (group base + a shuffle scan
+    // of the per-tile counts, stored for the next level kernel), then works through the non-empty tiles with no block
+    // barrier; the next tile's flag words are fetched while the current tile is written
+    for (int g = gwarp; g < groups; g += nwarps) {
+        const int i_l = g * 32 + lane;
+        const int cnt_l = (i_l < tiles) ? tb[i_l] : 0;
+        int incl = cnt_l;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int base_l = gbase[g] + incl - cnt_l;
+        if (i_l < tiles) tb[i_l] = base_l;
         unsigned live = __ballot_sync(0xffffffffu, cnt_l > 0);
+        auto load_words = [&](const int j) -> unsigned {
+            const int t0 = (g * 32 + j) * T;
+            const int nwords = (min(T, n - t0) + 31) >> 5;
+            return (lane < nwords) ? mask[(t0 >> 5) + lane] : 0u;
+        };
+        unsigned word_next = live ? load_words(__ffs(live) - 1) : 0u;
         while (live) {
             const int j = __ffs(live) - 1;
             live &= live - 1;
-            const int i = ib + j;
-            const int t0 = i * T;
+            const unsigned word = word_next;
+            if (live) word_next = load_words(__ffs(live) - 1);
+            const int t0 = (g * 32 + j) * T;
             const int base = __shfl_sync(0xffffffffu, base_l, j);
-            const int nwords = (min(T, n - t0) + 31) >> 5;
-            const unsigned word = (lane < nwords) ? mask[(t0 >> 5) + lane] : 0u;
-            int incl = __popc(word);
+            int wi = __popc(word);
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
+                const int v = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += v;
             }
-            const int pre = base + incl - __popc(word);               // rank of the first knot of this lane's word
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-                const unsigned w = __shfl_sync(0xffffffffu, word, r);
-                const int pr = __shfl_sync(0xffffffffu, pre, r);
-                if ((w >> lane) & 1u) {
-                    const int t = t0 + r * 32 + lane;
-                    const int rank = pr + __popc(w & lt_mask);
-                    tau[rank] = t;
-                    xk[rank] = (CarryT)carry[t];
+            const int pre = base + wi - __popc(word);                 // rank of the first knot of this lane's word
+#pragma unroll
+            for (int c = 0; c < 32; c += CH) {
+                if (__ballot_sync(0xffffffffu, (lane >= c && lane < c + CH) && word != 0u) == 0u) continue;
+                SrcT v[CH];
+                unsigned w[CH];
+#pragma unroll
+                for (int r = 0; r < CH; ++r) {                        // all loads of the chunk first ...
+                    w[r] = __shfl_sync(0xffffffffu, word, c + r);
+                    v[r] = ((w[r] >> lane) & 1u) ? carry[t0 + (c + r) * 32 + lane] : (SrcT)0;
+                }
+#pragma unroll
+                for (int r = 0; r < CH; ++r) {                        // ... then the stores
+                    const int pr = __shfl_sync(0xffffffffu, pre, c + r);
+                    if ((w[r] >> lane) & 1u) {
+                        const int rank = pr + __popc(w[r] & lt_mask);
+                        tau[rank] = t0 + (c + r) * 32 + lane;
+                        xk[rank] = (CarryT)v[r];
+                    }
                 }
             }
         }
