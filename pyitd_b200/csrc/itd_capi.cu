@@ -206,10 +206,12 @@ static cudaError_t launch_strided_t(const LevelParams &p, int cap, cudaStream_t 
                : launch_strided_v<InT, CarryT, OutT, false, false>(p, cap, st);
 }
 
-// compaction pass: a warp owns a group of 32 tiles, 8 warps per block, as many blocks as there are groups (at most 8 per SM x 4 rounds)
+// place_knots_kernel: a warp owns a group of 32 tiles, 8 warps per block; 4 blocks per SM measured best on 2^28 samples
+// (profiles/r1/s5/place_sweep.log: more blocks only widen the window of DRAM pages in flight)
 static int compact_grid(int tiles) {
     const int groups = (tiles + 31) / 32, blocks = (groups + 7) / 8;
-    return blocks < 148 * 32 ? blocks : 148 * 32;
+    static const int cap = getenv("PYITD_PLACE_BLOCKS") ? atoi(getenv("PYITD_PLACE_BLOCKS")) : 148 * 4;   // test hook
+    return blocks < cap ? blocks : cap;
 }
 
 // the strided path's knot scan: flag words + per-tile counts, then the prefix and the compaction pass
@@ -234,7 +236,7 @@ static cudaError_t launch_scan_strided_t(const pyitd_plan *pl, const ScanParams 
     tile_prefix_scan_kernel<InT, CarryT><<<1, 1024, 0, st>>>(p.out, p.x, p.sig0, p.tiles, p.n, p.input_knots);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    compact_from_mask_kernel<InT, CarryT><<<compact_grid(p.tiles), 256, 0, st>>>(p.out, p.x, p.sig0, p.n, p.tiles, -1, nullptr);
+    place_knots_kernel<CarryT><<<compact_grid(p.tiles), 256, 0, st>>>(p.out, p.sig0, p.tiles, -1, nullptr);
     return cudaGetLastError();
 }
 
@@ -529,7 +531,8 @@ static int ensure_workspace(pyitd_plan *pl) {
     const size_t b_desc = align_up((size_t)pl->S * pl->tiles * sizeof(unsigned long long));
     const long long gstride = pl->strided ? ((((long long)pl->tiles + 31) / 32 + 1 + 3) & ~3ll) : 0;
     const size_t b_group = align_up((size_t)pl->S * (size_t)gstride * sizeof(int));
-    size_t total = 2 * b_carry + 2 * (b_tau + b_xk + b_tbase + b_sig + b_endl + b_mask) + b_desc + 3 * b_sig + 2 * b_group;
+    const size_t b_stage = pl->strided ? b_tau + b_xk : 0;             // tile-local knot staging of the strided path
+    size_t total = 2 * b_carry + 2 * (b_tau + b_xk + b_tbase + b_sig + b_endl + b_mask) + b_desc + 3 * b_sig + 2 * b_group + b_stage;
     pl->ws_bytes = total;
     cudaError_t ce = cudaMalloc(&pl->ws, total);
     if (ce != cudaSuccess) {
@@ -557,7 +560,11 @@ static int ensure_workspace(pyitd_plan *pl) {
     pl->input_knots = (int *)take(b_sig);
     {
         int *gsum = (int *)take(b_group), *gbase = (int *)take(b_group);
+        int *stau = pl->strided ? (int *)take(b_tau) : nullptr;
+        void *sxk = pl->strided ? take(b_xk) : nullptr;
         for (int i = 0; i < 2; ++i) {
+            pl->table[i].stau = stau;
+            pl->table[i].sxk = sxk;
             pl->table[i].gsum = pl->strided ? gsum : nullptr;
             pl->table[i].gbase = pl->strided ? gbase : nullptr;
             pl->table[i].gstride = gstride;
@@ -652,7 +659,7 @@ static int run_scan(pyitd_plan *pl, const void *x, int *status, int *input_knots
 static bool strided_launchable(const pyitd_plan *pl, const void *in) {
     return pl->strided && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
 }
-// tile_prefix_kernel + compact_from_mask_kernel on the table the level launch `lp` just produced
+// tile_prefix_kernel + place_knots_kernel on the table the level launch `lp` just produced
 static int run_strided_passes(pyitd_plan *pl, const LevelParams &lp, cudaStream_t st) {
     const int last = (lp.e == lp.emax) ? 1 : 0;
     const int grid = compact_grid(pl->tiles);
@@ -662,12 +669,12 @@ static int run_strided_passes(pyitd_plan *pl, const LevelParams &lp, cudaStream_
         tile_prefix_kernel<double><<<1, 1024, 0, st>>>(lp.next, sig0, lp.tiles, lp.n, lp.e, lp.rows, lp.min_extrema, last,
                                                        lp.stop_e, lp.stop_kind, lp.n_rows, lp.knot_counts);
         CU(cudaGetLastError());
-        compact_from_mask_kernel<double, double><<<grid, 256, 0, st>>>(lp.next, lp.carry_out, sig0, lp.n, lp.tiles, lp.e, lp.stop_e);
+        place_knots_kernel<double><<<grid, 256, 0, st>>>(lp.next, sig0, lp.tiles, lp.e, lp.stop_e);
     } else {
         tile_prefix_kernel<float><<<1, 1024, 0, st>>>(lp.next, sig0, lp.tiles, lp.n, lp.e, lp.rows, lp.min_extrema, last,
                                                       lp.stop_e, lp.stop_kind, lp.n_rows, lp.knot_counts);
         CU(cudaGetLastError());
-        compact_from_mask_kernel<float, float><<<grid, 256, 0, st>>>(lp.next, lp.carry_out, sig0, lp.n, lp.tiles, lp.e, lp.stop_e);
+        place_knots_kernel<float><<<grid, 256, 0, st>>>(lp.next, sig0, lp.tiles, lp.e, lp.stop_e);
     }
     CU(cudaGetLastError());
     pl->launches += 2;

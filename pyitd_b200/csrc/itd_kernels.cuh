@@ -192,6 +192,8 @@ struct KnotTable {
     int *gsum;           // [S, gstride]  zero between uses (the prefix kernel clears what it read)
     int *gbase;          // [S, gstride]
     long long gstride;
+    int *stau;           // [S, kstride]  tile-local compaction: the knots of tile i at [i * T, i * T + count_i)
+    void *sxk;           // [S, kstride]  (carry type)
 };
 
 struct ScanParams {

@@ -10,12 +10,14 @@
 // pipeline as level_stream_kernel -- TMA ring for the samples, the flag words and the knot-table slice,
 // warp-private knot baseline / slopes (ITD.py:106-110, :116), B, R, the stencil on B -- with two changes
 // that remove the in-order carry between neighbouring tiles:
-//   * the level kernel does NOT compact the next level's knots: it stores their flag words and the tile's
-//     knot count only.  A rank needs the number of knots in ALL earlier tiles; a look-back chain inside a
-//     persistent grid puts every block in lock-step with the slowest one (measured: 5.1 ms per level, worse
-//     than one CTA per tile).  Instead tile_prefix_kernel turns the counts into the per-tile prefix (and
-//     applies the stop rule, ITD.py:400-404 / :418), and compact_from_mask_kernel writes (tau_k, X_k) from
-//     the flag words and the carry: the "extrema-compaction pass" as a pass of its own;
+//   * the level kernel cannot know the global rank of a new knot: that needs the number of knots in ALL earlier tiles,
+//     and a look-back chain inside a persistent grid puts every block in lock-step with the slowest one (measured:
+//     5.1 ms per level, worse than one CTA per tile).  So it compacts the new knots INSIDE the tile -- (tau, X) go to
+//     the tile's own slot [i*T, i*T + count_i) of the staging arrays, values straight from registers -- stores the flag
+//     words and the tile's count, and adds the count to the sum of its group of 32 tiles (one reduction per non-empty
+//     tile).  tile_prefix_kernel scans the group sums (8192 for 2^28 samples) and applies the stop rule
+//     (ITD.py:400-404 / :418); place_knots_kernel finishes the per-tile prefix and moves every slot to its global rank
+//     with contiguous loads and stores: the second half of the "extrema-compaction pass";
 //   * the halo samples x[t0 - 1], x[t0 + T] and the flag of sample t0 + T ride in with the tile (the TMA
 //     slice is four samples / four flag words wider on each side), so the first warp evaluates B[t0 - 1]
 //     from the knot table like every other warp and nobody peeks into a neighbour's stage.
@@ -157,6 +159,8 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_strided_kernel(const Leve
     unsigned *nmask0 = p.next.mask + (long long)sig * p.next.mstride + warp * ITEMS + lane;
     int *ntbase = p.next.tbase + (long long)sig * (tiles + 1);
     int *ngsum = p.next.gsum + (long long)sig * p.next.gstride;
+    int *stau = p.next.stau + (long long)sig * p.next.kstride;
+    CarryT *sxk = reinterpret_cast<CarryT *>(p.next.sxk) + (long long)sig * p.next.kstride;
     CarryT *nendl = reinterpret_cast<CarryT *>(p.next.endl) + 2ll * sig;
     LS *ls = sm.ls[warp];
     const unsigned le_mask = 0xffffffffu >> (31 - lane);
@@ -302,16 +306,28 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_strided_kernel(const Leve
                 nendl[0] = mean2<CarryT>(b[0], b1);
             }
         }
-        // ---- E. the tile's knot count (ranks are assigned by the compaction pass) ------------------
+        // ---- E. one block barrier: exchange the per-warp counts, then compact the new knots INSIDE the tile's own
+        // slot of the staging arrays (the global ranks are assigned by place_knots_kernel) -------------------------
         if (lane == 0) sm.cnt[k & 1][warp] = newc;
         named_barrier_sync(1, WARPS * 32);               // also: every warp is past its reads of stage s
+        if (tid == 0 && k + STAGES < my_tiles) issue_tile(k + STAGES, pf_kb, pf_kb1);
+        const int c = (lane < WARPS) ? sm.cnt[k & 1][lane] : 0;
+        const int tot = __reduce_add_sync(0xffffffffu, c);
+        int pre = t0 + __reduce_add_sync(0xffffffffu, (lane < warp) ? c : 0);
         if (tid == 0) {
-            if (k + STAGES < my_tiles) issue_tile(k + STAGES, pf_kb, pf_kb1);
-            int tot = 0;
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) tot += sm.cnt[k & 1][w];
-            ntbase[i] = tot;                             // the compaction pass turns counts into the exclusive prefix
+            ntbase[i] = tot;                             // place_knots_kernel turns counts into the exclusive prefix
             if (tot) atomicAdd(ngsum + (i >> 5), tot);   // knots per group of 32 tiles (tile_prefix_kernel scans these)
+        }
+        // (skipping this for knot-free tiles was measured: deep levels -0.02 ms, mid levels +0.05 ms each; not kept)
+        const unsigned lt_mask = le_mask >> 1;
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+            if ((fw[r] >> lane) & 1u) {
+                const int rank = pre + __popc(fw[r] & lt_mask);
+                stau[rank] = t0 + span0 + r * 32 + lane;
+                sxk[rank] = b[r];
+            }
+            pre += __popc(fw[r]);
         }
     };
 
@@ -331,7 +347,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_strided_kernel(const Leve
 
 // ---------------------------------------------------------------------------------------------
 // scan_strided_kernel: extrema of the raw input (ITD.py:87-98) for ONE long signal -- flag words and per-tile
-// counts only (tile_prefix_kernel / compact_from_mask_kernel finish the table).  Same persistent striding
+// counts + tile-local knot slots (tile_prefix_scan_kernel / place_knots_kernel finish the table).  Same persistent striding
 // and halo-carrying TMA slices as level_strided_kernel.
 // ---------------------------------------------------------------------------------------------
 template <typename InT, int WARPS, int ITEMS>
@@ -384,6 +400,8 @@ __global__ void __launch_bounds__(WARPS * 32, 4) scan_strided_kernel(const ScanP
     unsigned *nmask0 = p.out.mask + (long long)sig * p.out.mstride + warp * ITEMS + lane;
     int *ntbase = p.out.tbase + (long long)sig * (tiles + 1);
     int *ngsum = p.out.gsum + (long long)sig * p.out.gstride;
+    int *stau = p.out.stau + (long long)sig * p.out.kstride;
+    CarryT *sxk = reinterpret_cast<CarryT *>(p.out.sxk) + (long long)sig * p.out.kstride;
     CarryT *nendl = reinterpret_cast<CarryT *>(p.out.endl) + 2ll * sig;
     bool bad = false;
 
@@ -441,13 +459,23 @@ __global__ void __launch_bounds__(WARPS * 32, 4) scan_strided_kernel(const ScanP
         }
         if (lane == 0) sm.cnt[k & 1][warp] = newc;
         named_barrier_sync(1, WARPS * 32);               // also: every warp is past its reads of stage s
+        if (tid == 0 && k + STAGES < my_tiles) issue_tile(k + STAGES);
+        const int c = (lane < WARPS) ? sm.cnt[k & 1][lane] : 0;
+        const int tot = __reduce_add_sync(0xffffffffu, c);
+        int pre = t0 + __reduce_add_sync(0xffffffffu, (lane < warp) ? c : 0);
         if (tid == 0) {
-            if (k + STAGES < my_tiles) issue_tile(k + STAGES);
-            int tot = 0;
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) tot += sm.cnt[k & 1][w];
             ntbase[i] = tot;
             if (tot) atomicAdd(ngsum + (i >> 5), tot);
+        }
+        const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {                // tile-local compaction (see level_strided_kernel)
+            if ((fw[r] >> lane) & 1u) {
+                const int rank = pre + __popc(fw[r] & lt_mask);
+                stau[rank] = t0 + span0 + r * 32 + lane;
+                sxk[rank] = v[r];
+            }
+            pre += __popc(fw[r]);
         }
     };
     for (int k = 0; k < my_tiles; ++k) {
@@ -536,7 +564,7 @@ __global__ void __launch_bounds__(1024) tile_prefix_scan_kernel(KnotTable out, c
 // ---------------------------------------------------------------------------------------------
 // tile_prefix_kernel: per-group knot sums -> exclusive prefix over the groups, K, the closing knot (ITD.py:98),
 // what ITD.py:403 prints and the stop rule (ITD.py:404, :418).  One block.  (The per-tile prefix inside a group is
-// finished by the warp of compact_from_mask_kernel that owns the group.)
+// finished by the warp of place_knots_kernel that owns the group.)
 // ---------------------------------------------------------------------------------------------
 template <typename CarryT>
 __global__ void __launch_bounds__(1024) tile_prefix_kernel(KnotTable next, int sig, int tiles, int n, int e, int rows,
@@ -568,28 +596,27 @@ __global__ void __launch_bounds__(1024) tile_prefix_kernel(KnotTable next, int s
 }
 
 // ---------------------------------------------------------------------------------------------
-// compact_from_mask_kernel: the extrema-compaction pass.  (tau_k, X_k) of the next level from its flag words,
-// the per-tile prefix and the carry B (X_k = B[tau_k]).  Persistent blocks over 1024-sample tiles.
-// e_guard: the level whose output is compacted; nothing to do once the signal stopped before it.
+// place_knots_kernel: the second half of the extrema-compaction pass.  The level / scan kernel left the knots of tile i
+// compacted inside the tile's own slot of the staging arrays, stau / sxk [i * T, i * T + count_i); this pass finishes the
+// per-tile exclusive prefix (group base + a shuffle scan of 32 counts, stored for the next level kernel) and moves every
+// slot to its global rank: tau[1 + rank], xk[1 + rank].  A WARP owns a group of 32 consecutive tiles and walks the
+// group's knots 32 at a time -- lane q finds its tile by a five-step search over the 32 prefix values held in the
+// warp's registers -- so loads and stores are contiguous runs and nothing waits on a block barrier.
+// e_guard: the level whose output is placed; nothing to do once the signal stopped before it.
 // ---------------------------------------------------------------------------------------------
-template <typename SrcT, typename CarryT>
-__global__ void __launch_bounds__(256) compact_from_mask_kernel(KnotTable next, const void *carry_in, int sig, int n,
-                                                                int tiles, int e_guard, const int *stop_e) {
-    constexpr int T = 1024, CH = 16;                          // CH flag words (512 samples) of loads in flight per lane
+template <typename CarryT>
+__global__ void __launch_bounds__(256) place_knots_kernel(KnotTable next, int sig, int tiles, int e_guard, const int *stop_e) {
+    constexpr int T = 1024;
     if (stop_e && stop_e[sig] < e_guard) return;            // the level kernel of e_guard never ran (stop_e null: scan pass)
     const int lane = threadIdx.x & 31;
     const int gwarp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5);
-    const SrcT *__restrict__ carry = reinterpret_cast<const SrcT *>(carry_in) + (long long)sig * n;
-    const unsigned *__restrict__ mask = next.mask + (long long)sig * next.mstride;
     int *tb = next.tbase + (long long)sig * (tiles + 1);
     const int *__restrict__ gbase = next.gbase + (long long)sig * next.gstride;
+    const int *__restrict__ stau = next.stau + (long long)sig * next.kstride;
+    const CarryT *__restrict__ sxk = reinterpret_cast<const CarryT *>(next.sxk) + (long long)sig * next.kstride;
     int *__restrict__ tau = next.tau + (long long)sig * next.kstride + 1;
     CarryT *__restrict__ xk = reinterpret_cast<CarryT *>(next.xk) + (long long)sig * next.kstride + 1;
-    const unsigned lt_mask = (1u << lane) - 1u;
     const int groups = (tiles + 31) >> 5;
-    // a WARP owns a group of 32 consecutive tiles: it finishes their exclusive knot prefix (group base + a shuffle scan
-    // of the per-tile counts, stored for the next level kernel), then works through the non-empty tiles with no block
-    // barrier; the next tile's flag words are fetched while the current tile is written
     for (int g = gwarp; g < groups; g += nwarps) {
         const int i_l = g * 32 + lane;
         const int cnt_l = (i_l < tiles) ? tb[i_l] : 0;
@@ -599,49 +626,38 @@ __global__ void __launch_bounds__(256) compact_from_mask_kernel(KnotTable next, 
             const int v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
-        const int base_l = gbase[g] + incl - cnt_l;
-        if (i_l < tiles) tb[i_l] = base_l;
-        unsigned live = __ballot_sync(0xffffffffu, cnt_l > 0);
-        auto load_words = [&](const int j) -> unsigned {
-            const int t0 = (g * 32 + j) * T;
-            const int nwords = (min(T, n - t0) + 31) >> 5;
-            return (lane < nwords) ? mask[(t0 >> 5) + lane] : 0u;
-        };
-        unsigned word_next = live ? load_words(__ffs(live) - 1) : 0u;
-        while (live) {
-            const int j = __ffs(live) - 1;
-            live &= live - 1;
-            const unsigned word = word_next;
-            if (live) word_next = load_words(__ffs(live) - 1);
-            const int t0 = (g * 32 + j) * T;
-            const int base = __shfl_sync(0xffffffffu, base_l, j);
-            int wi = __popc(word);
+        const int ex_l = incl - cnt_l;                                // knots of the group before tile `lane`
+        const int base = gbase[g];
+        if (i_l < tiles) tb[i_l] = base + ex_l;
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const long long slot0 = (long long)g * 32 * T;
+        for (int q0 = 0; q0 < total; q0 += 128) {
+            int src[4], tv[4];
+            CarryT xv[4];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += v;
+            for (int u = 0; u < 4; ++u) {
+                const int q = q0 + u * 32 + lane;
+                int j = 0;                                            // last tile with ex_j <= q (it is never empty)
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int v = __shfl_sync(0xffffffffu, ex_l, (j + step) & 31);
+                    if (v <= q) j += step;
+                }
+                const int ex_j = __shfl_sync(0xffffffffu, ex_l, j);
+                src[u] = (q < total) ? j * T + (q - ex_j) : -1;
             }
-            const int pre = base + wi - __popc(word);                 // rank of the first knot of this lane's word
 #pragma unroll
-            for (int c = 0; c < 32; c += CH) {
-                if (__ballot_sync(0xffffffffu, (lane >= c && lane < c + CH) && word != 0u) == 0u) continue;
-                SrcT v[CH];
-                unsigned w[CH];
-#pragma unroll
-                for (int r = 0; r < CH; ++r) {                        // all loads of the chunk first ...
-                    w[r] = __shfl_sync(0xffffffffu, word, c + r);
-                    v[r] = ((w[r] >> lane) & 1u) ? carry[t0 + (c + r) * 32 + lane] : (SrcT)0;
+            for (int u = 0; u < 4; ++u)
+                if (src[u] >= 0) {
+                    tv[u] = stau[slot0 + src[u]];
+                    xv[u] = sxk[slot0 + src[u]];
                 }
 #pragma unroll
-                for (int r = 0; r < CH; ++r) {                        // ... then the stores
-                    const int pr = __shfl_sync(0xffffffffu, pre, c + r);
-                    if ((w[r] >> lane) & 1u) {
-                        const int rank = pr + __popc(w[r] & lt_mask);
-                        tau[rank] = t0 + (c + r) * 32 + lane;
-                        xk[rank] = (CarryT)v[r];
-                    }
+            for (int u = 0; u < 4; ++u)
+                if (src[u] >= 0) {
+                    tau[base + q0 + u * 32 + lane] = tv[u];
+                    xk[base + q0 + u * 32 + lane] = xv[u];
                 }
-            }
         }
     }
 }
