@@ -65,6 +65,8 @@ struct pyitd_plan {
     size_t ws_bytes = 0;
     void *carry[2] = {nullptr, nullptr};
     KnotTable table[2];
+    void *ls = nullptr;       // knot_ls_kernel table [S, lscap + 4] of {L, slope} (stream / strided paths)
+    int lscap = 0;
     unsigned long long *desc = nullptr;
     int *stop_e = nullptr, *stop_kind = nullptr, *input_knots = nullptr;
     unsigned tag = 0;
@@ -288,6 +290,10 @@ static cudaError_t launch_level(const pyitd_plan *pl, const LevelParams &p, bool
                                 long long nsig) {
     if (strided_launchable_fwd(pl, p.in)) {
         LevelParams q = p;
+        // a block takes a contiguous run of tiles (measured 19.5 -> 18.4 ms on 2^28 samples: the knot-free-span cache then
+        // survives from tile to tile on deep levels); PYITD_STRIDED_CONTIG=0 restores every-G-th-tile striding
+        const bool contig = !(getenv("PYITD_STRIDED_CONTIG") && atoi(getenv("PYITD_STRIDED_CONTIG")) == 0);
+        if (contig) q.opts |= kOptContigTiles;
         for (long long sg = 0; sg < pl->S; ++sg) {
             q.sig0 = (int)sg;
             cudaError_t e;
@@ -532,7 +538,12 @@ static int ensure_workspace(pyitd_plan *pl) {
     const long long gstride = pl->strided ? ((((long long)pl->tiles + 31) / 32 + 1 + 3) & ~3ll) : 0;
     const size_t b_group = align_up((size_t)pl->S * (size_t)gstride * sizeof(int));
     const size_t b_stage = pl->strided ? b_tau + b_xk : 0;             // tile-local knot staging of the strided path
-    size_t total = 2 * b_carry + 2 * (b_tau + b_xk + b_tbase + b_sig + b_endl + b_mask) + b_desc + 3 * b_sig + 2 * b_group + b_stage;
+    // knot baseline table of knot_ls_kernel: signals with at most n / 16 interior knots (sparser tables are where every
+    // warp would recompute the same few knots); PYITD_LS=0 turns the pre-pass off
+    const bool ls_on = !(getenv("PYITD_LS") && atoi(getenv("PYITD_LS")) == 0);      // read per plan (tests toggle it)
+    pl->lscap = (ls_on && (pl->stream || pl->strided)) ? (int)((pl->n / 16) & ~1ll) : 0;   // even: float rows stay 16-byte aligned
+    const size_t b_ls = pl->lscap ? align_up((size_t)pl->S * (size_t)(pl->lscap + 4) * 2 * pl->carry_elem) : 0;
+    size_t total = 2 * b_carry + 2 * (b_tau + b_xk + b_tbase + b_sig + b_endl + b_mask) + b_desc + 3 * b_sig + 2 * b_group + b_stage + b_ls;
     pl->ws_bytes = total;
     cudaError_t ce = cudaMalloc(&pl->ws, total);
     if (ce != cudaSuccess) {
@@ -570,6 +581,7 @@ static int ensure_workspace(pyitd_plan *pl) {
             pl->table[i].gstride = gstride;
         }
     }
+    pl->ls = b_ls ? take(b_ls) : nullptr;
     // the mask rows are padded to 4 words: the padding (and everything else) starts out as "no knot"
     ce = cudaMemset(pl->table[0].mask, 0, b_mask);
     if (ce == cudaSuccess) ce = cudaMemset(pl->table[1].mask, 0, b_mask);
@@ -820,9 +832,25 @@ extern "C" int pyitd_decompose_device(pyitd_plan *pl, const void *x, void *rotat
         lp.rows = pl->rows;
         lp.min_extrema = pl->min_extrema;
         lp.opts = pl->opts;
+        // knot baseline pre-pass (one thread per knot) for the signals whose table has become sparse: from level 1 on
+        const bool use_ls = pl->ls && e >= 1 && e <= pl->emax && (stream_launchable(pl, lp.in) || strided_launchable(pl, lp.in));
+        lp.ls = use_ls ? pl->ls : nullptr;
+        lp.lscap = use_ls ? pl->lscap : 0;
         for (int g = 0; g < G; ++g) {
             lp.sig0 = (int)g_lo(g);
-            CU(launch_level(pl, lp, e == 0, (G > 1) ? pl->gstream[g] : st, g_lo(g + 1) - g_lo(g)));
+            cudaStream_t gs = (G > 1) ? pl->gstream[g] : st;
+            const long long nsig = g_lo(g + 1) - g_lo(g);
+            if (use_ls) {
+                const long long y = (148 * 8 + nsig - 1) / nsig;
+                const dim3 grid((unsigned)nsig, (unsigned)(y < 1 ? 1 : y));
+                if (pl->carry_elem == 8)
+                    knot_ls_kernel<double><<<grid, 256, 0, gs>>>(lp.cur, pl->ls, pl->lscap, lp.sig0, e, pl->stop_e, status);
+                else
+                    knot_ls_kernel<float><<<grid, 256, 0, gs>>>(lp.cur, pl->ls, pl->lscap, lp.sig0, e, pl->stop_e, status);
+                CU(cudaGetLastError());
+                pl->launches++;
+            }
+            CU(launch_level(pl, lp, e == 0, gs, nsig));
             pl->launches++;
         }
         if (strided_launchable(pl, lp.in) && e <= pl->emax) {

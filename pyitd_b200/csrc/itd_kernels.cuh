@@ -34,6 +34,7 @@ constexpr int kStBadKnots = 8;
 
 constexpr unsigned kOptBaselines = 1u;
 constexpr unsigned kOptZeroTail = 2u;
+constexpr unsigned kOptContigTiles = 8u;  // internal (strided level kernel): a block takes a contiguous run of tiles instead of every G-th
 constexpr unsigned kOptGivenKnots = 4u;   // internal: segment ids from the stored flag mask, not from a stencil on x
 
 // ---------------------------------------------------------------------------------------------
@@ -227,7 +228,61 @@ struct LevelParams {
     int min_extrema;
     unsigned opts;
     int sig0 = 0;        // first signal of this launch (stream kernels: one launch per signal group)
+    // knot baseline table of knot_ls_kernel (stream / strided level kernels): ls[sig * (lscap + 4) + k] = {L_k, slope of
+    // segment [k, k+1)} for the signals with at most lscap interior knots; null: every tile computes its own
+    const void *ls = nullptr;
+    int lscap = 0;
 };
+
+// tiles with at most kLsTile interior knots take L_k / slopes from the knot_ls_kernel table (one TMA slice per tile)
+constexpr int kLsTile = 92;
+constexpr int kLsStage = kLsTile + 4;
+
+// ---------------------------------------------------------------------------------------------
+// knot_ls_kernel: the Frei-Osorio knot baseline with ONE THREAD PER KNOT (ITD.py:100-110) and the slope of the segment
+// that starts at the knot (ITD.py:116), for the signals whose table is sparse enough (K <= lscap) that the level kernel
+// would otherwise recompute the same few knots in every warp that touches their segments.  Same operations in the same
+// order as the level kernels' own evaluation: the results are bit-identical.
+// grid (signals, y): block (s, y) takes knots y * 256 + tid, + gridDim.y * 256, ...
+// ---------------------------------------------------------------------------------------------
+template <typename CarryT>
+struct alignas(2 * sizeof(CarryT)) KnotBaseSlope {
+    CarryT L, s;
+};
+template <typename CarryT>
+__global__ void __launch_bounds__(256) knot_ls_kernel(KnotTable cur, void *ls_out, int lscap, int sig0, int e,
+                                                      const int *stop_e, int *status) {
+    using A = Arith<CarryT>;
+    const int sig = blockIdx.x + sig0;
+    if (e > stop_e[sig]) return;
+    const int K = cur.kcount[sig];
+    if (K > lscap) return;
+    const int *tau = cur.tau + (long long)sig * cur.kstride;
+    const CarryT *xk = reinterpret_cast<const CarryT *>(cur.xk) + (long long)sig * cur.kstride;
+    const CarryT *endl = reinterpret_cast<const CarryT *>(cur.endl) + 2ll * sig;
+    KnotBaseSlope<CarryT> *out = reinterpret_cast<KnotBaseSlope<CarryT> *>(ls_out) + (long long)sig * (lscap + 4);
+    auto knot_L = [&](const int k) -> CarryT {
+        if (k == 0) return endl[0];
+        if (k >= K + 1) return endl[1];
+        const CarryT w = A::ratio(tau[k] - tau[k - 1], tau[k + 1] - tau[k - 1]);
+        const CarryT d = A::sub(xk[k + 1], xk[k - 1]);
+        const CarryT qq = A::add(xk[k - 1], A::mul(w, d));
+        return A::add(A::mul((CarryT)0.5, qq), A::mul((CarryT)0.5, xk[k]));
+    };
+    bool zero_dx = false;
+    for (int k = blockIdx.y * 256 + threadIdx.x; k <= K + 1; k += gridDim.y * 256) {
+        const CarryT L = knot_L(k);
+        CarryT sl = (CarryT)0;
+        if (k <= K) {
+            const CarryT den = A::sub(xk[k + 1], xk[k]);
+            sl = A::div(A::sub(knot_L(k + 1), L), den);
+            zero_dx |= (den == (CarryT)0);
+        }
+        out[k] = KnotBaseSlope<CarryT>{L, sl};
+    }
+    if (zero_dx) atomicOr(status + sig, kStZeroDx);
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // knot_scan_kernel: extrema detection + compaction on the raw input (ITD.py:87-98)

@@ -82,14 +82,16 @@ struct StreamSmem {
     static constexpr int SPAN = 32 * ITEMS;
     static constexpr int SC = WITH_KNOTS ? SPAN + 8 : 1; // per-warp knot scratch
     static constexpr int MAX_TILES = 1024;
+    struct alignas(2 * sizeof(CarryT)) LS {
+        CarryT L, s;                             // knot baseline L_k and slope of segment [k, k+1)
+    };
     struct Stage {
         alignas(16) InT x[T];
         alignas(16) unsigned mask[(T / 32 + 3) & ~3];
         alignas(16) int tau[KC];
         alignas(16) CarryT xk[KC];
-    };
-    struct alignas(2 * sizeof(CarryT)) LS {
-        CarryT L, s;                             // knot baseline L_k and slope of segment [k, k+1)
+        alignas(16) LS lsg[WITH_KNOTS ? kLsStage : 1];   // slice of the knot_ls_kernel table (tiles with few knots)
+        int ls_mode;                                      // 1: lsg holds {L, slope} of knots kb .. kb + cnt + 1
     };
     Stage stage[STAGES];
     alignas(8) unsigned long long full[STAGES];
@@ -241,6 +243,8 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_stream_kernel(const Level
     const int *gtau = p.cur.tau + (long long)sig * p.cur.kstride;
     const CarryT *gxk = reinterpret_cast<const CarryT *>(p.cur.xk) + (long long)sig * p.cur.kstride;
     const unsigned *gmask_in = p.cur.mask + (long long)sig * p.cur.mstride;
+    const LS *gls = reinterpret_cast<const LS *>(p.ls) + (long long)sig * (p.lscap + 4);
+    const bool ls_ok = (p.ls != nullptr) && K <= p.lscap;
     auto issue_tile = [&](const int i) {
         const int s = i % STAGES;
         const unsigned st = sbase + (unsigned)(offsetof(Smem, stage) + (size_t)s * sizeof(typename Smem::Stage));
@@ -255,10 +259,22 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_stream_kernel(const Level
         const unsigned bt = (unsigned)(nk * sizeof(int));
         const unsigned bk = (unsigned)(nk * sizeof(CarryT));
         const unsigned bar = full0 + 8 * s;
-        mbar_arrive_expect_tx(bar, bx + bm + bt + bk);
+        // few knots in the tile and a knot_ls_kernel table for this signal: {L_k, slope_k} of knots kb .. kb + cnt + 1
+        // arrive with the tile and no warp evaluates a knot baseline (the tau slice is then not needed)
+        const bool lsm = ls_ok && cnt <= kLsTile;
+        sm.stage[s].ls_mode = lsm ? 1 : 0;
+        if (lsm) {
+            const int lq = (sizeof(LS) == 8) ? (kb & ~1) : kb;       // 16-byte aligned start (float pairs are 8 bytes)
+            const int ne = min(kb + cnt + 1, K + 1) - lq + 1;
+            const unsigned bl = (unsigned)(((sizeof(LS) == 8) ? ((ne + 1) & ~1) : ne) * sizeof(LS));
+            mbar_arrive_expect_tx(bar, bx + bm + bk + bl);
+            tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, lsg), gls + lq, bl, bar);
+        } else {
+            mbar_arrive_expect_tx(bar, bx + bm + bt + bk);
+            tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, tau), gtau + lo, bt, bar);
+        }
         tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, x), x + t0, bx, bar);
         tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, mask), gmask_in + (t0 >> 5), bm, bar);
-        tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, tau), gtau + lo, bt, bar);
         tma_load_1d(st + (unsigned)offsetof(typename Smem::Stage, xk), gxk + lo, bk, bar);
     };
     if (tid == 0)
@@ -336,7 +352,9 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_stream_kernel(const Level
         // A knot-free span inside the same segment as the previous tile reuses the cached pair.
         const CarryT *xkb = st.xk + (wb - lo);                        // xkb[j] = X of knot wb + j
         const bool knot_free = (wcnt == 0 && fright == 0);
-        if (span_live && !(knot_free && wb == cached_wb)) {
+        const bool lsm = st.ls_mode != 0;                             // block-uniform
+        const LS *lsp = lsm ? st.lsg + (wb - ((sizeof(LS) == 8) ? (kb & ~1) : kb)) : ls;   // lsp[j] = {L, slope} of knot wb + j
+        if (!lsm && span_live && !(knot_free && wb == cached_wb)) {
             const int *taub = st.tau + (wb - lo);
             const int nl = min(wcnt + 3, K + 2 - wb);
             const int ns = min(wcnt + 2, K + 1 - wb);
@@ -371,7 +389,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_stream_kernel(const Level
             }
             __syncwarp();
         }
-        cached_wb = (span_live && knot_free) ? wb : -1;
+        cached_wb = (!lsm && span_live && knot_free) ? wb : -1;
 
         // ---- C. B, R for the span (+ one halo sample each side) --------------------------------
         CarryT b[ITEMS];
@@ -383,7 +401,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_stream_kernel(const Level
             if (!EDGE || jt < len) {
                 const CarryT xv = (CarryT)xs[r * 32];
                 const int j = wpre[r] + __popc(mw[r] & le_mask);
-                const LS q = ls[j];
+                const LS q = lsp[j];
                 bv = A::add(q.L, A::mul(q.s, A::sub(xv, xkb[j])));    // ITD.py:115-117
                 if (EDGE && t0 + jt == n - 1) bv = (CarryT)0;         // ITD.py:112
                 const CarryT rr = A::sub(xv, bv);
@@ -404,14 +422,14 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_stream_kernel(const Level
                 bleft = sm.carry_b[(i + 1) & 1];
             } else {
                 const CarryT xl = (CarryT)st.x[span0 - 1];
-                const LS q = ls[0];
+                const LS q = lsp[0];
                 bleft = A::add(q.L, A::mul(q.s, A::sub(xl, xkb[0])));
             }
         }
         CarryT bright = (CarryT)0;
         if (have_right && (!EDGE || tend < n - 1)) {
             const int j = wcnt + fright;
-            const LS q = ls[j];
+            const LS q = lsp[j];
             bright = A::add(q.L, A::mul(q.s, A::sub(xright, xkb[j])));
         }
 

@@ -35,16 +35,18 @@ struct StridedSmem {
     static constexpr int KC = T + 16;                   // knot slice capacity (T + 5, start aligned down to 4)
     static constexpr int SPAN = 32 * ITEMS;
     static constexpr int SC = SPAN + 8;                 // per-warp knot scratch
+    struct alignas(2 * sizeof(CarryT)) LS {
+        CarryT L, s;
+    };
     struct Stage {
         alignas(16) InT xpad[4];                        // x[t0 - 4 .. t0 - 1]
         InT x[T + 4];                                   // x[t0 .. t0 + T + 3]
         alignas(16) unsigned mask[T / 32 + 4];          // flag words of the tile + the next tile's first word
         alignas(16) int tau[KC];
         alignas(16) CarryT xk[KC];
+        alignas(16) LS lsg[kLsStage];                   // slice of the knot_ls_kernel table (tiles with few knots)
         int kb, cnt;                                    // knots before / inside the tile (from the per-tile prefix)
-    };
-    struct alignas(2 * sizeof(CarryT)) LS {
-        CarryT L, s;
+        int ls_mode;                                    // 1: lsg holds {L, slope} of knots kb .. kb + cnt + 1
     };
     Stage stage[STAGES];
     alignas(8) unsigned long long full[STAGES];
@@ -73,6 +75,14 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_strided_kernel(const Leve
     const int n = p.n, e = p.e, tiles = p.tiles;
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // tile k of this block is tile first + k * tstride of the signal: every G-th tile (neighbouring blocks stream
+    // neighbouring tiles), or a contiguous run (kOptContigTiles: the knot-free-span cache of section B then survives
+    // from one tile to the next, as in level_stream_kernel)
+    const bool contig = (p.opts & kOptContigTiles) != 0;
+    const int per = (tiles + G - 1) / G;
+    const int first = contig ? cta * per : cta;
+    const int tstride = contig ? 1 : G;
+    const int my_tiles = contig ? max(0, min(per, tiles - first)) : (tiles - cta + G - 1) / G;
     const long long row_off = (long long)sig * p.out_sig_stride;
 
     // ---- a signal that already stopped: trend-row fix-up / zero tail, tile by tile ----------------
@@ -118,9 +128,11 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_strided_kernel(const Leve
     const int *gtau = p.cur.tau + (long long)sig * p.cur.kstride;
     const CarryT *gxk = reinterpret_cast<const CarryT *>(p.cur.xk) + (long long)sig * p.cur.kstride;
     const unsigned *gmask_in = p.cur.mask + (long long)sig * p.cur.mstride;
+    const LS *gls = reinterpret_cast<const LS *>(p.ls) + (long long)sig * (p.lscap + 4);
+    const bool ls_ok = (p.ls != nullptr) && K <= p.lscap;
     // TMA bulk loads of this block's k-th tile into stage k % STAGES (one thread)
     auto issue_tile = [&](const int k, const int kb, const int kb1) {
-        const int i = cta + k * G;
+        const int i = first + k * tstride;
         const int s = k % STAGES;
         Stage &sg = sm.stage[s];
         const unsigned st = sbase + (unsigned)(offsetof(Smem, stage) + (size_t)s * sizeof(Stage));
@@ -139,15 +151,26 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_strided_kernel(const Leve
         const unsigned bt = (unsigned)(nk * sizeof(int));
         const unsigned bk = (unsigned)(nk * sizeof(CarryT));
         const unsigned bar = full0 + 8 * s;
-        mbar_arrive_expect_tx(bar, bx + bm + bt + bk);
+        // few knots in the tile and a knot_ls_kernel table: {L_k, slope_k} of knots kb .. kb + cnt + 1 arrive with the tile
+        const bool lsm = ls_ok && cnt <= kLsTile;
+        sg.ls_mode = lsm ? 1 : 0;
+        if (lsm) {
+            const int lq = (sizeof(LS) == 8) ? (kb & ~1) : kb;       // 16-byte aligned start (float pairs are 8 bytes)
+            const int ne = min(kb + cnt + 1, K + 1) - lq + 1;
+            const unsigned bl = (unsigned)(((sizeof(LS) == 8) ? ((ne + 1) & ~1) : ne) * sizeof(LS));
+            mbar_arrive_expect_tx(bar, bx + bm + bk + bl);
+            tma_load_1d(st + (unsigned)offsetof(Stage, lsg), gls + lq, bl, bar);
+        } else {
+            mbar_arrive_expect_tx(bar, bx + bm + bt + bk);
+            tma_load_1d(st + (unsigned)offsetof(Stage, tau), gtau + lo, bt, bar);
+        }
         tma_load_1d(st + (unsigned)(offsetof(Stage, x) - left * sizeof(InT)), x + t0 - left, bx, bar);
         tma_load_1d(st + (unsigned)offsetof(Stage, mask), gmask_in + (t0 >> 5), bm, bar);
-        tma_load_1d(st + (unsigned)offsetof(Stage, tau), gtau + lo, bt, bar);
         tma_load_1d(st + (unsigned)offsetof(Stage, xk), gxk + lo, bk, bar);
     };
-    const int my_tiles = (tiles - cta + G - 1) / G;                     // tiles of this block (cta < tiles)
     if (tid == 0)
-        for (int k = 0; k < STAGES && k < my_tiles; ++k) issue_tile(k, gtb[cta + k * G], gtb[cta + k * G + 1]);
+        for (int k = 0; k < STAGES && k < my_tiles; ++k)
+            issue_tile(k, gtb[first + k * tstride], gtb[first + k * tstride + 1]);
     int pf_kb = 0, pf_kb1 = 0;     // thread 0: per-tile knot prefix of the tile it will issue after this one (loaded early)
 
     const int span0 = warp * SPAN;                        // first sample of this warp's span (in tile)
@@ -170,7 +193,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_strided_kernel(const Leve
 
     auto tile_body = [&](auto edge_tag, const int k) {
         constexpr bool EDGE = decltype(edge_tag)::value;
-        const int i = cta + k * G;
+        const int i = first + k * tstride;
         const int s = k % STAGES;
         Stage &st = sm.stage[s];
         const int t0 = i * T;
@@ -217,7 +240,9 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_strided_kernel(const Leve
         // ---- B. knot baseline + slopes for the knots this span touches (warp-private) ----------
         const CarryT *xkb = st.xk + (wb - lo);                        // xkb[j] = X of knot wb + j
         const bool knot_free = (wcnt == 0 && fright == 0);
-        if (span_live && !(knot_free && wb == cached_wb)) {
+        const bool lsm = st.ls_mode != 0;                             // block-uniform
+        const LS *lsp = lsm ? st.lsg + (wb - ((sizeof(LS) == 8) ? (kb & ~1) : kb)) : ls;   // lsp[j] = {L, slope} of knot wb + j
+        if (!lsm && span_live && !(knot_free && wb == cached_wb)) {
             const int *taub = st.tau + (wb - lo);
             const int nl = min(wcnt + 3, K + 2 - wb);
             const int ns = min(wcnt + 2, K + 1 - wb);
@@ -251,7 +276,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_strided_kernel(const Leve
             }
             __syncwarp();
         }
-        cached_wb = (span_live && knot_free) ? wb : -1;
+        cached_wb = (!lsm && span_live && knot_free) ? wb : -1;
 
         // ---- C. B, R for the span (+ one halo sample each side) --------------------------------
         CarryT b[ITEMS];
@@ -263,7 +288,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_strided_kernel(const Leve
             if (!EDGE || jt < len) {
                 const CarryT xv = (CarryT)xs[r * 32];
                 const int j = wpre[r] + __popc(mw[r] & le_mask);
-                const LS q = ls[j];
+                const LS q = lsp[j];
                 bv = A::add(q.L, A::mul(q.s, A::sub(xv, xkb[j])));    // ITD.py:115-117
                 if (EDGE && t0 + jt == n - 1) bv = (CarryT)0;         // ITD.py:112
                 const CarryT rr = A::sub(xv, bv);
@@ -279,13 +304,13 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_strided_kernel(const Leve
         CarryT bleft = (CarryT)0;
         if (span_live && (t0 + span0 > 0)) {
             const CarryT xl = (CarryT)xt[span0 - 1];
-            const LS q = ls[0];
+            const LS q = lsp[0];
             bleft = A::add(q.L, A::mul(q.s, A::sub(xl, xkb[0])));
         }
         CarryT bright = (CarryT)0;
         if (have_right && (!EDGE || tend < n - 1)) {
             const int j = wcnt + fright;
-            const LS q = ls[j];
+            const LS q = lsp[j];
             bright = A::add(q.L, A::mul(q.s, A::sub(xright, xkb[j])));
         }
 
@@ -332,10 +357,10 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_strided_kernel(const Leve
     };
 
     for (int k = 0; k < my_tiles; ++k) {
-        const int i = cta + k * G;
+        const int i = first + k * tstride;
         if (tid == 0 && k + STAGES < my_tiles) {
-            pf_kb = gtb[i + STAGES * G];
-            pf_kb1 = gtb[i + STAGES * G + 1];
+            pf_kb = gtb[i + STAGES * tstride];
+            pf_kb1 = gtb[i + STAGES * tstride + 1];
         }
         if (i == 0 || i == tiles - 1)
             tile_body(std::true_type{}, k);

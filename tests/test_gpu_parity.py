@@ -733,3 +733,33 @@ def test_config5_chunked_shard_matches_unchunked():
             assert torch.equal(part.rows_of(s), whole.rows_of(c0 + s))
     want = o.c_decompose(x[639].cpu().numpy(), 11)
     assert whole.rows_of(639).cpu().numpy().tobytes() == want.rotations.tobytes()
+
+
+@pytest.mark.parametrize("path,S,n", [("stream", 170, 6000), ("stream", 161, 4116), ("strided", 1, 70000),
+                                      ("strided", 2, 33000)])
+def test_knot_ls_prepass_equals_in_kernel_knot_baseline(path, S, n, monkeypatch):
+    """knot_ls_kernel (one thread per knot: L_k and the slope of its segment, ITD.py:106-110 / :116) feeds the tiles with
+    few knots from level 1 on.  With the pre-pass switched off (PYITD_LS=0) every warp evaluates its own knots inside the
+    level kernel: both must give the same bytes and the same status words, in every precision variant, and match the
+    oracle."""
+    monkeypatch.setenv("PYITD_FORCE_PATH", path)
+    rng = np.random.default_rng(S * 31 + n)
+    x = _mixed_batch(rng, S, n)
+    x32 = x.astype(np.float32)
+    try:
+        out = {}
+        for ls in ("0", "1"):
+            monkeypatch.setenv("PYITD_LS", ls)
+            pyitd_b200.clear_plan_cache()
+            from pyitd_b200.itd import get_plan
+            assert get_plan(0, S, n, _capi.F64, 11, 2, _capi.OPT_BASELINES).path[0] == path
+            for dt, xin in (("f64", x), ("f32_mixed", x32), ("f32", x32)):
+                r = pyitd_b200.decompose(gpu(xin), max_iteration=11, dtype=dt, return_baselines=True, zero_tail=True)
+                torch.cuda.synchronize()
+                out[ls, dt] = (r.rotations.cpu().numpy().tobytes(), r.baselines.cpu().numpy().tobytes(),
+                               r.n_rows.cpu().tolist(), r.status.cpu().tolist(), r.knot_counts.cpu().tolist())
+        for dt in ("f64", "f32_mixed", "f32"):
+            assert out["0", dt] == out["1", dt], dt
+        check_against_oracle(x[: min(S, 12)], max_iteration=11) if path == "strided" else check_against_oracle(x, max_iteration=11)
+    finally:
+        pyitd_b200.clear_plan_cache()
