@@ -541,7 +541,8 @@ static int ensure_workspace(pyitd_plan *pl) {
     // knot baseline table of knot_ls_kernel: signals with at most n / 16 interior knots (sparser tables are where every
     // warp would recompute the same few knots); PYITD_LS=0 turns the pre-pass off
     const bool ls_on = !(getenv("PYITD_LS") && atoi(getenv("PYITD_LS")) == 0);      // read per plan (tests toggle it)
-    pl->lscap = (ls_on && (pl->stream || pl->strided)) ? (int)((pl->n / 16) & ~1ll) : 0;   // even: float rows stay 16-byte aligned
+    const int ls_div = getenv("PYITD_LS_DIV") ? (atoi(getenv("PYITD_LS_DIV")) > 1 ? atoi(getenv("PYITD_LS_DIV")) : 16) : 16;   // experiment hook (n/16 measured best: profiles/r1/s5/ls_probe2.log)
+    pl->lscap = (ls_on && (pl->stream || pl->strided)) ? (int)((pl->n / ls_div) & ~1ll) : 0;   // even: float rows stay 16-byte aligned
     const size_t b_ls = pl->lscap ? align_up((size_t)pl->S * (size_t)(pl->lscap + 4) * 2 * pl->carry_elem) : 0;
     size_t total = 2 * b_carry + 2 * (b_tau + b_xk + b_tbase + b_sig + b_endl + b_mask) + b_desc + 3 * b_sig + 2 * b_group + b_stage + b_ls;
     pl->ws_bytes = total;
