@@ -65,8 +65,6 @@ struct pyitd_plan {
     size_t ws_bytes = 0;
     void *carry[2] = {nullptr, nullptr};
     KnotTable table[2];
-    int *trend_done = nullptr; // [S] stream path: the level kernel wrote the knot-stop trend row itself (look-ahead pass)
-    bool lookahead = true;     // PYITD_LOOKAHEAD=0 turns the look-ahead pass off
     void *ls = nullptr;       // knot_ls_kernel table [S, lscap + 4] of {L, slope} (stream / strided paths)
     int lscap = 0;
     unsigned long long *desc = nullptr;
@@ -544,9 +542,9 @@ static int ensure_workspace(pyitd_plan *pl) {
     // warp would recompute the same few knots); PYITD_LS=0 turns the pre-pass off
     const bool ls_on = !(getenv("PYITD_LS") && atoi(getenv("PYITD_LS")) == 0);      // read per plan (tests toggle it)
     const int ls_div = getenv("PYITD_LS_DIV") ? (atoi(getenv("PYITD_LS_DIV")) > 1 ? atoi(getenv("PYITD_LS_DIV")) : 16) : 16;   // experiment hook (n/16 measured best: profiles/r1/s5/ls_probe2.log)
-    pl->lscap = (ls_on && (pl->stream || pl->strided) && pl->n >= 16384) ? (int)((pl->n / ls_div) & ~1ll) : 0;   // short signals (config 4: 8 tiles) lose more to the extra launch than they gain   // even: float rows stay 16-byte aligned
+    pl->lscap = (ls_on && (pl->stream || pl->strided)) ? (int)((pl->n / ls_div) & ~1ll) : 0;   // even: float rows stay 16-byte aligned
     const size_t b_ls = pl->lscap ? align_up((size_t)pl->S * (size_t)(pl->lscap + 4) * 2 * pl->carry_elem) : 0;
-    size_t total = 2 * b_carry + 2 * (b_tau + b_xk + b_tbase + b_sig + b_endl + b_mask) + b_desc + 3 * b_sig + 2 * b_group + b_stage + b_ls + b_sig;
+    size_t total = 2 * b_carry + 2 * (b_tau + b_xk + b_tbase + b_sig + b_endl + b_mask) + b_desc + 3 * b_sig + 2 * b_group + b_stage + b_ls;
     pl->ws_bytes = total;
     cudaError_t ce = cudaMalloc(&pl->ws, total);
     if (ce != cudaSuccess) {
@@ -585,8 +583,6 @@ static int ensure_workspace(pyitd_plan *pl) {
         }
     }
     pl->ls = b_ls ? take(b_ls) : nullptr;
-    pl->trend_done = (int *)take(b_sig);
-    pl->lookahead = !(getenv("PYITD_LOOKAHEAD") && atoi(getenv("PYITD_LOOKAHEAD")) == 0);
     // the mask rows are padded to 4 words: the padding (and everything else) starts out as "no knot"
     ce = cudaMemset(pl->table[0].mask, 0, b_mask);
     if (ce == cudaSuccess) ce = cudaMemset(pl->table[1].mask, 0, b_mask);
@@ -789,7 +785,6 @@ extern "C" int pyitd_decompose_device(pyitd_plan *pl, const void *x, void *rotat
     int *sk = stop_kind ? stop_kind : pl->stop_kind;
     const size_t b_sig = (size_t)pl->S * sizeof(int);
     CU(cudaMemsetAsync(pl->stop_e, 0x7f, b_sig, st));
-    CU(cudaMemsetAsync(pl->trend_done, 0, b_sig, st));
     CU(cudaMemsetAsync(sk, 0, b_sig, st));
     CU(cudaMemsetAsync(status, 0, b_sig, st));
     CU(cudaMemsetAsync(n_rows, 0, b_sig, st));
@@ -838,7 +833,6 @@ extern "C" int pyitd_decompose_device(pyitd_plan *pl, const void *x, void *rotat
         lp.rows = pl->rows;
         lp.min_extrema = pl->min_extrema;
         lp.opts = pl->opts;
-        lp.trend_done = pl->lookahead ? pl->trend_done : nullptr;
         // knot baseline pre-pass (one thread per knot) for the signals whose table has become sparse: from level 1 on
         const bool use_ls = pl->ls && e >= 1 && e <= pl->emax && (stream_launchable(pl, lp.in) || strided_launchable(pl, lp.in));
         lp.ls = use_ls ? pl->ls : nullptr;

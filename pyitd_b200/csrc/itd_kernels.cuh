@@ -232,8 +232,6 @@ struct LevelParams {
     // segment [k, k+1)} for the signals with at most lscap interior knots; null: every tile computes its own
     const void *ls = nullptr;
     int lscap = 0;
-    // stream kernel: trend_done[sig] = 1 when the level kernel itself wrote the trend row of a knot stop (look-ahead pass)
-    int *trend_done = nullptr;
 };
 
 // tiles with at most kLsTile interior knots take L_k / slopes from the knot_ls_kernel table (one TMA slice per tile)

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_stream_kernel(const Level
         OutT *rot = reinterpret_cast<OutT *>(p.rot) + row_off;
         OutT *bas = BAS ? reinterpret_cast<OutT *>(p.bas) + row_off : nullptr;
         const CarryT *src = reinterpret_cast<const CarryT *>(p.fix_src) + (long long)sig * n;
-        if (e == se + 1 && p.stop_kind[sig] == kStopKnots && !(p.trend_done && p.trend_done[sig])) {
+        if (e == se + 1 && p.stop_kind[sig] == kStopKnots) {
             // the discarded extraction `se` wrote R_se into row se; the reference returns
             // baselines[se-1] there, i.e. the INPUT of that extraction (zeros when se == 0)
             copy_row(rot + (long long)se * n, src, n, se == 0);
@@ -297,19 +297,15 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_stream_kernel(const Level
     int cached_wb = -1;         // segment whose (L, slope) sit in ls[0..1] from a knot-free span
     bool zero_dx = false;
 
-    // COUNT: the look-ahead pass of a signal that will probably stop at this level -- same arithmetic, nothing stored
-    // outside the CTA, only the running count of B's extrema.  ph0 / ph1: mbarrier phases already used per stage.
-    auto tile_body = [&](auto edge_tag, auto count_tag, const int i, const int ph0, const int ph1) {
+    auto tile_body = [&](auto edge_tag, const int i) {
         constexpr bool EDGE = decltype(edge_tag)::value;
-        constexpr bool COUNT = decltype(count_tag)::value;
-        static_assert(STAGES == 2, "phase offsets are kept per stage for a two-stage ring");
         const int s = i % STAGES;
         typename Smem::Stage &st = sm.stage[s];
         const int t0 = i * T;
         const int len = EDGE ? min(T, n - t0) : T;
         const int kb = sm.tbase[i];
         const int lo = max(kb - 1, 0) & ~3;
-        mbar_wait(full0 + 8 * s, (i / STAGES + (s ? ph1 : ph0)) & 1);
+        mbar_wait(full0 + 8 * s, (i / STAGES) & 1);
 
         // ---- A. segment bases from the stored flag words --------------------------------------
         const int nwords = (len + 31) >> 5;
@@ -345,7 +341,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_stream_kernel(const Level
             } else {
                 // first sample of the NEXT tile: its load was issued STAGES-1 tiles ago
                 const int s2 = (i + 1) % STAGES;
-                mbar_wait(full0 + 8 * s2, ((i + 1) / STAGES + (s2 ? ph1 : ph0)) & 1);
+                mbar_wait(full0 + 8 * s2, ((i + 1) / STAGES) & 1);
                 xright = (CarryT)sm.stage[s2].x[0];
                 fright = (int)(sm.stage[s2].mask[0] & 1u);
             }
@@ -408,21 +404,17 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_stream_kernel(const Level
                 const LS q = lsp[j];
                 bv = A::add(q.L, A::mul(q.s, A::sub(xv, xkb[j])));    // ITD.py:115-117
                 if (EDGE && t0 + jt == n - 1) bv = (CarryT)0;         // ITD.py:112
-                if (!COUNT) {
-                    const CarryT rr = A::sub(xv, bv);
-                    rot[r * 32] = (OutT)(LAST ? A::add(rr, bv) : rr); // ITD.py:119 / :420
-                    carry[r * 32] = bv;
-                    if (BAS) bas[r * 32] = LAST ? (OutT)0 : (OutT)bv; // ITD.py:424
-                    if (EDGE && t0 + jt == n - 2) nendl[1] = mean2<CarryT>(bv, (CarryT)0);
-                }
+                const CarryT rr = A::sub(xv, bv);
+                rot[r * 32] = (OutT)(LAST ? A::add(rr, bv) : rr);     // ITD.py:119 / :420
+                carry[r * 32] = bv;
+                if (BAS) bas[r * 32] = LAST ? (OutT)0 : (OutT)bv;     // ITD.py:424
+                if (EDGE && t0 + jt == n - 2) nendl[1] = mean2<CarryT>(bv, (CarryT)0);
             }
             b[r] = bv;
         }
-        if (!COUNT) {
-            rot += T;
-            carry += T;
-            if (BAS) bas += T;
-        }
+        rot += T;
+        carry += T;
+        if (BAS) bas += T;
         // left halo B[span0 - 1]: previous warp's last sample (same tile) or the previous tile's
         CarryT bleft = (CarryT)0;
         if (span_live) {
@@ -444,17 +436,15 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_stream_kernel(const Level
         // ---- D. extrema of B: next level's flag words -----------------------------------------
         unsigned fw[ITEMS];
         const int newc = span_extrema<EDGE, ITEMS, CarryT>(b, bleft, bright, lane, t0 + span0, n, fw);
-        if (!COUNT) {
-            if (lane < ITEMS && (!EDGE || span0 + lane * 32 < len)) {
-                unsigned v = fw[0];
+        if (lane < ITEMS && (!EDGE || span0 + lane * 32 < len)) {
+            unsigned v = fw[0];
 #pragma unroll
-                for (int r = 1; r < ITEMS; ++r) v = (lane == r) ? fw[r] : v;
-                nmask[0] = v;
-            }
-            nmask += T / 32;
+            for (int r = 1; r < ITEMS; ++r) v = (lane == r) ? fw[r] : v;
+            nmask[0] = v;
         }
+        nmask += T / 32;
         if (warp == WARPS - 1 && lane == 31) sm.carry_b[i & 1] = b[ITEMS - 1];
-        if (!COUNT && EDGE && i == 0 && warp == 0) {
+        if (EDGE && i == 0 && warp == 0) {
             const CarryT b1 = shfl_idx(b[0], 1);
             if (lane == 0) {
                 ntau[0] = 0;
@@ -463,62 +453,17 @@ __global__ void __launch_bounds__(WARPS * 32, 3) level_stream_kernel(const Level
             }
         }
         // ---- E/F/G. one block barrier, then compact the new knots ------------------------------
-        if (COUNT) {
-            if (lane == 0) sm.cnt[i & 1][warp] = newc;
-            named_barrier_sync(1, WARPS * 32);
-            run_total += __reduce_add_sync(0xffffffffu, (lane < WARPS) ? sm.cnt[i & 1][lane] : 0);
-        } else {
-            compact_knots<WARPS, ITEMS, CarryT>(sm.cnt, i, warp, lane, newc, fw, b, t0 + span0, run_total, ntau, nxk,
-                                                ntbase);
-        }
+        compact_knots<WARPS, ITEMS, CarryT>(sm.cnt, i, warp, lane, newc, fw, b, t0 + span0, run_total, ntau, nxk,
+                                            ntbase);
         // every warp is past its reads of stage s: refill it with the tile STAGES ahead
         if (tid == 0 && i + STAGES < tiles) issue_tile(i + STAGES);
     };
 
-    // ---- look-ahead for a signal that will probably stop here (ITD.py:404): with at most min_extrema + 1 knots left,
-    // two thirds of the extractions are the discarded last one (profiles/r1/s5: 221 of 333 on config 2), whose R row and
-    // carry would be written only to be replaced by the trend row in the next launch.  Count B's extrema first; on a
-    // stop write the trend row (= this level's input, ITD.py:410-411) here and now, else run the level as usual.
-    int ph0 = 0, ph1 = 0;
-    if (!LAST && e >= 1 && p.trend_done != nullptr && p.min_extrema > 0 && K <= p.min_extrema + 1) {
-        for (int i = 0; i < tiles; ++i) {
-            if (i == 0 || i == tiles - 1)
-                tile_body(std::true_type{}, std::true_type{}, i, 0, 0);
-            else
-                tile_body(std::false_type{}, std::true_type{}, i, 0, 0);
-        }
-        if (run_total < p.min_extrema) {
-            OutT *rotp = reinterpret_cast<OutT *>(p.rot) + row_off;
-            copy_row(rotp + (long long)e * n, x, n, false);
-            if (BAS && (p.opts & kOptZeroTail)) copy_row(reinterpret_cast<OutT *>(p.bas) + row_off + (long long)e * n, x, n, true);
-            if (zero_dx) atomicOr(p.status + sig, kStZeroDx);
-            if (warp == 0 && lane == 0) {
-                p.knot_counts[(long long)sig * p.rows + e] = run_total;   // what ITD.py:403 prints
-                p.stop_kind[sig] = kStopKnots;
-                p.n_rows[sig] = e + 1;
-                p.stop_e[sig] = e;
-                p.trend_done[sig] = 1;                                    // the next launch has nothing to fix up
-            }
-            return;
-        }
-        // the level goes ahead: restart the ring (every load of the look-ahead pass has been consumed)
-        __syncthreads();
-        ph0 = (tiles + 1) / 2;
-        ph1 = tiles / 2;
-        run_total = 0;
-        cached_wb = -1;
-        if (tid == 0) {
-            sm.carry_b[0] = sm.carry_b[1] = (CarryT)0;
-            for (int i = 0; i < STAGES && i < tiles; ++i) issue_tile(i);
-        }
-        __syncthreads();
-    }
-
     for (int i = 0; i < tiles; ++i) {
         if (i == 0 || i == tiles - 1)
-            tile_body(std::true_type{}, std::false_type{}, i, ph0, ph1);
+            tile_body(std::true_type{}, i);
         else
-            tile_body(std::false_type{}, std::false_type{}, i, ph0, ph1);
+            tile_body(std::false_type{}, i);
     }
 
     if (zero_dx) atomicOr(p.status + sig, kStZeroDx);

@@ -763,37 +763,3 @@ def test_knot_ls_prepass_equals_in_kernel_knot_baseline(path, S, n, monkeypatch)
         check_against_oracle(x[: min(S, 12)], max_iteration=11) if path == "strided" else check_against_oracle(x, max_iteration=11)
     finally:
         pyitd_b200.clear_plan_cache()
-
-
-@pytest.mark.parametrize("S,n,opts", [(170, 6000, {}), (161, 4116, {"min_extrema": 4}), (200, 2048, {"max_iteration": 3})])
-def test_lookahead_pass_equals_fixup_flow(S, n, opts, monkeypatch):
-    """Stream path: a signal with at most min_extrema + 1 knots left first counts the extrema of its next baseline without
-    storing anything; on a stop (ITD.py:404) the level kernel writes the trend row (ITD.py:410-411) itself, otherwise it
-    runs the level.  With PYITD_LOOKAHEAD=0 the level is stored first and the next launch replaces row `se` by the trend
-    row.  Same bytes (zero tail requested, so every row is defined), same bookkeeping, and both match the oracle."""
-    monkeypatch.setenv("PYITD_FORCE_PATH", "stream")
-    rng = np.random.default_rng(S + n)
-    x = _mixed_batch(rng, S, n)
-    x32 = x.astype(np.float32)
-    kw = dict(max_iteration=11, min_extrema=2)
-    kw.update(opts)
-    try:
-        out = {}
-        for la in ("0", "1"):
-            monkeypatch.setenv("PYITD_LOOKAHEAD", la)
-            pyitd_b200.clear_plan_cache()
-            for dt, xin in (("f64", x), ("f32_mixed", x32), ("f32", x32)):
-                r = pyitd_b200.decompose(gpu(xin), dtype=dt, return_baselines=True, zero_tail=True, **kw)
-                torch.cuda.synchronize()
-                nr = r.n_rows.cpu().numpy()
-                bas = r.baselines.cpu().numpy()
-                kind = r.stop_kind.cpu().numpy()
-                # baselines rows beyond the valid ones are unspecified on the iteration stop only when not zero-filled;
-                # zero_tail defines them all
-                out[la, dt] = (r.rotations.cpu().numpy().tobytes(), bas.tobytes(), nr.tolist(), kind.tolist(),
-                               r.status.cpu().tolist(), r.knot_counts.cpu().tolist())
-        for dt in ("f64", "f32_mixed", "f32"):
-            assert out["0", dt] == out["1", dt], dt
-        check_against_oracle(x, **kw)
-    finally:
-        pyitd_b200.clear_plan_cache()
