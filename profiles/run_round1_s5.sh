@@ -9,7 +9,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 tail -c 600 gpurun_out/bench.err
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2>> gpurun_out/bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:pyitd|stream|scan|level" -c 400 --csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:stream|scan|level|knot_ls|place_knots|tile_prefix" -c 400 --csv \
     --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_under_ncu.log 2>&1
 for dt in f32_mixed f32; do timeout 300 python profiles/bench_configs.py --config 3 --dtype $dt; done > gpurun_out/bench_config3.jsonl 2> gpurun_out/bench_config3.err
 timeout 300 python profiles/bench_configs.py --config 4 > gpurun_out/bench_config4.jsonl 2> gpurun_out/bench_config4.err
