@@ -42,6 +42,26 @@ METRIC = "input samples/s fully decomposed (all levels)"
 UNIT = "samples/s"
 
 
+_JSON_OUT = None
+
+
+def protect_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+    "NCCL version ..." banner there whatever NCCL_DEBUG_FILE says): keep a private duplicate of the real stdout for the
+    JSON line and point descriptor 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -122,7 +142,7 @@ def run_reference_arm(args):
         "note": "oracle/itd_oracle.c (bit-exact C port of ITD.py, pthreads over channels): the reference is "
                 "Python+numba and is not shipped to the GPU box",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -185,6 +205,7 @@ class ClockSampler:
 # our arm
 # ---------------------------------------------------------------------------------------------
 def main():
+    protect_stdout()
     args = parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -404,7 +425,7 @@ def main():
             "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu,
             "rows_per_channel_mean": float(nr.double().mean()),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

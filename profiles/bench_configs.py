@@ -21,6 +21,11 @@ sys.path.insert(0, ROOT)
 
 
 def main():
+    # stdout carries exactly one JSON line per run: NCCL prints its version banner to file descriptor 1 whatever
+    # NCCL_DEBUG_FILE says, so keep a private duplicate of the real stdout and point descriptor 1 at stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, required=True, choices=[3, 4, 5])
     ap.add_argument("--dtype", default=None)
@@ -107,7 +112,7 @@ def main():
         pass
     if rank == 0:
         path = plans[Smax].path
-        print(json.dumps({
+        json_out.write(json.dumps({
             "metric": "input samples/s fully decomposed (all levels)", "value": S_total * N / (ms * 1e-3), "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "dtype": dt,
             "data": "synthetic", "scaling": "strong" if args.config == 5 else "n/a",
@@ -118,7 +123,8 @@ def main():
             "roofline_whole_step": {"bound": "hbm", "algorithmic_bytes_per_step": alg, "achieved": alg / (ms * 1e-3) / 1e9 / world,
                                     "peak": peak, "unit": "GB/s per GPU", "frac": alg / (ms * 1e-3) / 1e9 / world / peak},
             "status_max": int(ints[4].max()), "t": time.strftime("%Y-%m-%dT%H:%M:%S"),
-        }), flush=True)
+        }) + "\n")
+        json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 
