@@ -147,7 +147,11 @@ static cudaError_t launch_level_cfg(int cfg, const LevelParams &p, long long cta
 }
 
 // one CTA per signal, 8 warps x 4 samples/lane = 1024-sample tiles, 2-stage TMA ring, 3 CTAs per SM
-constexpr int kStreamWarps = 8, kStreamItems = 4, kStreamStages = 2;
+#ifndef PYITD_STREAM_WARPS
+#define PYITD_STREAM_WARPS 8          // experiment hook: 4 = 512-sample tiles for the one-CTA-per-signal kernels
+#endif
+constexpr int kStridedWarps = 8;      // the strided path's passes are written for 1024-sample tiles
+constexpr int kStreamWarps = PYITD_STREAM_WARPS, kStreamItems = 4, kStreamStages = 2;
 constexpr int kStreamTile = kStreamWarps * 32 * kStreamItems;
 
 template <typename InT, typename CarryT, typename OutT, bool LAST, bool BAS>
@@ -183,12 +187,12 @@ static cudaError_t launch_scan_stream_t(const ScanParams &p, long long ctas, cud
 // over the tiles needs every block to make progress), block c takes tiles c, c + G, ...
 template <typename InT, typename CarryT, typename OutT, bool LAST, bool BAS>
 static cudaError_t launch_strided_v(const LevelParams &p, int cap, cudaStream_t st) {
-    auto k = level_strided_kernel<InT, CarryT, OutT, kStreamWarps, kStreamItems, kStreamStages, LAST, BAS>;
-    constexpr size_t smem = sizeof(StridedSmem<InT, CarryT, kStreamWarps, kStreamItems, kStreamStages>);
+    auto k = level_strided_kernel<InT, CarryT, OutT, kStridedWarps, kStreamItems, kStreamStages, LAST, BAS>;
+    constexpr size_t smem = sizeof(StridedSmem<InT, CarryT, kStridedWarps, kStreamItems, kStreamStages>);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0, dev = 0, sms = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kStreamWarps * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kStridedWarps * 32, smem);
     if (e != cudaSuccess) return e;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -196,7 +200,7 @@ static cudaError_t launch_strided_v(const LevelParams &p, int cap, cudaStream_t 
     if (g < 1) return cudaErrorLaunchOutOfResources;
     if (cap > 0 && g > cap) g = cap;
     if (g > p.tiles) g = p.tiles;
-    k<<<(unsigned)g, kStreamWarps * 32, smem, st>>>(p);
+    k<<<(unsigned)g, kStridedWarps * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 template <typename InT, typename CarryT, typename OutT>
@@ -219,12 +223,12 @@ static int compact_grid(int tiles) {
 // the strided path's knot scan: flag words + per-tile counts, then the prefix and the compaction pass
 template <typename InT, typename CarryT>
 static cudaError_t launch_scan_strided_t(const pyitd_plan *pl, const ScanParams &p, cudaStream_t st) {
-    auto k = scan_strided_kernel<InT, CarryT, kStreamWarps, kStreamItems>;
-    constexpr size_t smem = sizeof(ScanStridedSmem<InT, kStreamWarps, kStreamItems>);
+    auto k = scan_strided_kernel<InT, CarryT, kStridedWarps, kStreamItems>;
+    constexpr size_t smem = sizeof(ScanStridedSmem<InT, kStridedWarps, kStreamItems>);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0, dev = 0, sms = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kStreamWarps * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kStridedWarps * 32, smem);
     if (e != cudaSuccess) return e;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -232,7 +236,7 @@ static cudaError_t launch_scan_strided_t(const pyitd_plan *pl, const ScanParams 
     if (g < 1) return cudaErrorLaunchOutOfResources;
     if (pl->strided_cap > 0 && g > pl->strided_cap) g = pl->strided_cap;
     if (g > p.tiles) g = p.tiles;
-    k<<<(unsigned)g, kStreamWarps * 32, smem, st>>>(p);
+    k<<<(unsigned)g, kStridedWarps * 32, smem, st>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     tile_prefix_scan_kernel<InT, CarryT><<<1, 1024, 0, st>>>(p.out, p.x, p.sig0, p.tiles, p.n, p.input_knots);
@@ -495,7 +499,7 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
     if (const char *env = getenv("PYITD_FORCE_PATH")) strided = !strcmp(env, "strided") && n_signals <= 64 && stream_ok_rows;
     pl->resident = resident && res_configure(pl);
     if (pl->resident) stream = strided = false;
-    if (stream || strided) cfg = 1;            // both kernels must agree on the 1024-sample tile
+    if (stream || strided) cfg = (stream && kStreamWarps == 4) ? 0 : 1;   // the look-back kernels must agree on the tile of the stream / strided kernels
     pl->strided = strided;
     if (const char *env = getenv("PYITD_STRIDED_CTAS")) pl->strided_cap = atoi(env);
     pl->stream = stream;
