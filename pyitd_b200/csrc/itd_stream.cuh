@@ -165,15 +165,16 @@ __device__ __forceinline__ void compact_knots(int (&cnt)[2][WARPS], int i, int w
 // vectorised row copy / fill used by the trend-row fix-up
 template <typename OutT, typename CarryT>
 __device__ __forceinline__ void copy_row(OutT *dst, const CarryT *src, int n, bool zero) {
-    for (int t = threadIdx.x; t < n; t += blockDim.x * 4) {
-        CarryT a[4];
+    constexpr int U = 8;                                  // loads in flight per thread (a fix-up block copies 512 KB)
+    for (int t = threadIdx.x; t < n; t += blockDim.x * U) {
+        CarryT a[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int tt = t + u * blockDim.x;
             a[u] = (!zero && tt < n) ? src[tt] : (CarryT)0;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int tt = t + u * blockDim.x;
             if (tt < n) dst[tt] = (OutT)a[u];
         }
