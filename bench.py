@@ -16,7 +16,11 @@ Keys beyond the base contract:
   e2e           the same metric through the C ABI with HOST buffers (pyitd_decompose_host: H2D of the
                 inputs and D2H of every output row inside the timed region);
   cpu_baseline  the oracle's C port on this box's host cores over a bounded sample of the same
-                workload (a reported baseline, not the target).
+                workload (a reported baseline, not the target);
+  parity        64 randomly chosen channels of the LAST timed step compared bit for bit with the oracle
+                (rows, row counts, per-level knot counts); the run fails when they differ;
+  extra_configs BASELINE.json configs[4] as a STRONG split (65 536 channels / N GPUs, 4096-channel
+                chunks) at every N, and configs[2], configs[3] on one GPU.
 `--impl reference` times that CPU port alone (the reference is Python+numba and cannot travel to the
 GPU box).
 """
@@ -74,6 +78,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--groups", type=int, default=0, help="stream-path launch groups (0 = the library's default)")
+    ap.add_argument("--parity-channels", type=int, default=64, help="channels of the timed output checked against the oracle")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs legs (configs 3, 4, 5)")
+    ap.add_argument("--config5-channels", type=int, default=65536, help="total channels of the strong-scaling leg")
+    ap.add_argument("--no-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
     return ap.parse_args()
 
 
@@ -91,7 +99,15 @@ def workload_config(args, n_gpus):
 # ---------------------------------------------------------------------------------------------
 # CPU port timing (cpu_baseline leg and --impl reference)
 # ---------------------------------------------------------------------------------------------
-def cpu_port_throughput(n_samples: int, budget_s: float = 12.0, max_channels: int = 4096):
+CPU_SAMPLE_CHANNELS = 1024          # both CPU legs (cpu_baseline and --impl reference) time the same bounded sample
+# SURVEY.md section 6 (survey container, one core of an 8-core Xeon, numba 0.65, JIT excluded): the reference's own
+# ITD().itd on a 65 536-sample signal.  The reference is Python + numba and cannot travel to the GPU box; the C port
+# timed here is ~8x faster per core, i.e. a conservative baseline.
+NUMBA_REFERENCE_PER_CORE = {"value": 1.2e6, "unit": UNIT, "source": "SURVEY.md section 6 / BASELINE.md: ITD.py (numba) "
+                            "on one core of the survey container, 52-57 ms per 65 536-sample signal; not measured on this box"}
+
+
+def cpu_port_throughput(n_samples: int, budget_s: float = 12.0, max_channels: int = CPU_SAMPLE_CHANNELS):
     """Times oracle/itd_oracle.c (pthreads, one channel per thread) on a bounded sample of the
     workload.  Returns (samples_per_s, threads, n_channels, seconds)."""
     import torch
@@ -124,7 +140,7 @@ def run_reference_arm(args):
     vals = []
     threads = n_ch = 0
     for i in range(args.warmup + args.steps):
-        v, threads, n_ch, secs = cpu_port_throughput(args.samples, budget_s=per_step_budget, max_channels=1024)
+        v, threads, n_ch, secs = cpu_port_throughput(args.samples, budget_s=per_step_budget)
         if i >= args.warmup:
             vals.append((v, secs, n_ch))
     tot_samples = sum(n * args.samples for _, _, n in vals)
@@ -136,7 +152,8 @@ def run_reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_secs / max(len(vals), 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "numba_per_core": NUMBA_REFERENCE_PER_CORE},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "oracle/itd_oracle.c (bit-exact C port of ITD.py, pthreads over channels): the reference is "
@@ -201,6 +218,126 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+
+# ---------------------------------------------------------------------------------------------
+# helpers of our arm
+# ---------------------------------------------------------------------------------------------
+def kernel_source_hash() -> str:
+    """sha256[:16] over the CUDA sources of libpyitd_b200.so: the ncu traffic capture under profiles/ is keyed by it."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "pyitd_b200", "csrc", "*.cu*"))):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def parity_check(torch, x, rot, n_rows, counts, n_check: int, seed: int):
+    """n_check randomly chosen channels of the timed output against the oracle, bit for bit (checker only)."""
+    from oracle import itd_oracle
+    S = x.shape[0]
+    g = torch.Generator()
+    g.manual_seed(seed)
+    idx = torch.randperm(S, generator=g)[: min(n_check, S)].sort().values
+    dev_idx = idx.to(x.device)
+    xs = x[dev_idx].cpu().numpy()
+    got_rot = rot[dev_idx].cpu().numpy()
+    got_nr = n_rows[dev_idx].cpu().numpy()
+    got_cnt = counts[dev_idx].cpu().numpy()
+    want_rot, want_nr, want_cnt, st, _ = itd_oracle.c_decompose_batch(xs, MAX_ITERATION)
+    bad = []
+    for i, ch in enumerate(idx.tolist()):
+        nr = int(want_nr[i])
+        ok = (int(st[i]) == 0 and int(got_nr[i]) == nr and got_cnt[i, :nr].tolist() == want_cnt[i, :nr].tolist()
+              and got_rot[i, :nr].tobytes() == want_rot[i, :nr].tobytes())
+        if not ok:
+            bad.append(ch)
+    return {"channels": len(idx), "bit_exact": not bad, "mismatching_channels": bad[:8],
+            "checked": "every rotation / trend row, the row count and the per-level knot counts of the last timed step "
+                       "vs oracle/itd_oracle.c (ITD.py:351-433)", "seed": seed}
+
+
+def timed_passes(torch, shard, step, stream, dev, steps: int, warmup: int, world: int, dist):
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        step()
+    ev1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    return shard.max_over_ranks(ev0.elapsed_time(ev1), device=dev) / steps
+
+
+def extra_config(torch, dist, which: int, args, rank, world, local_rank, dev, peak, rot_buf=None):
+    """BASELINE.json configs[2] / [3] / [4] through the same C ABI; device-event time."""
+    from pyitd_b200 import _capi, shard, synth
+    from pyitd_b200.itd import get_plan
+    stream = torch.cuda.current_stream(dev)
+    if which == 5:
+        code, tdt, mi, N, io, carry = _capi.F64, torch.float64, MAX_ITERATION, N_SAMPLES, 8, 8
+        a, b = shard.shard_range(args.config5_channels, rank, world)
+        chunks = [synth.eeg_like(c1 - c0, N, seed=SEED + c0 // 4096, device=dev, first_channel=c0,
+                                 total_channels=args.config5_channels)
+                  for c0, c1 in shard.chunk_ranges(a, b, 4096)]
+        what = (f"configs[4]: {args.config5_channels} x 65536-sample fp64 channels, STRONG split over {world} GPU(s): "
+                f"{b - a} channels on this rank in {len(chunks)} chunk(s) of <= 4096 that recycle one output buffer")
+        steps, warm = 2, 1
+    elif which == 3:
+        code, tdt, mi, N, io, carry = _capi.F32_MIXED, torch.float32, MAX_ITERATION, 1 << 28, 4, 8
+        chunks = [synth.long_signal(n=N, seed=3, device=dev).unsqueeze(0)]
+        what = "configs[2]: single long signal of 2^28 samples, fp32 in/out around an fp64 carry (f32_mixed)"
+        steps, warm = 5, 3
+    else:
+        code, tdt, mi, N, io, carry = _capi.F32_MIXED, torch.float32, 7, 8192, 4, 8
+        chunks = [torch.from_numpy(synth.audio_frames()).to(dev)]
+        what = f"configs[3]: 48 kHz audio, 10 min, {chunks[0].shape[0]} frames of 8192, fixed 8 iterations, f32_mixed"
+        steps, warm = 10, 3
+    if not chunks:
+        chunks = []
+    Smax = max((c.shape[0] for c in chunks), default=1)
+    plans = {c.shape[0]: get_plan(local_rank, c.shape[0], N, code, mi, 2, 0) for c in chunks}
+    rows = mi + 2
+    need = Smax * rows * N
+    if rot_buf is not None and rot_buf.dtype == tdt and rot_buf.numel() >= need:
+        rot = rot_buf.view(-1)[:need].view(Smax, rows, N)
+    else:
+        rot = torch.empty((Smax, rows, N), dtype=tdt, device=dev)
+    ints = [torch.empty(Smax * (rows if i == 1 else 1), dtype=torch.int32, device=dev) for i in range(5)]
+    nr_all = [torch.empty(c.shape[0], dtype=torch.int32, device=dev) for c in chunks]
+    st_all = [torch.empty(c.shape[0], dtype=torch.int32, device=dev) for c in chunks]
+
+    def step():
+        for c, nra, sta in zip(chunks, nr_all, st_all):
+            plans[c.shape[0]].decompose_device(c.data_ptr(), rot.data_ptr(), None, nra.data_ptr(), ints[1].data_ptr(),
+                                               ints[2].data_ptr(), ints[3].data_ptr(), sta.data_ptr(), stream.cuda_stream)
+
+    ms = timed_passes(torch, shard, step, stream, dev, steps, warm, world, dist)
+    tot = torch.tensor([sum(c.shape[0] for c in chunks), sum(int(t.long().sum()) for t in nr_all),
+                        max((int(t.abs().max()) for t in st_all), default=0)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot[:2])
+        dist.all_reduce(tot[2:], op=dist.ReduceOp.MAX)
+    S_total, levels_total, st_max = int(tot[0]), int(tot[1]), int(tot[2])
+    # algorithmic bytes (SURVEY 8d): per executed level read X (carry type; the first level reads the io type),
+    # write R (io type), write B (carry type)
+    alg = levels_total * N * (carry + io + carry) - S_total * N * (carry - io)
+    path = next(iter(plans.values())).path if plans else ("none", 1)
+    out = {"workload": what, "value": S_total * N / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+           "n_gpus": world, "scaling": "strong" if which == 5 else "single GPU", "signals": S_total, "n_samples": N,
+           "rows_mean": levels_total / max(S_total, 1), "kernel_path": path[0], "status_max": st_max,
+           "roofline_whole_step": {"bound": "hbm", "algorithmic_bytes_per_step": alg, "unit": "GB/s per GPU",
+                                   "achieved": alg / (ms * 1e-3) / 1e9 / world, "peak": peak,
+                                   "frac": alg / (ms * 1e-3) / 1e9 / world / peak}}
+    del chunks, plans, rot, ints
+    return out
+
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
@@ -225,6 +362,11 @@ def main():
         raise SystemExit("bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU port")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # the pinned host buffers of the e2e leg should live next to this rank's GPU, not wherever torchrun started the
+    # process (SCALE_r01: eight D2H streams into one NUMA node); the CPU baseline leg gets the full mask back
+    from pyitd_b200 import shard
+    cpu_mask = os.sched_getaffinity(0)
+    bound = None if args.no_bind else shard.bind_to_gpu_numa_node(local_rank)
     if world > 1:
         # stdout carries exactly one JSON line: NCCL's own log lines (e.g. the "NCCL version" banner) go to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -282,6 +424,14 @@ def main():
     ms_per_step = ms_total / args.steps
     value = world * S * N / (ms_per_step * 1e-3)
 
+    # ---- parity of the timed output (every rank checks its own shard; rank 0 reports the worst) ----
+    parity = parity_check(torch, x, rot, n_rows, counts, args.parity_channels, seed=SEED + 77 + rank)
+    pbad = torch.tensor([0 if parity["bit_exact"] else 1], dtype=torch.int32, device=dev)
+    if world > 1:
+        dist.all_reduce(pbad, op=dist.ReduceOp.MAX)
+    parity["all_ranks_bit_exact"] = int(pbad.item()) == 0
+    parity["channels_all_ranks"] = parity["channels"] * world
+
     # ---- roofline of the dominant kernel, per-launch CUDA events on the launching stream ----------
     # (a) launch chains serialised (one group): every launch timed alone; (b) with the library's launch groups the
     # chains overlap, so the call is timed fork-to-join and the level kernel's share is taken from its bytes
@@ -303,6 +453,7 @@ def main():
             span_ms += plan.launch_times_ms()[0] / reps
     plan.enable_timing(False)
     nr = n_rows.long()
+    rows_mean = float(nr.double().mean())
     active = [int((nr >= e + 1).sum()) for e in range(rows)]        # signals that execute extraction e
     level_bytes = [a * N * 24 for a in active]                      # read X + write R + write B, fp64
     alg_bytes = sum(level_bytes)
@@ -314,12 +465,22 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
     path, cluster = plan.path
-    traffic_ratio = None
+    # dram__bytes of the dominant kernel come from an ncu --set full capture (profiles/run_ncu_traffic.sh writes
+    # profiles/dominant_kernel_traffic.json with the hash of the CUDA sources it profiled); a capture of another build
+    # says nothing about this one, so the field is dropped (null) when the hashes differ
+    src_hash = kernel_source_hash()
+    traffic = None
+    traffic_note = "no ncu capture of this build under profiles/ (source hash %s): not reported" % src_hash
     try:
-        traffic_ratio = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"))).get("traffic_over_algorithmic")
+        cap = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
+        if cap.get("source_hash") == src_hash and cap.get("dram_bytes_per_launch"):
+            traffic = float(cap["dram_bytes_per_launch"])
+            traffic_note = cap.get("how", "ncu --set full capture of this build")
+        elif cap.get("source_hash"):
+            traffic_note = ("the committed ncu capture is of source hash %s, this build is %s: dropped"
+                            % (cap.get("source_hash"), src_hash))
     except Exception:
         pass
-    traffic = None
     sample_levels = int(nr.sum()) * N
     if path in ("resident", "regres"):
         # ONE launch decomposes the whole batch; the carry never leaves the SMs, so the bytes that MUST
@@ -366,11 +527,8 @@ def main():
                 "avg_launch_ms": span_ms / max(n_lv, 1), "launch_groups": groups, "call_span_ms": span_ms,
                 "achieved_definition": "level-kernel algorithmic bytes of the call / fork-to-join CUDA-event time of the "
                                        "call (the knot-scan launches run inside that span and are not credited)"})
-        if traffic_ratio and path == "stream":
-            # dram__bytes_read+write of this kernel from the committed ncu --set full capture, as a ratio to the
-            # algorithmic bytes of the captured launch, applied to this run's average launch
-            roofline["traffic"] = traffic_ratio * roofline["algorithmic_bytes_per_launch"]
-            roofline["traffic_source"] = "profiles/dominant_kernel_traffic.json (ncu dram bytes / algorithmic bytes = %.2f)" % traffic_ratio
+    roofline["traffic_source"] = traffic_note
+    roofline["kernel_source_hash"] = src_hash
 
     # ---- e2e: host buffers through the C ABI (pyitd_decompose_host) -------------------------------
     e2e = None
@@ -407,14 +565,62 @@ def main():
                "d2h_bytes_per_step": d2h, "channels_per_step": Se, "steps": k_e2e,
                "api": "pyitd_decompose_host (C ABI, pinned host buffers; chunked H2D/kernel/D2H pipeline, "
                       "every produced rotation row copied back)"}
+        # ceiling of this call: the raw pinned D2H rate with ALL ranks copying at once (the call returns ~86 bytes
+        # for every 8-byte input sample, so PCIe / the host memory path bounds it, not the kernels)
+        n_probe = min(hrot.numel(), rot.numel(), 1 << 30)            # <= 8 GiB per rank
+        src = rot.view(-1)[:n_probe]
+        dst = hrot.view(-1)[:n_probe]
+        dst.copy_(src, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        dtp = time.perf_counter() - t0
+        tp = torch.tensor([dtp], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        ceil_gbs = world * 2 * n_probe * 8 / float(tp.item()) / 1e9
+        d2h_gbs = world * d2h * k_e2e / dt / 1e9
+        e2e.update({"d2h_gbs": d2h_gbs, "d2h_ceiling_gbs": ceil_gbs, "pcie_frac": d2h_gbs / ceil_gbs,
+                    "d2h_ceiling_how": f"{world} rank(s) each copying {n_probe * 8 >> 20} MiB device -> pinned host twice, "
+                                       "concurrently, max over ranks (aggregate GB/s)",
+                    "bytes_returned_per_input_sample": d2h / (Se * N),
+                    "numa_bound_cpus": (f"{bound[0]}-{bound[-1]} ({len(bound)} cores)" if bound else None)})
+        del hx, hrot
+
+    # ---- the other BASELINE.json configs, reported beside the headline ------------------------------
+    extra = None
+    if not args.no_extra:
+        extra = {}
+        # configs[4]: 65 536 channels as a STRONG split over the ranks (the weak-scaling headline above is unchanged)
+        try:
+            extra["config5"] = extra_config(torch, dist, 5, args, rank, world, local_rank, dev, peak, rot_buf=rot)
+        except Exception as ex:                                        # never lose the headline line to an extra leg
+            extra["config5"] = {"error": repr(ex)}
+        if world == 1:
+            del x
+            for which, name in ((4, "config4"), (3, "config3")):
+                try:
+                    pyitd_b200.clear_plan_cache()
+                    torch.cuda.empty_cache()
+                    extra[name] = extra_config(torch, dist, which, args, rank, world, local_rank, dev, peak)
+                except Exception as ex:
+                    extra[name] = {"error": repr(ex)}
+        pyitd_b200.clear_plan_cache()
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
+    try:
+        os.sched_setaffinity(0, cpu_mask)
+    except OSError:
+        pass
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, threads, n_ch, secs = cpu_port_throughput(N)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{n_ch} channels x {N} samples of the same generator in {secs:.1f} s "
-                         f"(oracle/itd_oracle.c, one channel per pthread)"}
+                         f"(oracle/itd_oracle.c, one channel per pthread; the same sample as one step of --impl reference)",
+               "numba_per_core": NUMBA_REFERENCE_PER_CORE}
 
     if rank == 0:
         line = {
@@ -423,11 +629,15 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu,
-            "rows_per_channel_mean": float(nr.double().mean()),
+            "rows_per_channel_mean": rows_mean, "parity": parity, "extra_configs": extra,
+            "notes": "value / roofline run with options = 0 (rotation + trend rows only; the drop-in ITD.itd also stores "
+                     "the baselines, +8 B per sample-level); --impl reference times the oracle's C port, not numba",
         }
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if not parity["all_ranks_bit_exact"]:
+        raise SystemExit("bench.py: the timed output differs from the oracle on channels %s" % parity["mismatching_channels"])
 
 
 if __name__ == "__main__":

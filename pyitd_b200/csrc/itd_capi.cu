@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 
@@ -36,6 +37,23 @@ static int fail(int code, const std::string &msg) {
     } while (0)
 
 constexpr int kMaxGroups = 16;
+
+// every entry point runs on the plan's device and puts the caller's current device back on return
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+#define ON_DEVICE(dev)      \
+    DeviceGuard _guard(dev); \
+    CU(_guard.err)
 
 struct pyitd_plan {
     int device = 0;
@@ -92,7 +110,28 @@ struct pyitd_plan {
         cudaStream_t stream = nullptr;
     } slot[2];
     long long host_chunk = 0;
+    // A plan's workspace (carry buffers, knot tables, look-back descriptors, stop bookkeeping) belongs to ONE call at
+    // a time.  `mu` serialises host threads for the duration of a call (calls only enqueue work); `busy` is recorded on
+    // the caller's stream at the end of every device call and the next call on a DIFFERENT stream waits for it, so
+    // two calls that share a cached plan never overlap on the GPU.
+    std::mutex mu;
+    cudaEvent_t busy = nullptr;
+    cudaStream_t busy_stream = nullptr;
+    bool busy_valid = false;
 };
+
+// order this call after the plan's previous call when that one ran on another stream
+static int plan_acquire(pyitd_plan *pl, cudaStream_t st) {
+    if (pl->busy_valid && pl->busy_stream != st) CU(cudaStreamWaitEvent(st, pl->busy, 0));
+    return 0;
+}
+static int plan_release(pyitd_plan *pl, cudaStream_t st) {
+    if (!pl->busy) CU(cudaEventCreateWithFlags(&pl->busy, cudaEventDisableTiming));
+    CU(cudaEventRecord(pl->busy, st));
+    pl->busy_stream = st;
+    pl->busy_valid = true;
+    return 0;
+}
 
 // ---------------------------------------------------------------------------------------------
 // tile configurations.  T = THREADS * ITEMS samples per CTA.
@@ -454,7 +493,7 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
     int ndev = pyitd_device_count();
     if (ndev <= 0) return fail(PYITD_E_NODEVICE, "no CUDA device visible");
     if (device < 0 || device >= ndev) return fail(PYITD_E_INVALID, "device index out of range");
-    CU(cudaSetDevice(device));
+    ON_DEVICE(device);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10)
@@ -524,9 +563,8 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
 
 // the device workspace is allocated on the first device call: a plan that is only used through
 // pyitd_decompose_host never needs the full-batch workspace (its chunk sub-plans own theirs)
-static int ensure_workspace(pyitd_plan *pl) {
+static int ensure_workspace(pyitd_plan *pl, cudaStream_t st) {
     if (pl->ws) return 0;
-    CU(cudaSetDevice(pl->device));
     const size_t SN = (size_t)pl->S * (size_t)pl->n;
     const long long kstride = (((long long)pl->n + 3) & ~3ll) + 4;
     const long long mstride = ((((long long)pl->n + 31) / 32) + 3) & ~3ll;
@@ -588,9 +626,11 @@ static int ensure_workspace(pyitd_plan *pl) {
     }
     pl->ls = b_ls ? take(b_ls) : nullptr;
     // the mask rows are padded to 4 words: the padding (and everything else) starts out as "no knot"
-    ce = cudaMemset(pl->table[0].mask, 0, b_mask);
-    if (ce == cudaSuccess) ce = cudaMemset(pl->table[1].mask, 0, b_mask);
-    if (ce == cudaSuccess) ce = cudaMemset(pl->desc, 0, b_desc);
+    // on the CALLER's stream: a cudaStreamNonBlocking stream is not ordered after the legacy default stream, so a
+    // synchronous cudaMemset could land after the first kernels of this call had written mask words or descriptors
+    ce = cudaMemsetAsync(pl->table[0].mask, 0, b_mask, st);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(pl->table[1].mask, 0, b_mask, st);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(pl->desc, 0, b_desc, st);
     if (ce != cudaSuccess) {
         cudaFree(pl->ws);
         pl->ws = nullptr;
@@ -601,7 +641,8 @@ static int ensure_workspace(pyitd_plan *pl) {
 
 extern "C" void pyitd_plan_destroy(pyitd_plan *pl) {
     if (!pl) return;
-    cudaSetDevice(pl->device);
+    DeviceGuard guard(pl->device);
+    if (pl->busy) cudaEventDestroy(pl->busy);
     for (auto &sl : pl->slot) {
         if (sl.sub) pyitd_plan_destroy(sl.sub);
         cudaFree(sl.x);
@@ -771,7 +812,7 @@ static int run_resident(pyitd_plan *pl, const void *x, void *rotations, void *ba
     return mark(pl, st);
 }
 
-extern "C" int pyitd_decompose_device(pyitd_plan *pl, const void *x, void *rotations, void *baselines,
+static int pyitd_decompose_device_impl(pyitd_plan *pl, const void *x, void *rotations, void *baselines,
                                       int32_t *n_rows, int32_t *knot_counts, int32_t *input_knots,
                                       int32_t *stop_kind, int32_t *status, void *stream) {
     if (!pl || !x || !rotations || !n_rows || !knot_counts || !status)
@@ -780,10 +821,9 @@ extern "C" int pyitd_decompose_device(pyitd_plan *pl, const void *x, void *rotat
         return fail(PYITD_E_INVALID, "plan was created with PYITD_OPT_BASELINES but baselines is null");
     if (!(pl->opts & kOptBaselines)) baselines = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(pl->device));
     if (pl->resident)
         return run_resident(pl, x, rotations, baselines, n_rows, knot_counts, input_knots, stop_kind, status, st);
-    if (int rc = ensure_workspace(pl)) return rc;
+    if (int rc = ensure_workspace(pl, st)) return rc;
     pl->launches = 0;
     pl->events_used = 0;
     int *sk = stop_kind ? stop_kind : pl->stop_kind;
@@ -917,7 +957,7 @@ extern "C" int pyitd_probe_mixed_traffic(const void *x, void *y, void *z, int64_
 
 extern "C" int pyitd_plan_enable_timing(pyitd_plan *pl, int enable) {
     if (!pl) return fail(PYITD_E_INVALID, "null plan");
-    CU(cudaSetDevice(pl->device));
+    ON_DEVICE(pl->device);
     if (enable && !pl->events) {
         pl->n_events = pl->emax + 5;
         pl->events = new (std::nothrow) cudaEvent_t[pl->n_events];
@@ -932,7 +972,7 @@ extern "C" int pyitd_plan_enable_timing(pyitd_plan *pl, int enable) {
 extern "C" int pyitd_plan_launch_times(pyitd_plan *pl, float *ms, int capacity) {
     if (!pl || !ms) return fail(PYITD_E_INVALID, "null argument");
     if (!pl->timing || pl->events_used < 2) return 0;
-    CU(cudaSetDevice(pl->device));
+    ON_DEVICE(pl->device);
     CU(cudaEventSynchronize(pl->events[pl->events_used - 1]));
     int n = pl->events_used - 1;
     if (n > capacity) n = capacity;
@@ -940,13 +980,12 @@ extern "C" int pyitd_plan_launch_times(pyitd_plan *pl, float *ms, int capacity) 
     return n;
 }
 
-extern "C" int pyitd_extract_level_device(pyitd_plan *pl, const void *x, void *rotation, void *baseline,
+static int pyitd_extract_level_device_impl(pyitd_plan *pl, const void *x, void *rotation, void *baseline,
                                           int32_t *knot_count, int32_t *status, void *stream) {
     if (!pl || !x || !rotation || !baseline || !knot_count || !status)
         return fail(PYITD_E_INVALID, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(pl->device));
-    if (int rc = ensure_workspace(pl)) return rc;
+    if (int rc = ensure_workspace(pl, st)) return rc;
     pl->launches = 0;
     const size_t b_sig = (size_t)pl->S * sizeof(int);
     CU(cudaMemsetAsync(pl->stop_e, 0x7f, b_sig, st));
@@ -980,7 +1019,7 @@ extern "C" int pyitd_extract_level_device(pyitd_plan *pl, const void *x, void *r
     return 0;
 }
 
-extern "C" int pyitd_extract_with_knots_device(pyitd_plan *pl, const void *x, const int32_t *knots,
+static int pyitd_extract_with_knots_device_impl(pyitd_plan *pl, const void *x, const int32_t *knots,
                                                int64_t knot_capacity, const int32_t *knot_count, int64_t n_knot_rows,
                                                void *rotation, void *baseline, int32_t *status, void *stream) {
     if (!pl || !x || !knots || !knot_count || !rotation || !baseline || !status || knot_capacity < 0)
@@ -988,8 +1027,7 @@ extern "C" int pyitd_extract_with_knots_device(pyitd_plan *pl, const void *x, co
     if (n_knot_rows != 1 && n_knot_rows != pl->S)
         return fail(PYITD_E_INVALID, "n_knot_rows must be 1 (one list shared by every signal) or n_signals");
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(pl->device));
-    if (int rc = ensure_workspace(pl)) return rc;
+    if (int rc = ensure_workspace(pl, st)) return rc;
     pl->launches = 0;
     const size_t b_sig = (size_t)pl->S * sizeof(int);
     CU(cudaMemsetAsync(pl->stop_e, 0x7f, b_sig, st));
@@ -1054,7 +1092,7 @@ static int run_spline(pyitd_plan *pl, const void *x, void *rotation, void *basel
                       int32_t *status, int min_knots, cudaStream_t st) {
     if (pl->dtype == PYITD_F32)
         return fail(PYITD_E_INVALID, "the spline variant computes in float64: use a PYITD_F64 or PYITD_F32_MIXED plan");
-    if (int rc = ensure_workspace(pl)) return rc;
+    if (int rc = ensure_workspace(pl, st)) return rc;
     CU(cudaMemsetAsync(status, 0, (size_t)pl->S * sizeof(int), st));
     if (int rc = run_scan(pl, x, status, knot_count, st)) return rc;
     SplineParams sp;
@@ -1081,10 +1119,9 @@ static int run_spline(pyitd_plan *pl, const void *x, void *rotation, void *basel
     return mark(pl, st);
 }
 
-extern "C" int pyitd_extract_spline_device(pyitd_plan *pl, const void *x, void *rotation, void *baseline,
+static int pyitd_extract_spline_device_impl(pyitd_plan *pl, const void *x, void *rotation, void *baseline,
                                            int32_t *knot_count, int32_t *status, int min_knots, void *stream) {
     if (!pl || !x || !baseline || !knot_count || !status) return fail(PYITD_E_INVALID, "null argument");
-    CU(cudaSetDevice(pl->device));
     pl->launches = 0;
     pl->events_used = 0;
     return run_spline(pl, x, rotation, baseline, knot_count, status, min_knots, (cudaStream_t)stream);
@@ -1120,8 +1157,8 @@ static int sift2d_crossways(pyitd_plan *rp, pyitd_plan *cp, const void *x, void 
                             int min_knots, cudaStream_t st) {
     const size_t elems = (size_t)sh.B * sh.H * sh.W;
     T *b0 = (T *)scratch, *b1 = b0 + elems, *b2 = b1 + elems;
-    if (int rc = ensure_workspace(rp)) return rc;
-    if (int rc = ensure_workspace(cp)) return rc;
+    if (int rc = ensure_workspace(rp, st)) return rc;
+    if (int rc = ensure_workspace(cp, st)) return rc;
     int *rk = rp->input_knots, *rs = rp->stop_kind, *ck = cp->input_knots, *cs = cp->stop_kind;   // per-signal scratch
     // lengthwise[r, :] = base(data[r, :])
     if (int rc = run_spline(rp, x, nullptr, b0, rk, rs, min_knots, st)) return rc;
@@ -1147,11 +1184,10 @@ extern "C" int64_t pyitd_crossways_scratch_bytes(const pyitd_plan *rp, int64_t n
     return (int64_t)(3 * (size_t)n_images * (size_t)height * (size_t)width * rp->io_elem);
 }
 
-extern "C" int pyitd_crossways_device(pyitd_plan *rp, pyitd_plan *cp, const void *images, void *out, void *scratch,
+static int pyitd_crossways_device_impl(pyitd_plan *rp, pyitd_plan *cp, const void *images, void *out, void *scratch,
                                       int64_t n_images, int64_t height, int64_t width, int min_knots, void *stream) {
     if (!images || !out || !scratch) return fail(PYITD_E_INVALID, "null argument");
     if (int rc = sift2d_check(rp, cp, n_images, height, width)) return rc;
-    CU(cudaSetDevice(rp->device));
     rp->launches = cp->launches = 0;
     rp->events_used = cp->events_used = 0;
     const Sift2dShape sh = {n_images, (int)height, (int)width};
@@ -1181,13 +1217,12 @@ static int sift2d_ensemble(pyitd_plan *rp, pyitd_plan *cp, const void *image, co
     return 0;
 }
 
-extern "C" int pyitd_ensemble2d_device(pyitd_plan *rp, pyitd_plan *cp, const void *image, const void *noise, void *lowpass,
+static int pyitd_ensemble2d_device_impl(pyitd_plan *rp, pyitd_plan *cp, const void *image, const void *noise, void *lowpass,
                                        void *scratch, int64_t draws, int64_t height, int64_t width, int min_knots,
                                        void *stream) {
     if (!image || !noise || !lowpass || !scratch) return fail(PYITD_E_INVALID, "null argument");
     if (draws < 1) return fail(PYITD_E_INVALID, "draws must be >= 1");
     if (int rc = sift2d_check(rp, cp, 2 * draws, height, width)) return rc;
-    CU(cudaSetDevice(rp->device));
     rp->launches = cp->launches = 0;
     rp->events_used = cp->events_used = 0;
     if (rp->dtype == PYITD_F64)
@@ -1239,15 +1274,14 @@ extern "C" int pyitd_column_fsum_device(const void *rows, int64_t n_signals, int
     return 0;
 }
 
-extern "C" int pyitd_find_knots_device(pyitd_plan *pl, const void *x, int kinds, int32_t *knots,
+static int pyitd_find_knots_device_impl(pyitd_plan *pl, const void *x, int kinds, int32_t *knots,
                                        int64_t knot_capacity, int32_t *knot_count, int32_t *status,
                                        void *stream) {
     if (!pl || !x || !knots || !knot_count || !status || knot_capacity < 0)
         return fail(PYITD_E_INVALID, "null argument");
     if (kinds < 1 || kinds > 3) return fail(PYITD_E_INVALID, "kinds must be 1 (valleys), 2 (peaks) or 3 (both)");
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaSetDevice(pl->device));
-    if (int rc = ensure_workspace(pl)) return rc;
+    if (int rc = ensure_workspace(pl, st)) return rc;
     pl->launches = 0;
     CU(cudaMemsetAsync(status, 0, (size_t)pl->S * sizeof(int), st));
     if (int rc = run_scan(pl, x, status, nullptr, st, kinds)) return rc;
@@ -1272,23 +1306,54 @@ extern "C" int pyitd_find_knots_device(pyitd_plan *pl, const void *x, int kinds,
 // ~8 x rows bytes come back for every 8 bytes that go in).  Only the rows a signal actually
 // produced are copied back unless PYITD_OPT_ZERO_TAIL asks for the zero-filled tail.
 // ---------------------------------------------------------------------------------------------
+// bytes one host-pipeline slot needs per signal: the device mirrors of x / rotations / baselines plus the sub-plan's
+// workspace (two carry buffers, two knot tables, flag masks; the knot_ls table of the stream / strided paths)
+static size_t host_slot_bytes_per_signal(const pyitd_plan *pl) {
+    const size_t n = (size_t)pl->n;
+    const size_t io = n * pl->io_elem, out = io * pl->rows;
+    const size_t ws = 2 * n * pl->carry_elem + 2 * (n + 8) * (sizeof(int) + pl->carry_elem) + n / 2 + n * pl->carry_elem;
+    return io + out * ((pl->opts & kOptBaselines) ? 2 : 1) + ws;
+}
+
 static long long pick_host_chunk(const pyitd_plan *pl) {
     if (const char *env = getenv("PYITD_HOST_CHUNK")) {
         long long v = atoll(env);
         if (v >= 1) return v < pl->S ? v : pl->S;
     }
-    // ~128 MiB of input per chunk, at least 256 signals when the batch has them (the one-CTA-per-
-    // signal kernels want a full GPU), and at least 4 chunks for the pipeline to overlap anything
+    // ~128 MiB of input per chunk, at least 4 chunks for the pipeline to overlap anything, and -- when the signals are
+    // short enough for the one-CTA-per-signal kernels -- at least 256 signals (those kernels want a full GPU)
     long long c = (long long)((128ull << 20) / ((size_t)pl->n * pl->io_elem));
-    if (c < 256) c = 256;
+    const bool stream_shape = (pl->n % 4 == 0) && (((long long)pl->n + kStreamTile - 1) / kStreamTile <= kStreamMaxTiles);
+    if (c < 256 && stream_shape) c = 256;
     if (c > pl->S / 4 && pl->S >= 1024) c = pl->S / 4;
+    // two slots must fit in 70 % of the free device memory: long signals get small chunks instead of E_NOMEM
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        const size_t per = host_slot_bytes_per_signal(pl);
+        const long long cap = (long long)((double)free_b * 0.7 / 2.0 / (double)per);
+        if (c > cap) c = cap;
+    } else {
+        cudaGetLastError();
+    }
     if (c > pl->S) c = pl->S;
     return c < 1 ? 1 : c;
 }
 
-static int ensure_host_slots(pyitd_plan *pl) {
-    if (pl->host_chunk) return 0;
-    const long long C = pick_host_chunk(pl);
+static void free_host_slots(pyitd_plan *pl) {
+    for (auto &sl : pl->slot) {
+        if (sl.sub) pyitd_plan_destroy(sl.sub);
+        cudaFree(sl.x);
+        cudaFree(sl.rot);
+        cudaFree(sl.bas);
+        cudaFree(sl.ints);
+        if (sl.h_rows) cudaFreeHost(sl.h_rows);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+        sl = pyitd_plan::HostSlot();
+    }
+    pl->host_chunk = 0;
+}
+
+static int create_host_slots(pyitd_plan *pl, long long C) {
     const bool want_bas = (pl->opts & kOptBaselines) != 0;
     const int nslots = (C < pl->S) ? 2 : 1;
     for (int b = 0; b < nslots; ++b) {
@@ -1304,19 +1369,28 @@ static int ensure_host_slots(pyitd_plan *pl) {
         CU(cudaMalloc((void **)&sl.ints, (4 + (size_t)pl->rows) * (size_t)C * sizeof(int)));
         CU(cudaMallocHost((void **)&sl.h_rows, 2 * (size_t)C * sizeof(int)));
     }
+    return 0;
+}
+
+static int ensure_host_slots(pyitd_plan *pl) {
+    if (pl->host_chunk) return 0;
+    const long long C = pick_host_chunk(pl);
+    if (int rc = create_host_slots(pl, C)) {
+        // a slot that was only partly created must not survive: the next call would overwrite (and leak) it
+        const std::string msg = g_err;
+        cudaGetLastError();
+        free_host_slots(pl);
+        return fail(rc, msg);
+    }
     pl->host_chunk = C;
     return 0;
 }
 
-extern "C" int pyitd_decompose_host(pyitd_plan *pl, const void *x, void *rotations, void *baselines,
-                                    int32_t *n_rows, int32_t *knot_counts, int32_t *input_knots,
-                                    int32_t *stop_kind, int32_t *status) {
-    if (!pl || !x || !rotations || !n_rows || !knot_counts || !status)
-        return fail(PYITD_E_INVALID, "null argument");
+// the chunk loop of pyitd_decompose_host; on an error the caller drains both slot streams before returning
+static int host_chunk_loop(pyitd_plan *pl, const void *x, void *rotations, void *baselines,
+                           int32_t *n_rows, int32_t *knot_counts, int32_t *input_knots,
+                           int32_t *stop_kind, int32_t *status) {
     const bool want_bas = (pl->opts & kOptBaselines) != 0;
-    if (want_bas && !baselines) return fail(PYITD_E_INVALID, "baselines is null");
-    CU(cudaSetDevice(pl->device));
-    if (int rc = ensure_host_slots(pl)) return rc;
     const long long C = pl->host_chunk;
     const size_t row_b = (size_t)pl->n * pl->io_elem;          // bytes of one row
     const size_t sig_out_b = row_b * pl->rows;                 // bytes of one signal's output block
@@ -1332,8 +1406,9 @@ extern "C" int pyitd_decompose_host(pyitd_plan *pl, const void *x, void *rotatio
         int *d_nrows = sl.ints, *d_counts = d_nrows + C, *d_ik = d_counts + C * pl->rows, *d_kind = d_ik + C,
             *d_status = d_kind + C;
         CU(cudaMemcpyAsync(sl.x, (const char *)x + (size_t)s0 * row_b, (size_t)cs * row_b, cudaMemcpyHostToDevice, st));
-        // a short last chunk runs on the full-size sub-plan: the tail signals decompose stale data
-        // that is never copied back
+        // a short last chunk runs on the full-size sub-plan: its tail signals decompose zeros (monotone input: one
+        // level, one all-zero row) instead of whatever the slot held, and are never copied back
+        if (cs < C) CU(cudaMemsetAsync((char *)sl.x + (size_t)cs * row_b, 0, (size_t)(C - cs) * row_b, st));
         if (int rc = pyitd_decompose_device(sl.sub, sl.x, sl.rot, want_bas ? sl.bas : nullptr, d_nrows, d_counts,
                                             d_ik, d_kind, d_status, st))
             return rc;
@@ -1376,7 +1451,130 @@ extern "C" int pyitd_decompose_host(pyitd_plan *pl, const void *x, void *rotatio
         if (stop_kind)
             for (long long s = 0; s < cs; ++s) stop_kind[s0 + s] = sl.h_rows[C + s];
     }
-    for (auto &sl : pl->slot)
-        if (sl.stream) CU(cudaStreamSynchronize(sl.stream));
     return 0;
 }
+
+static int pyitd_decompose_host_impl(pyitd_plan *pl, const void *x, void *rotations, void *baselines,
+                                    int32_t *n_rows, int32_t *knot_counts, int32_t *input_knots,
+                                    int32_t *stop_kind, int32_t *status) {
+    if (!pl || !x || !rotations || !n_rows || !knot_counts || !status)
+        return fail(PYITD_E_INVALID, "null argument");
+    if ((pl->opts & kOptBaselines) && !baselines) return fail(PYITD_E_INVALID, "baselines is null");
+    if (int rc = ensure_host_slots(pl)) return rc;
+    const int rc = host_chunk_loop(pl, x, rotations, baselines, n_rows, knot_counts, input_knots, stop_kind, status);
+    // success or not, nothing of this call may still be in flight when it returns: the other slot's copies write into
+    // the caller's buffers and its kernels use the slot's workspace
+    const std::string msg = g_err;
+    cudaError_t de = cudaSuccess;
+    for (auto &sl : pl->slot)
+        if (sl.stream) {
+            const cudaError_t e = cudaStreamSynchronize(sl.stream);
+            if (e != cudaSuccess && de == cudaSuccess) de = e;
+        }
+    if (rc) return fail(rc, msg);
+    if (de != cudaSuccess) return fail(PYITD_E_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(de));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// public entry points: one call at a time per plan (host lock), on the plan's device (restored on return), ordered
+// after the plan's previous call when that ran on another stream
+// ---------------------------------------------------------------------------------------------
+extern "C" int pyitd_decompose_device(pyitd_plan *pl, const void *x, void *rotations, void *baselines, int32_t *n_rows, int32_t *knot_counts, int32_t *input_knots, int32_t *stop_kind, int32_t *status, void *stream) {
+    if (!pl) return fail(PYITD_E_INVALID, "null plan");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    ON_DEVICE(pl->device);
+    if (int rc = plan_acquire(pl, (cudaStream_t)stream)) return rc;
+    const int rc = pyitd_decompose_device_impl(pl, x, rotations, baselines, n_rows, knot_counts, input_knots, stop_kind, status, stream);
+    if (rc == 0) {
+        if (int rr = plan_release(pl, (cudaStream_t)stream)) return rr;
+    }
+    return rc;
+}
+
+extern "C" int pyitd_extract_level_device(pyitd_plan *pl, const void *x, void *rotation, void *baseline, int32_t *knot_count, int32_t *status, void *stream) {
+    if (!pl) return fail(PYITD_E_INVALID, "null plan");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    ON_DEVICE(pl->device);
+    if (int rc = plan_acquire(pl, (cudaStream_t)stream)) return rc;
+    const int rc = pyitd_extract_level_device_impl(pl, x, rotation, baseline, knot_count, status, stream);
+    if (rc == 0) {
+        if (int rr = plan_release(pl, (cudaStream_t)stream)) return rr;
+    }
+    return rc;
+}
+
+extern "C" int pyitd_extract_with_knots_device(pyitd_plan *pl, const void *x, const int32_t *knots, int64_t knot_capacity, const int32_t *knot_count, int64_t n_knot_rows, void *rotation, void *baseline, int32_t *status, void *stream) {
+    if (!pl) return fail(PYITD_E_INVALID, "null plan");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    ON_DEVICE(pl->device);
+    if (int rc = plan_acquire(pl, (cudaStream_t)stream)) return rc;
+    const int rc = pyitd_extract_with_knots_device_impl(pl, x, knots, knot_capacity, knot_count, n_knot_rows, rotation, baseline, status, stream);
+    if (rc == 0) {
+        if (int rr = plan_release(pl, (cudaStream_t)stream)) return rr;
+    }
+    return rc;
+}
+
+extern "C" int pyitd_extract_spline_device(pyitd_plan *pl, const void *x, void *rotation, void *baseline, int32_t *knot_count, int32_t *status, int min_knots, void *stream) {
+    if (!pl) return fail(PYITD_E_INVALID, "null plan");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    ON_DEVICE(pl->device);
+    if (int rc = plan_acquire(pl, (cudaStream_t)stream)) return rc;
+    const int rc = pyitd_extract_spline_device_impl(pl, x, rotation, baseline, knot_count, status, min_knots, stream);
+    if (rc == 0) {
+        if (int rr = plan_release(pl, (cudaStream_t)stream)) return rr;
+    }
+    return rc;
+}
+
+extern "C" int pyitd_find_knots_device(pyitd_plan *pl, const void *x, int kinds, int32_t *knots, int64_t knot_capacity, int32_t *knot_count, int32_t *status, void *stream) {
+    if (!pl) return fail(PYITD_E_INVALID, "null plan");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    ON_DEVICE(pl->device);
+    if (int rc = plan_acquire(pl, (cudaStream_t)stream)) return rc;
+    const int rc = pyitd_find_knots_device_impl(pl, x, kinds, knots, knot_capacity, knot_count, status, stream);
+    if (rc == 0) {
+        if (int rr = plan_release(pl, (cudaStream_t)stream)) return rr;
+    }
+    return rc;
+}
+
+extern "C" int pyitd_crossways_device(pyitd_plan *rp, pyitd_plan *cp, const void *images, void *out, void *scratch, int64_t n_images, int64_t height, int64_t width, int min_knots, void *stream) {
+    if (!rp || !cp) return fail(PYITD_E_INVALID, "null plan");
+    std::unique_lock<std::mutex> lk0(rp->mu, std::defer_lock), lk1(cp->mu, std::defer_lock);
+    if (rp == cp) lk0.lock(); else std::lock(lk0, lk1);
+    ON_DEVICE(rp->device);
+    if (int rc = plan_acquire(rp, (cudaStream_t)stream)) return rc;
+    if (int rc = plan_acquire(cp, (cudaStream_t)stream)) return rc;
+    const int rc = pyitd_crossways_device_impl(rp, cp, images, out, scratch, n_images, height, width, min_knots, stream);
+    if (rc == 0) {
+        if (int rr = plan_release(rp, (cudaStream_t)stream)) return rr;
+        if (int rr = plan_release(cp, (cudaStream_t)stream)) return rr;
+    }
+    return rc;
+}
+
+extern "C" int pyitd_ensemble2d_device(pyitd_plan *rp, pyitd_plan *cp, const void *image, const void *noise, void *lowpass, void *scratch, int64_t draws, int64_t height, int64_t width, int min_knots, void *stream) {
+    if (!rp || !cp) return fail(PYITD_E_INVALID, "null plan");
+    std::unique_lock<std::mutex> lk0(rp->mu, std::defer_lock), lk1(cp->mu, std::defer_lock);
+    if (rp == cp) lk0.lock(); else std::lock(lk0, lk1);
+    ON_DEVICE(rp->device);
+    if (int rc = plan_acquire(rp, (cudaStream_t)stream)) return rc;
+    if (int rc = plan_acquire(cp, (cudaStream_t)stream)) return rc;
+    const int rc = pyitd_ensemble2d_device_impl(rp, cp, image, noise, lowpass, scratch, draws, height, width, min_knots, stream);
+    if (rc == 0) {
+        if (int rr = plan_release(rp, (cudaStream_t)stream)) return rr;
+        if (int rr = plan_release(cp, (cudaStream_t)stream)) return rr;
+    }
+    return rc;
+}
+
+extern "C" int pyitd_decompose_host(pyitd_plan *pl, const void *x, void *rotations, void *baselines, int32_t *n_rows, int32_t *knot_counts, int32_t *input_knots, int32_t *stop_kind, int32_t *status) {
+    if (!pl) return fail(PYITD_E_INVALID, "null plan");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    ON_DEVICE(pl->device);
+    const int rc = pyitd_decompose_host_impl(pl, x, rotations, baselines, n_rows, knot_counts, input_knots, stop_kind, status);
+    return rc;
+}
+

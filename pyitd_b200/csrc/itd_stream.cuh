@@ -53,8 +53,17 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
         : "memory");
     return ok != 0;
 }
+// try_wait itself suspends the thread for a bounded time; after a few failed rounds back off with nanosleep so that a
+// long wait (a TMA slice behind a busy memory system) does not burn issue slots.  -DPYITD_DEBUG_TRAP turns a wait that
+// never ends (a descriptor or byte-count bug) into a trap instead of a hang.
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (++spins > 16u) __nanosleep(64);
+#ifdef PYITD_DEBUG_TRAP
+        if (spins > (1u << 24)) __trap();
+#endif
     }
 }
 // global -> shared bulk copy; dst, src 16-byte aligned, bytes a multiple of 16

@@ -15,6 +15,7 @@
 #include <torch/library.h>
 
 #include <list>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <tuple>
@@ -27,12 +28,15 @@ using at::Tensor;
 
 // ---- plan cache: a plan owns the HBM workspace of one batch shape (GBs for big batches) ---------------------------
 using PlanKey = std::tuple<int, int64_t, int64_t, int, int, int, int>;
-struct PlanEntry { PlanKey key; pyitd_plan *plan; };
+// a caller holds a reference for the duration of its call: an LRU eviction from another thread only drops the cache's
+// reference, the plan is destroyed when its last user returns (the C library itself serialises calls on one plan)
+using PlanRef = std::shared_ptr<pyitd_plan>;
+struct PlanEntry { PlanKey key; PlanRef plan; };
 std::mutex g_mu;
 std::list<PlanEntry> g_plans;               // most recently used first
 constexpr size_t kMaxPlans = 4;
 
-pyitd_plan *get_plan(int device, int64_t S, int64_t N, int dtype, int max_iteration, int min_extrema, int options) {
+PlanRef get_plan(int device, int64_t S, int64_t N, int dtype, int max_iteration, int min_extrema, int options) {
     PlanKey key{device, S, N, dtype, max_iteration, min_extrema, options};
     std::lock_guard<std::mutex> lock(g_mu);
     for (auto it = g_plans.begin(); it != g_plans.end(); ++it)
@@ -40,20 +44,16 @@ pyitd_plan *get_plan(int device, int64_t S, int64_t N, int dtype, int max_iterat
             g_plans.splice(g_plans.begin(), g_plans, it);
             return g_plans.front().plan;
         }
-    while (g_plans.size() >= kMaxPlans) {
-        pyitd_plan_destroy(g_plans.back().plan);
-        g_plans.pop_back();
-    }
+    while (g_plans.size() >= kMaxPlans) g_plans.pop_back();
     pyitd_plan *p = nullptr;
     int rc = pyitd_plan_create(&p, device, S, N, dtype, max_iteration, min_extrema, options);
     TORCH_CHECK(rc == 0, "pyitd_plan_create failed (", rc, "): ", pyitd_last_error());
-    g_plans.push_front({key, p});
-    return p;
+    g_plans.push_front({key, PlanRef(p, [](pyitd_plan *q) { pyitd_plan_destroy(q); })});
+    return g_plans.front().plan;
 }
 
 void clear_plans() {
     std::lock_guard<std::mutex> lock(g_mu);
-    for (auto &e : g_plans) pyitd_plan_destroy(e.plan);
     g_plans.clear();
 }
 
@@ -85,7 +85,8 @@ std::tuple<Tensor, Tensor, Tensor> find_knots_cuda(const Tensor &x_, int64_t kin
     Tensor x = as_batch(x_);
     c10::cuda::CUDAGuard guard(x.device());
     const int64_t S = x.size(0), N = x.size(1), cap = capacity > 0 ? capacity : N;
-    pyitd_plan *plan = get_plan(x.get_device(), S, N, precision_code(x, ""), 0, 2, 0);
+    PlanRef plan_ref = get_plan(x.get_device(), S, N, precision_code(x, ""), 0, 2, 0);
+    pyitd_plan *plan = plan_ref.get();
     auto iopt = x.options().dtype(at::kInt);
     Tensor knots = at::empty({S, cap}, iopt), count = at::empty({S}, iopt), status = at::empty({S}, iopt);
     check_rc(pyitd_find_knots_device(plan, x.data_ptr(), (int)kinds, knots.data_ptr<int32_t>(), cap, count.data_ptr<int32_t>(),
@@ -98,7 +99,8 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> extract_level_cuda(const Tensor &x_, 
     Tensor x = as_batch(x_);
     c10::cuda::CUDAGuard guard(x.device());
     const int64_t S = x.size(0), N = x.size(1);
-    pyitd_plan *plan = get_plan(x.get_device(), S, N, precision_code(x, precision), 0, 2, 0);
+    PlanRef plan_ref = get_plan(x.get_device(), S, N, precision_code(x, precision), 0, 2, 0);
+    pyitd_plan *plan = plan_ref.get();
     auto iopt = x.options().dtype(at::kInt);
     Tensor R = at::empty_like(x), B = at::empty_like(x), count = at::empty({S}, iopt), status = at::empty({S}, iopt);
     check_rc(pyitd_extract_level_device(plan, x.data_ptr(), R.data_ptr(), B.data_ptr(), count.data_ptr<int32_t>(),
@@ -116,7 +118,8 @@ decompose_cuda(const Tensor &x_, int64_t max_iteration, int64_t min_extrema, boo
     c10::cuda::CUDAGuard guard(x.device());
     const int64_t S = x.size(0), N = x.size(1);
     const int options = (return_baselines ? PYITD_OPT_BASELINES : 0) | (zero_tail ? PYITD_OPT_ZERO_TAIL : 0);
-    pyitd_plan *plan = get_plan(x.get_device(), S, N, precision_code(x, precision), (int)max_iteration, (int)min_extrema, options);
+    PlanRef plan_ref = get_plan(x.get_device(), S, N, precision_code(x, precision), (int)max_iteration, (int)min_extrema, options);
+    pyitd_plan *plan = plan_ref.get();
     const int64_t rows = pyitd_plan_rows(plan);
     auto iopt = x.options().dtype(at::kInt);
     Tensor rot = at::empty({S, rows, N}, x.options());

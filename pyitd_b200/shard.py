@@ -85,6 +85,61 @@ def gather_summary(n_signals: int, n_rows: torch.Tensor, stop_kind: torch.Tensor
                         _all_gather_ragged(status, sizes), _all_gather_ragged(knot_counts, sizes), owner)
 
 
+def gpu_numa_cpus(device_index: int) -> Optional[list[int]]:
+    """CPU cores local to the GPU's PCIe root (``/sys/bus/pci/devices/<bdf>/local_cpulist``), or None when the
+    platform does not say (single-socket box, container without sysfs)."""
+    bdf = None
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        if all(hasattr(pr, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+    except Exception:
+        bdf = None
+    if not bdf:
+        try:
+            import subprocess
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device_index)],
+                                 capture_output=True, text=True, timeout=20).stdout.strip()
+            bdf = out.splitlines()[0].strip() if out else None
+        except Exception:
+            bdf = None
+    if not bdf:
+        return None
+    bdf = bdf.lower()
+    if len(bdf.split(":")[0]) == 8:            # nvidia-smi prints an 8-digit PCI domain, sysfs uses 4
+        bdf = bdf[4:]
+    try:
+        text = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+    except OSError:
+        return None
+    cpus: list[int] = []
+    for part in text.split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus or None
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[list[int]]:
+    """Pin this process to the CPU cores next to its GPU.  Pinned host buffers allocated afterwards are first-touched
+    on that NUMA node, so the D2H stream of every rank stays on its own socket instead of all ranks sharing the node
+    the launcher happened to start them on (SCALE_r01: eight D2H streams saturated one node's memory path).  Returns
+    the CPU list used, or None when nothing was changed."""
+    cpus = gpu_numa_cpus(device_index)
+    if not cpus:
+        return None
+    try:
+        allowed = os.sched_getaffinity(0)
+        use = sorted(set(cpus) & set(allowed))
+        if not use:
+            return None
+        os.sched_setaffinity(0, use)
+        return use
+    except (AttributeError, OSError):
+        return None
+
+
 def max_over_ranks(value: float, device=None) -> float:
     """MAX-reduce a timing over the ranks (every multi-GPU number is the slowest rank's)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
@@ -111,7 +166,16 @@ def decompose_sharded(make_shard: Callable[[int, int], torch.Tensor], n_signals:
     x = make_shard(start, stop)
     if x.shape[0] != stop - start:
         raise ValueError(f"make_shard returned {x.shape[0]} channels for the block [{start}, {stop})")
-    res = decompose_fn(x, max_iteration=max_iteration, min_extrema=min_extrema, **kw)
+    if stop == start:
+        # fewer signals than ranks: this rank owns nothing, but it must still enter the gather below (the other ranks
+        # would block in all_gather forever if it raised on the empty batch instead)
+        from .itd import ITDResult
+        rows = max_iteration + 2
+        i32 = dict(dtype=torch.int32, device=x.device)
+        res = ITDResult(torch.empty((0, rows, x.shape[1]), dtype=x.dtype, device=x.device), torch.empty(0, **i32),
+                        torch.empty((0, rows), **i32), torch.empty(0, **i32), torch.empty(0, **i32), torch.empty(0, **i32))
+    else:
+        res = decompose_fn(x, max_iteration=max_iteration, min_extrema=min_extrema, **kw)
     summary = None
     if gather:
         summary = gather_summary(n_signals, res.n_rows, res.stop_kind, res.status, res.knot_counts)

@@ -448,6 +448,54 @@ def test_eeg_like_batch_config2_subset():
     assert len(set(res.n_rows.cpu().tolist())) > 1
 
 
+def check_batch_against_c_oracle(res, x, max_iteration=11, baselines=True):
+    """every channel of a big batch bit-for-bit against the multi-threaded C oracle (rows, baselines, knot counts,
+    stop kind) -- one oracle call for the whole batch, so hundreds of 65 536-sample channels take a second or two."""
+    rot, n_rows, counts, status, bas = o.c_decompose_batch(x, max_iteration, want_baselines=baselines)
+    assert int(np.abs(status).max()) == 0
+    assert res.status.cpu().tolist() == [0] * x.shape[0]
+    assert res.n_rows.cpu().tolist() == n_rows.tolist()
+    got_rot = res.rotations.cpu().numpy()
+    got_bas = res.baselines.cpu().numpy() if baselines else None
+    got_cnt = res.knot_counts.cpu().numpy()
+    kind = res.stop_kind.cpu().numpy()
+    emax = max_iteration + 1
+    for s in range(x.shape[0]):
+        nr = int(n_rows[s])
+        assert got_rot[s, :nr].tobytes() == rot[s, :nr].tobytes(), f"signal {s}: rotations differ"
+        assert got_cnt[s, :nr].tolist() == counts[s, :nr].tolist(), f"signal {s}: knot counts differ"
+        want_kind = _capi.STOP_KNOTS if counts[s, nr - 1] < 2 else _capi.STOP_ITER
+        assert int(kind[s]) == want_kind and (want_kind == _capi.STOP_KNOTS or nr == emax + 1), s
+        if baselines:
+            nb = nr if want_kind == _capi.STOP_ITER else nr - 1
+            assert got_bas[s, :nb].tobytes() == bas[s, :nb].tobytes(), f"signal {s}: baselines differ"
+
+
+@pytest.mark.parametrize("groups", [1, 2])
+def test_benchmarked_stream_path_256_channels_bit_exact(groups, monkeypatch):
+    """The kernel the headline number comes from (one CTA per signal, N = 65 536 = 64 tiles per signal, launch groups 1
+    and 2, bench.py's generator): 256 channels, EVERY channel bit for bit against the oracle -- rotations, baselines,
+    per-level knot counts, stop kind (ITD.py:351-433)."""
+    monkeypatch.setenv("PYITD_FORCE_PATH", "stream")
+    monkeypatch.setenv("PYITD_GROUPS", str(groups))
+    pyitd_b200.clear_plan_cache()
+    try:
+        from pyitd_b200.itd import get_plan
+        plan = get_plan(0, 256, 65536, _capi.F64, 11, 2, _capi.OPT_BASELINES)
+        assert plan.path[0] == "stream" and plan.groups == groups
+        xg = synth.eeg_like(256, 65536, seed=1234, device="cuda")
+        res = pyitd_b200.decompose(xg, max_iteration=11, return_baselines=True)
+        torch.cuda.synchronize()
+        check_batch_against_c_oracle(res, xg.cpu().numpy(), 11)
+        assert len(set(res.n_rows.cpu().tolist())) > 2            # ragged stops
+        # the bench itself runs without baselines (options = 0): same rows
+        res0 = pyitd_b200.decompose(xg, max_iteration=11)
+        torch.cuda.synchronize()
+        check_batch_against_c_oracle(res0, xg.cpu().numpy(), 11, baselines=False)
+    finally:
+        pyitd_b200.clear_plan_cache()
+
+
 def test_zero_tail_option():
     rng = np.random.default_rng(13)
     x = _mixed_batch(rng, 6, 5000)

@@ -45,8 +45,10 @@ def _oracle_decompose(x, max_iteration=11, min_extrema=2, **kw):
 def _batch(n_signals, n):
     rng = np.random.default_rng(11)
     x = rng.standard_normal((n_signals, n))
-    x[1] = np.cumsum(x[1])
-    x[2] = np.arange(n, dtype=np.float64)          # monotone: one zero row
+    if n_signals > 1:
+        x[1] = np.cumsum(x[1])
+    if n_signals > 2:
+        x[2] = np.arange(n, dtype=np.float64)      # monotone: one zero row
     return torch.from_numpy(x)
 
 
@@ -75,7 +77,7 @@ def _worker(rank, world, port, n_signals, n, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_signals", [5, 8])
+@pytest.mark.parametrize("n_signals", [1, 5, 8])      # 1: rank 1 owns an EMPTY block and must still enter the gather
 def test_two_rank_sharded_driver_matches_single_process(tmp_path, n_signals):
     n, world = 600, 2
     port = _free_port()
@@ -99,3 +101,16 @@ def test_single_process_paths_need_no_process_group():
     res, summ = shard.decompose_sharded(lambda a, b: full[a:b], 4, max_iteration=3, decompose_fn=_oracle_decompose)
     assert torch.equal(summ.n_rows, res.n_rows) and int(summ.owner.max()) == 0
     assert shard.max_over_ranks(3.5) == 3.5
+
+
+def test_numa_binding_helper_is_safe_without_a_gpu():
+    """bind_to_gpu_numa_node only narrows the affinity mask to cores the platform lists next to the GPU; with no GPU
+    (or no sysfs entry) it changes nothing and says so."""
+    before = os.sched_getaffinity(0)
+    got = shard.bind_to_gpu_numa_node(0)
+    after = os.sched_getaffinity(0)
+    if got is None:
+        assert after == before
+    else:
+        assert set(got) == after and after <= before
+        os.sched_setaffinity(0, before)
