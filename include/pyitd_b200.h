@@ -86,6 +86,8 @@ PYITD_API int     pyitd_plan_launches(const pyitd_plan *plan);         /* kernel
 #define PYITD_PATH_STREAM   1
 #define PYITD_PATH_RESIDENT 2
 #define PYITD_PATH_STRIDED  3
+#define PYITD_PATH_SWEEP    4   /* many signals: ONE persistent launch decomposes the whole batch, every level (ticket-
+                                   scheduled (level, signal) items, one CTA per item, carry in HBM) */
 PYITD_API int     pyitd_plan_path(const pyitd_plan *plan, int *cluster_size);
 
 /* Stream path only: cut the batch into `groups` contiguous signal ranges (1..16), each with its own launch

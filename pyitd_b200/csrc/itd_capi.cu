@@ -15,6 +15,7 @@
 #include "itd_kernels.cuh"
 #include "itd_stream.cuh"
 #include "itd_strided.cuh"
+#include "itd_sweep.cuh"
 #include "itd_resident.cuh"
 #include "itd_spline.cuh"
 #include "itd_sift2d.cuh"
@@ -67,6 +68,12 @@ struct pyitd_plan {
     int tile = 1024, tiles = 0;
     bool stream = false;      // one-CTA-per-signal TMA-pipelined level kernel (itd_stream.cuh)
     bool strided = false;     // a few long signals, one at a time: persistent blocks stride over the tiles (itd_strided.cuh)
+    // many signals: the whole decomposition in one persistent launch (itd_sweep.cuh).  `stream` stays set when the shape
+    // allows it: the single-level entry points (extract_level, find_knots, ...) keep using those kernels.
+    bool sweep = false;
+    int sw_spans = 0, sw_spw = 0, sw_rs = 0, sw_grid = 0;
+    int *sw_ticket = nullptr, *sw_done = nullptr, *sw_rcount[2] = {nullptr, nullptr};
+    unsigned long long *sw_stage_ns = nullptr;
     int strided_cap = 0;      // test hook: upper bound on the persistent grid (PYITD_STRIDED_CTAS)
     // whole-decomposition-on-chip kernel (itd_resident.cuh): one cluster per signal, one launch per batch
     bool resident = false;
@@ -542,9 +549,17 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
     pl->strided = strided;
     if (const char *env = getenv("PYITD_STRIDED_CTAS")) pl->strided_cap = atoi(env);
     pl->stream = stream;
+    // the sweep kernel takes over pyitd_decompose_* wherever the one-CTA-per-signal kernels were chosen (it has no row
+    // alignment requirement: plain 8-byte loads); PYITD_FORCE_PATH=stream keeps the round-1 launch chain
+    bool sweep = !pl->resident && !strided && n_signals >= 160 && n_samples >= 2048;
+    if (const char *env = getenv("PYITD_FORCE_PATH")) sweep = !strcmp(env, "sweep");
+    pl->sweep = sweep;
+    pl->sw_spans = (int)((n_samples + kSweepSpan - 1) / kSweepSpan);
+    pl->sw_spw = (pl->sw_spans + kSweepWarps - 1) / kSweepWarps;
+    pl->sw_rs = pl->sw_spw * kSweepSpan + 8;
     // two launch chains hide most of the partial last wave of every level launch (measured: 17.35 -> 16.56 ms/step
     // on 4096 x 65536; more groups add nothing)
-    pl->groups = (stream && n_signals >= 1024) ? 2 : 1;
+    pl->groups = (stream && !sweep && n_signals >= 1024) ? 2 : 1;
     if (const char *env = getenv("PYITD_GROUPS")) {
         const int v = atoi(env);
         if (v >= 1 && v <= kMaxGroups) pl->groups = v;
@@ -566,7 +581,8 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
 static int ensure_workspace(pyitd_plan *pl, cudaStream_t st) {
     if (pl->ws) return 0;
     const size_t SN = (size_t)pl->S * (size_t)pl->n;
-    const long long kstride = (((long long)pl->n + 3) & ~3ll) + 4;
+    long long kstride = (((long long)pl->n + 3) & ~3ll) + 4;
+    if (pl->sweep && kstride < (long long)kSweepWarps * pl->sw_rs) kstride = (long long)kSweepWarps * pl->sw_rs;   // eight region lists
     const long long mstride = ((((long long)pl->n + 31) / 32) + 3) & ~3ll;
     const size_t SK = (size_t)pl->S * (size_t)kstride;
     const size_t b_carry = align_up(SN * pl->carry_elem);
@@ -586,7 +602,11 @@ static int ensure_workspace(pyitd_plan *pl, cudaStream_t st) {
     const int ls_div = getenv("PYITD_LS_DIV") ? (atoi(getenv("PYITD_LS_DIV")) > 1 ? atoi(getenv("PYITD_LS_DIV")) : 16) : 16;   // experiment hook (n/16 measured best: profiles/r1/s5/ls_probe2.log)
     pl->lscap = (ls_on && (pl->stream || pl->strided)) ? (int)((pl->n / ls_div) & ~1ll) : 0;   // even: float rows stay 16-byte aligned
     const size_t b_ls = pl->lscap ? align_up((size_t)pl->S * (size_t)(pl->lscap + 4) * 2 * pl->carry_elem) : 0;
-    size_t total = 2 * b_carry + 2 * (b_tau + b_xk + b_tbase + b_sig + b_endl + b_mask) + b_desc + 3 * b_sig + 2 * b_group + b_stage + b_ls;
+    const size_t b_sweep = pl->sweep ? align_up((size_t)(pl->rows + 4) * sizeof(int)) + align_up((size_t)pl->S * sizeof(int)) +
+                                           2 * align_up((size_t)pl->S * kSweepWarps * sizeof(int)) +
+                                           align_up((size_t)(pl->rows + 2) * sizeof(unsigned long long))
+                                     : 0;
+    size_t total = 2 * b_carry + 2 * (b_tau + b_xk + b_tbase + b_sig + b_endl + b_mask) + b_desc + 3 * b_sig + 2 * b_group + b_stage + b_ls + b_sweep;
     pl->ws_bytes = total;
     cudaError_t ce = cudaMalloc(&pl->ws, total);
     if (ce != cudaSuccess) {
@@ -625,6 +645,12 @@ static int ensure_workspace(pyitd_plan *pl, cudaStream_t st) {
         }
     }
     pl->ls = b_ls ? take(b_ls) : nullptr;
+    if (pl->sweep) {
+        pl->sw_ticket = (int *)take(align_up((size_t)(pl->rows + 4) * sizeof(int)));
+        pl->sw_done = (int *)take(align_up((size_t)pl->S * sizeof(int)));
+        for (int i = 0; i < 2; ++i) pl->sw_rcount[i] = (int *)take(align_up((size_t)pl->S * kSweepWarps * sizeof(int)));
+        pl->sw_stage_ns = (unsigned long long *)take(align_up((size_t)(pl->rows + 2) * sizeof(unsigned long long)));
+    }
     // the mask rows are padded to 4 words: the padding (and everything else) starts out as "no knot"
     // on the CALLER's stream: a cudaStreamNonBlocking stream is not ordered after the legacy default stream, so a
     // synchronous cudaMemset could land after the first kernels of this call had written mask words or descriptors
@@ -674,6 +700,7 @@ extern "C" int pyitd_plan_path(const pyitd_plan *pl, int *cluster_size) {
     if (!pl) return PYITD_E_INVALID;
     if (cluster_size) *cluster_size = pl->resident ? pl->res_cl : 1;
     if (pl->strided) return PYITD_PATH_STRIDED;
+    if (pl->sweep) return PYITD_PATH_SWEEP;
     return pl->resident ? PYITD_PATH_RESIDENT : (pl->stream ? PYITD_PATH_STREAM : PYITD_PATH_LOOKBACK);
 }
 
@@ -812,6 +839,9 @@ static int run_resident(pyitd_plan *pl, const void *x, void *rotations, void *ba
     return mark(pl, st);
 }
 
+static int run_sweep(pyitd_plan *pl, const void *x, void *rotations, void *baselines, int32_t *n_rows,
+                     int32_t *knot_counts, int32_t *input_knots, int *sk, int32_t *status, cudaStream_t st);
+
 static int pyitd_decompose_device_impl(pyitd_plan *pl, const void *x, void *rotations, void *baselines,
                                       int32_t *n_rows, int32_t *knot_counts, int32_t *input_knots,
                                       int32_t *stop_kind, int32_t *status, void *stream) {
@@ -833,6 +863,7 @@ static int pyitd_decompose_device_impl(pyitd_plan *pl, const void *x, void *rota
     CU(cudaMemsetAsync(status, 0, b_sig, st));
     CU(cudaMemsetAsync(n_rows, 0, b_sig, st));
     CU(cudaMemsetAsync(knot_counts, 0, b_sig * pl->rows, st));
+    if (pl->sweep) return run_sweep(pl, x, rotations, baselines, n_rows, knot_counts, input_knots, sk, status, st);
 
     // G > 1: fork one launch chain per signal range off the caller's stream and join them at the end; with
     // timing enabled the two events then bracket the whole call instead of every launch
@@ -913,6 +944,98 @@ static int pyitd_decompose_device_impl(pyitd_plan *pl, const void *x, void *rota
         if (int rc = mark(pl, st)) return rc;
     }
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sweep kernel: the whole decomposition of the batch in one persistent launch (itd_sweep.cuh)
+// ---------------------------------------------------------------------------------------------
+template <typename InT, typename CarryT, typename OutT>
+static cudaError_t sweep_launch_t(const SweepParams &p, bool bas, int *grid_cache, cudaStream_t st) {
+    constexpr size_t smem = sizeof(SweepSmem<CarryT>);
+    auto k = bas ? sweep_kernel<InT, CarryT, OutT, true> : sweep_kernel<InT, CarryT, OutT, false>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (*grid_cache == 0) {
+        int per_sm = 0, dev = 0, sms = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kSweepWarps * 32, smem);
+        if (e != cudaSuccess) return e;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        if (const char *env = getenv("PYITD_SWEEP_CTAS_PER_SM")) {       // experiment hook
+            const int v = atoi(env);
+            if (v >= 1 && v < per_sm) per_sm = v;
+        }
+        *grid_cache = per_sm * sms;
+    }
+    long long g = *grid_cache;
+    const long long items = (long long)(p.stage_last - p.stage_first + 1) * p.S;
+    if (g > items) g = items;
+    k<<<(unsigned)g, kSweepWarps * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+static int run_sweep(pyitd_plan *pl, const void *x, void *rotations, void *baselines, int32_t *n_rows,
+                     int32_t *knot_counts, int32_t *input_knots, int *sk, int32_t *status, cudaStream_t st) {
+    const int stages = pl->emax + 2;                        // the scan + extractions 0 .. emax
+    CU(cudaMemsetAsync(pl->sw_ticket, 0, (size_t)(pl->rows + 4) * sizeof(int), st));
+    CU(cudaMemsetAsync(pl->sw_done, 0, (size_t)pl->S * sizeof(int), st));
+    SweepParams sp = {};
+    sp.x = x;
+    sp.carry[0] = pl->carry[0];
+    sp.carry[1] = pl->carry[1];
+    for (int i = 0; i < 2; ++i) {
+        sp.tab[i].tau = pl->table[i].tau;
+        sp.tab[i].xk = pl->table[i].xk;
+        sp.tab[i].mask = pl->table[i].mask;
+        sp.tab[i].rcount = pl->sw_rcount[i];
+    }
+    sp.rot = rotations;
+    sp.bas = baselines;
+    sp.out_sig_stride = (long long)pl->rows * pl->n;
+    sp.kstride = pl->table[0].kstride;
+    sp.mstride = pl->table[0].mstride;
+    sp.done = pl->sw_done;
+    sp.stop_e = pl->stop_e;
+    sp.stop_kind = sk;
+    sp.n_rows = n_rows;
+    sp.knot_counts = knot_counts;
+    sp.status = status;
+    sp.input_knots = input_knots ? input_knots : pl->input_knots;
+    sp.stage_ns = nullptr;
+    sp.S = (int)pl->S;
+    sp.n = pl->n;
+    sp.spans = pl->sw_spans;
+    sp.spw = pl->sw_spw;
+    sp.rs = pl->sw_rs;
+    sp.emax = pl->emax;
+    sp.rows = pl->rows;
+    sp.min_extrema = pl->min_extrema;
+    sp.opts = pl->opts;
+    auto launch = [&](int first, int last, int ticket_slot) -> cudaError_t {
+        sp.stage_first = first;
+        sp.stage_last = last;
+        sp.ticket = pl->sw_ticket + ticket_slot;
+        const bool bas = baselines != nullptr;
+        switch (pl->dtype) {
+            case PYITD_F64: return sweep_launch_t<double, double, double>(sp, bas, &pl->sw_grid, st);
+            case PYITD_F32_MIXED: return sweep_launch_t<float, double, float>(sp, bas, &pl->sw_grid, st);
+            default: return sweep_launch_t<float, float, float>(sp, bas, &pl->sw_grid, st);
+        }
+    };
+    if (int rc = mark(pl, st)) return rc;
+    if (pl->timing || getenv("PYITD_SWEEP_PER_STAGE")) {
+        // measurement mode: one launch per stage, so that every stage can be timed (and profiled) on its own
+        for (int s = 0; s < stages; ++s) {
+            CU(launch(s - 1, s - 1, s));
+            pl->launches++;
+            if (int rc = mark(pl, st)) return rc;
+        }
+        return 0;
+    }
+    CU(launch(-1, pl->emax, 0));
+    pl->launches = 1;
+    return mark(pl, st);
 }
 
 extern "C" int pyitd_plan_set_groups(pyitd_plan *pl, int groups) {

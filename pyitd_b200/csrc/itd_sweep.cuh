@@ -1,0 +1,570 @@
+// itd_sweep.cuh -- the batched-channel path of round 2: the WHOLE decomposition of a batch in ONE launch.
+//
+// A persistent grid (as many CTAs as fit) pulls work items (stage, signal) from a ticket counter, stage-major:
+// stage -1 is the extrema-compaction pass over the raw input (ITD.py:87-98), stage e >= 0 is extraction e
+// (ITD.py:79-121 applied to X_e, plus the driver's stop test ITD.py:400-404, which IS the next level's knot detection).
+// The item (e, s) waits for (e-1, s) through a per-signal counter (release / acquire); because tickets are handed out
+// in order, the item it waits for was taken earlier by a CTA that is running, so the wait cannot deadlock, and with
+// more signals than resident CTAs it never actually spins.  There are no launch boundaries between levels: no partial
+// last wave per level, no tail of nearly empty launches once most signals have stopped, no host involvement.
+//
+// Inside an item the eight warps of the CTA do not talk to each other while they stream:
+//
+//   * warp w owns the w-th contiguous REGION of the signal (1/8 of its 128-sample spans) and walks it span by span.
+//     Samples come straight from global memory into registers (coalesced 8-byte loads, the next span's loads issued
+//     before the current span's arithmetic, an L2 prefetch a few spans further ahead); R and B go straight back with
+//     coalesced stores.  No shared-memory staging of samples, no mbarrier, no block barrier per tile.
+//   * the knots a warp finds in B (= the next level's knots) are compacted into the warp's OWN region list
+//     (tau, X) in the order found, with the running count in a register: the global rank of a knot is not needed
+//     while streaming.  The knot flags are also kept as a bit mask (segment id of a sample = knots at or before it).
+//   * the per-knot work of ITD.py:100-110 and :116 -- L_k and the slope of the segment that starts at knot k --
+//     is done ONE THREAD PER KNOT:
+//       - few knots (K + 2 <= kSweepCap): by the whole block, once per item, into a shared-memory table
+//         {X_k, L_k, s_k} indexed by global rank (three block barriers per signal-level instead of one per tile);
+//       - many knots (the first two or three levels): per warp and per span into a warp-private scratch, from the
+//         region's own list, whose two slots before and three slots after the region's knots are filled with the
+//         neighbouring regions' knots ("halo") by 40 threads at the start of the item.
+//
+// Same arithmetic, same operation order, -fmad=false: bit-identical to the reference in fp64.
+#pragma once
+
+#include <type_traits>
+
+#include "itd_kernels.cuh"
+#include "itd_stream.cuh"
+
+namespace pyitd {
+
+constexpr int kSweepWarps = 8;
+constexpr int kSweepItems = 4;
+constexpr int kSweepSpan = 32 * kSweepItems;          // samples per warp iteration
+constexpr int kSweepCap = 2048;                       // shared-memory knot table: K + 2 <= kSweepCap
+constexpr int kSweepPre = 2, kSweepPost = 3;          // halo slots of a region list
+constexpr int kSweepScratch = kSweepSpan + 8;         // warp-private scratch entries (span knots + 5)
+constexpr int kSweepPrefetch = 6;                     // L2 prefetch distance in spans
+constexpr int kSweepDoneAll = 0x3fffffff;             // done[] value of a signal that has stopped
+static_assert(kSweepWarps * kSweepScratch * 3 <= kSweepCap * 2, "warp scratches + their tau words (8-byte carry) must fit in a table array");
+
+struct SweepTable {
+    int *tau;            // [S, 8 * rs]  region r at r * rs: kSweepPre halo slots, the region's knots in order, kSweepPost halo slots
+    void *xk;            // same layout (carry type): X at the knot
+    unsigned *mask;      // [S, mstride] knot flags of the level's input, bit (t & 31) of word (t >> 5)
+    int *rcount;         // [S, 8]       knots per region
+};
+
+struct SweepParams {
+    const void *x;       // [S, N] input type
+    void *carry[2];      // [S, N] carry type: extraction e reads carry[(e - 1) & 1] (x for e == 0), writes carry[e & 1]
+    SweepTable tab[2];   // extraction e reads tab[e & 1] (written by the scan for e == 0), writes tab[(e + 1) & 1]
+    void *rot, *bas;     // [S, rows, N] output type; bas may be null
+    long long out_sig_stride;
+    long long kstride, mstride;
+    int *ticket;         // [1]  zeroed before the launch
+    int *done;           // [S]  stages completed: 1 after the scan, e + 2 after extraction e
+    int *stop_e, *stop_kind, *n_rows, *knot_counts, *status, *input_knots;
+    unsigned long long *stage_ns;   // optional [rows + 1]: CTA-nanoseconds spent per stage (index stage + 1)
+    int S, n;
+    int spans, spw, rs;  // spans of a signal, spans per warp region, slots per region list
+    int stage_first, stage_last;   // stages of this launch: -1 (scan) .. emax
+    int emax, rows, min_extrema;
+    unsigned opts;
+};
+
+template <typename CarryT>
+struct SweepSmem {
+    // few knots: {X, L, S}[global rank]; many knots: warp w's scratch at w * kSweepScratch in each array
+    CarryT X[kSweepCap], L[kSweepCap], S[kSweepCap];
+    // many knots only: tau of the scratch entries; with an 8-byte carry they fit in the part of X the warp scratches
+    // leave free, a 4-byte carry gets an array of its own (its tables are half the size anyway)
+    int tau_extra[sizeof(CarryT) == 4 ? kSweepWarps * kSweepScratch : 1];
+    __device__ __forceinline__ int *tauw() {
+        return sizeof(CarryT) == 4 ? tau_extra : reinterpret_cast<int *>(X + kSweepWarps * kSweepScratch);
+    }
+    int prefix[kSweepWarps + 1];               // knots before each region (prefix[8] = K)
+    int cnt[kSweepWarps];                      // next level's knots per region
+    CarryT endl[2], endx[2];                   // L_0, L_{K+1} (ITD.py:101-102); X_0 = in[0], X_{K+1} = in[n-1]
+    int ticket, zero_dx;
+};
+
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// data written earlier in this launch by another CTA: read through L2 (the L1 of this SM may hold a stale line)
+template <typename T>
+__device__ __forceinline__ T ld_cg(const T *p) {
+    return __ldcg(p);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one region of one signal, one stage.  XT = element type of the stage's input (the caller's input type for the scan
+// and extraction 0, the carry type afterwards).
+// ---------------------------------------------------------------------------------------------
+template <typename XT, typename CarryT, typename OutT, bool SCAN, bool BAS>
+__device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<CarryT> &sm, const XT *__restrict__ in,
+                                             const int sig, const int e, const bool dense, const bool last,
+                                             const int K, const int warp, const int lane, int &region_knots,
+                                             bool &zero_dx, bool &bad) {
+    using A = Arith<CarryT>;
+    constexpr int ITEMS = kSweepItems, SPAN = kSweepSpan;
+    const int n = p.n;
+    const int sp0 = warp * p.spw;
+    const int sp1 = min(sp0 + p.spw, p.spans);
+    region_knots = 0;
+    if (sp0 >= sp1) return;
+
+    const SweepTable &cur = p.tab[e & 1];                    // (unused by the scan)
+    const SweepTable &nxt = p.tab[(e + 1) & 1];
+    const unsigned *gmask = cur.mask + (long long)sig * p.mstride;
+    const int *ctau = cur.tau + (long long)sig * p.kstride + (long long)warp * p.rs;
+    const CarryT *cxk = reinterpret_cast<const CarryT *>(cur.xk) + (long long)sig * p.kstride + (long long)warp * p.rs;
+    unsigned *nmask = nxt.mask + (long long)sig * p.mstride;
+    int *ntau = nxt.tau + (long long)sig * p.kstride + (long long)warp * p.rs + kSweepPre;
+    CarryT *nxk = reinterpret_cast<CarryT *>(nxt.xk) + (long long)sig * p.kstride + (long long)warp * p.rs + kSweepPre;
+    const long long row = (long long)sig * p.out_sig_stride + (long long)e * n;
+    OutT *rot = SCAN ? nullptr : reinterpret_cast<OutT *>(p.rot) + row;
+    OutT *bas = (SCAN || !BAS) ? nullptr : reinterpret_cast<OutT *>(p.bas) + row;
+    CarryT *carry = SCAN ? nullptr : reinterpret_cast<CarryT *>(p.carry[e & 1]) + (long long)sig * n;
+
+    // knot records: few knots -> the block's table by global rank; many knots -> this warp's scratch
+    const CarryT *Xp = dense ? sm.X + warp * kSweepScratch : sm.X;
+    const CarryT *Lp = dense ? sm.L + warp * kSweepScratch : sm.L;
+    const CarryT *Sp = dense ? sm.S + warp * kSweepScratch : sm.S;
+    CarryT *Xw = sm.X + warp * kSweepScratch, *Lw = sm.L + warp * kSweepScratch, *Sw = sm.S + warp * kSweepScratch;
+    int *tw = sm.tauw() + warp * kSweepScratch;
+    const int gbase0 = SCAN ? 0 : sm.prefix[warp];            // global rank of the last knot before the region
+    const unsigned le_mask = 0xffffffffu >> (31 - lane);
+
+    int pos = 0;                 // knots of this region's list consumed so far
+    int npos = 0;                // next-level knots of this region found so far
+
+    // ---- first span's samples and flag words ---------------------------------------------------
+    XT xc[ITEMS], xn[ITEMS];
+    uint4 mc = make_uint4(0, 0, 0, 0), mn = make_uint4(0, 0, 0, 0);
+    {
+        const int t0 = sp0 * SPAN;
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+            const int t = t0 + r * 32 + lane;
+            xc[r] = (t < n) ? ld_cg(in + t) : (XT)0;
+        }
+        if (!SCAN) mc = ld_cg(reinterpret_cast<const uint4 *>(gmask + sp0 * ITEMS));
+    }
+    CarryT bleft = (CarryT)0;    // value left of the span (previous span's last B, or the previous region's)
+    CarryT xleft0 = (CarryT)0;   // x just before the region
+    if (sp0 > 0) xleft0 = (CarryT)ld_cg(in + sp0 * SPAN - 1);
+
+    auto span_body = [&](auto edge_tag, const int sp) {
+        constexpr bool EDGE = decltype(edge_tag)::value;
+        const int t0 = sp * SPAN;
+        // ---- the next span's loads first: they are in flight during this span's arithmetic ----
+        {
+            const int tn = t0 + SPAN;
+#pragma unroll
+            for (int r = 0; r < ITEMS; ++r) {
+                const int t = tn + r * 32 + lane;
+                xn[r] = (t < n) ? ld_cg(in + t) : (XT)0;
+            }
+            if (!SCAN && sp + 1 < p.spans) mn = ld_cg(reinterpret_cast<const uint4 *>(gmask + (sp + 1) * ITEMS));
+            const long long tp = (long long)t0 + (long long)kSweepPrefetch * SPAN + lane * (128 / (int)sizeof(XT));
+            if (lane < SPAN * (int)sizeof(XT) / 128 && tp < n) prefetch_l2(in + tp);
+        }
+        unsigned mw[ITEMS] = {mc.x, mc.y, mc.z, mc.w};
+        int wpre[ITEMS];
+        wpre[0] = 0;
+#pragma unroll
+        for (int r = 1; r < ITEMS; ++r) wpre[r] = wpre[r - 1] + __popc(mw[r - 1]);
+        const int cnt = SCAN ? 0 : wpre[ITEMS - 1] + __popc(mw[ITEMS - 1]);
+        const int tend = t0 + SPAN;                            // first sample after the span
+        const bool have_right = !EDGE || tend <= n - 1;
+        const int fright = (!SCAN && have_right) ? (int)(mn.x & 1u) : 0;
+
+        int ibase = 0;
+        if (!SCAN) {
+            if (dense) {
+                // ---- knot records of this span from the region's list: scratch[i] = list slot pos + i, i.e. the
+                // knot with global rank g0 + i, g0 = gbase0 + pos - 1; scratch[1] is the last knot before the span.
+                // L for i in [1, cnt+3], slope for i in [1, cnt+2]  (ITD.py:100-110, :116)
+                const int g0 = gbase0 + pos - 1;
+                const int m = cnt + 5;
+                __syncwarp();
+                for (int i = lane; i < m; i += 32) {
+                    tw[i] = ld_cg(ctau + pos + i);
+                    Xw[i] = ld_cg(cxk + pos + i);
+                }
+                if (lane < 2 && pos + 512 + 64 < p.rs) {
+                    prefetch_l2(ctau + pos + 512 + lane * 32);
+                    prefetch_l2(cxk + pos + 512 + lane * 16);
+                }
+                __syncwarp();
+                for (int i = 1 + lane; i <= cnt + 3; i += 32) {
+                    const int g = g0 + i;
+                    CarryT Lv = (CarryT)0;
+                    if (g <= 0) {
+                        Lv = sm.endl[0];
+                    } else if (g >= K + 1) {
+                        Lv = sm.endl[1];
+                    } else {
+                        const CarryT w = A::ratio(tw[i] - tw[i - 1], tw[i + 1] - tw[i - 1]);
+                        const CarryT d = A::sub(Xw[i + 1], Xw[i - 1]);
+                        const CarryT qq = A::add(Xw[i - 1], A::mul(w, d));
+                        Lv = A::add(A::mul((CarryT)0.5, qq), A::mul((CarryT)0.5, Xw[i]));
+                    }
+                    Lw[i] = Lv;
+                }
+                __syncwarp();
+                for (int i = 1 + lane; i <= cnt + 2; i += 32) {
+                    const int g = g0 + i;
+                    CarryT sl = (CarryT)0;
+                    if (g >= 0 && g <= K) {
+                        const CarryT den = A::sub(Xw[i + 1], Xw[i]);
+                        sl = A::div(A::sub(Lw[i + 1], Lw[i]), den);
+                        zero_dx |= (den == (CarryT)0);
+                    }
+                    Sw[i] = sl;
+                }
+                __syncwarp();
+                ibase = 1;
+            } else {
+                ibase = gbase0 + pos;
+            }
+        }
+
+        // ---- B, R for the span ------------------------------------------------------------------
+        CarryT b[ITEMS];
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+            const int t = t0 + r * 32 + lane;
+            const CarryT xv = (CarryT)xc[r];
+            if (SCAN) {
+                b[r] = xv;
+                if (!EDGE || t < n) bad |= !isfinite(xv);
+            } else {
+                const int j = ibase + wpre[r] + __popc(mw[r] & le_mask);
+                CarryT bv = A::add(Lp[j], A::mul(Sp[j], A::sub(xv, Xp[j])));      // ITD.py:115-117
+                if (EDGE && t >= n - 1) bv = (CarryT)0;                            // ITD.py:112 (and the padding lanes)
+                if (!EDGE || t < n) {
+                    const CarryT rr = A::sub(xv, bv);                              // ITD.py:119
+                    __stcs(rot + t, (OutT)(last ? A::add(rr, bv) : rr));           // ITD.py:420 on the last extraction
+                    carry[t] = bv;
+                    if (BAS) __stcs(bas + t, last ? (OutT)0 : (OutT)bv);           // ITD.py:424
+                }
+                b[r] = bv;
+            }
+        }
+        // left / right neighbours of the span
+        if (sp == sp0 && sp0 > 0) {
+            if (SCAN) {
+                bleft = xleft0;
+            } else {
+                bleft = A::add(Lp[ibase], A::mul(Sp[ibase], A::sub(xleft0, Xp[ibase])));
+            }
+        }
+        CarryT bright = (CarryT)0;
+        if (have_right && (!EDGE || tend < n - 1)) {
+            const CarryT xr = (CarryT)shfl_idx(xn[0], 0);
+            if (SCAN) {
+                bright = xr;
+            } else {
+                const int j = ibase + cnt + fright;
+                bright = A::add(Lp[j], A::mul(Sp[j], A::sub(xr, Xp[j])));
+            }
+        } else if (SCAN && have_right) {
+            bright = (CarryT)shfl_idx(xn[0], 0);                                   // x[n-1] itself (B[n-1] is 0)
+        }
+
+        // ---- extrema of B (of x for the scan): the next level's flag words and knots -------------
+        unsigned fw[ITEMS];
+        const int newc = span_extrema<EDGE, ITEMS, CarryT>(b, bleft, bright, lane, t0, n, fw);
+        if (lane < ITEMS) {
+            unsigned v = fw[0];
+#pragma unroll
+            for (int r = 1; r < ITEMS; ++r) v = (lane == r) ? fw[r] : v;
+            nmask[sp * ITEMS + lane] = v;
+        }
+        if (newc) {
+            const unsigned lt_mask = (1u << lane) - 1u;
+            int pre = npos;
+#pragma unroll
+            for (int r = 0; r < ITEMS; ++r) {
+                if ((fw[r] >> lane) & 1u) {
+                    const int rank = pre + __popc(fw[r] & lt_mask);
+                    ntau[rank] = t0 + r * 32 + lane;
+                    nxk[rank] = b[r];
+                }
+                pre += __popc(fw[r]);
+            }
+        }
+        npos += newc;
+        pos += cnt;
+        bleft = shfl_idx(b[ITEMS - 1], 31);
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) xc[r] = xn[r];
+        mc = mn;
+    };
+
+    for (int sp = sp0; sp < sp1; ++sp) {
+        // EDGE: the span holds sample 0, or sample n-1 is in it or right behind it (B[n-1] = 0, no knot after n-2)
+        if (sp == 0 || (sp + 1) * SPAN >= n - 1)
+            span_body(std::true_type{}, sp);
+        else
+            span_body(std::false_type{}, sp);
+    }
+    region_knots = npos;
+}
+
+// zero or copy one output row (the knot-stop trend row, zero tails)
+template <typename OutT, typename CarryT>
+__device__ __forceinline__ void sweep_fill_row(OutT *dst, const CarryT *src, int n, bool zero) {
+    constexpr int U = 8;
+    for (int t = threadIdx.x; t < n; t += blockDim.x * U) {
+        CarryT a[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int tt = t + u * blockDim.x;
+            a[u] = (!zero && tt < n) ? ld_cg(src + tt) : (CarryT)0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int tt = t + u * blockDim.x;
+            if (tt < n) __stcs(dst + tt, (OutT)a[u]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sweep_kernel
+// ---------------------------------------------------------------------------------------------
+template <typename InT, typename CarryT, typename OutT, bool BAS>
+__global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepParams p) {
+    using A = Arith<CarryT>;
+    extern __shared__ __align__(16) unsigned char smem_sweep_raw[];
+    SweepSmem<CarryT> &sm = *reinterpret_cast<SweepSmem<CarryT> *>(smem_sweep_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = p.n, S = p.S;
+    const long long n_items = (long long)(p.stage_last - p.stage_first + 1) * S;
+
+    for (;;) {
+        __syncthreads();                                       // everyone is done with the previous item's shared state
+        if (tid == 0) sm.ticket = atomicAdd(p.ticket, 1);
+        __syncthreads();
+        const long long t = sm.ticket;
+        if (t >= n_items) break;
+        const int e = p.stage_first + (int)(t / S);            // -1: scan
+        const int sig = (int)(t % S);
+        unsigned long long t_start = 0;
+        if (p.stage_ns && tid == 0) t_start = global_ns();
+
+        // ---- wait for the previous stage of this signal ----------------------------------------
+        if (e >= 0) {
+            if (tid == 0) {
+                while (ld_acquire(p.done + sig) < e + 1) __nanosleep(200);
+                __threadfence();
+            }
+            __syncthreads();
+        }
+        const int se = (e >= 0) ? ld_cg(p.stop_e + sig) : kStopOpen;
+        if (e > se) {
+            // the signal stopped at extraction se: rows beyond its last one are zero-filled on request
+            if (p.opts & kOptZeroTail) {
+                OutT *rot = reinterpret_cast<OutT *>(p.rot) + (long long)sig * p.out_sig_stride + (long long)e * n;
+                sweep_fill_row<OutT, CarryT>(rot, nullptr, n, true);
+                if (BAS) {
+                    OutT *bas = reinterpret_cast<OutT *>(p.bas) + (long long)sig * p.out_sig_stride + (long long)e * n;
+                    sweep_fill_row<OutT, CarryT>(bas, nullptr, n, true);
+                }
+            }
+            continue;
+        }
+
+        // ---- per-item setup: region prefix, end values ------------------------------------------
+        int K = 0;
+        bool dense = false;
+        if (e >= 0) {
+            const SweepTable &cur = p.tab[e & 1];
+            if (tid == 0) {
+                int run = 0;
+                for (int r = 0; r < kSweepWarps; ++r) {
+                    sm.prefix[r] = run;
+                    run += ld_cg(cur.rcount + (long long)sig * kSweepWarps + r);
+                }
+                sm.prefix[kSweepWarps] = run;
+                sm.zero_dx = 0;
+            }
+            if (tid == 32) {
+                // ITD.py:100-102 and the values at the two end knots
+                CarryT a0, a1, z0, z1;
+                if (e == 0) {
+                    const InT *xi = reinterpret_cast<const InT *>(p.x) + (long long)sig * n;
+                    a0 = (CarryT)xi[0]; a1 = (CarryT)xi[1]; z0 = (CarryT)xi[n - 2]; z1 = (CarryT)xi[n - 1];
+                } else {
+                    const CarryT *xi = reinterpret_cast<const CarryT *>(p.carry[(e - 1) & 1]) + (long long)sig * n;
+                    a0 = ld_cg(xi); a1 = ld_cg(xi + 1); z0 = ld_cg(xi + n - 2); z1 = ld_cg(xi + n - 1);
+                }
+                sm.endl[0] = mean2<CarryT>(a0, a1);
+                sm.endl[1] = mean2<CarryT>(z0, z1);
+                sm.endx[0] = a0;
+                sm.endx[1] = z1;
+            }
+            __syncthreads();
+            K = sm.prefix[kSweepWarps];
+            dense = (K + 2 > kSweepCap);
+            const int *ctau = cur.tau + (long long)sig * p.kstride;
+            const CarryT *cxk = reinterpret_cast<const CarryT *>(cur.xk) + (long long)sig * p.kstride;
+            // list slot of the interior knot with global rank g (1 <= g <= K)
+            auto slot_of = [&](const int g) -> long long {
+                int r = 0;
+#pragma unroll
+                for (int q = 1; q < kSweepWarps; ++q) r += (sm.prefix[q] < g) ? 1 : 0;
+                return (long long)r * p.rs + kSweepPre + (g - 1 - sm.prefix[r]);
+            };
+            if (dense) {
+                // ---- halo slots of every region list: the two knots before and the three after the region ----
+                if (tid < kSweepWarps * (kSweepPre + kSweepPost)) {
+                    const int r = tid / (kSweepPre + kSweepPost), h = tid % (kSweepPre + kSweepPost);
+                    const int c = sm.prefix[r + 1] - sm.prefix[r];
+                    const int j = (h < kSweepPre) ? h - kSweepPre : c + (h - kSweepPre);       // local index in region r
+                    const int g = 1 + sm.prefix[r] + j;
+                    int tv = 0;
+                    CarryT xv = (CarryT)0;
+                    if (g == 0) {
+                        tv = 0;
+                        xv = sm.endx[0];
+                    } else if (g == K + 1) {
+                        tv = n - 1;
+                        xv = sm.endx[1];
+                    } else if (g >= 1 && g <= K) {
+                        const long long sl = slot_of(g);
+                        tv = ld_cg(ctau + sl);
+                        xv = ld_cg(cxk + sl);
+                    }
+                    const long long dst = (long long)r * p.rs + kSweepPre + j;
+                    const_cast<int *>(ctau)[dst] = tv;
+                    const_cast<CarryT *>(cxk)[dst] = xv;
+                }
+                __syncthreads();
+            } else {
+                // ---- the block's knot table {X, L, S}[0 .. K+1], one thread per knot ----------------
+                int *taus = reinterpret_cast<int *>(sm.S);            // tau lives in S's storage until S is computed
+                for (int k = tid; k <= K + 1; k += blockDim.x) {
+                    int tv;
+                    CarryT xv;
+                    if (k == 0) {
+                        tv = 0;
+                        xv = sm.endx[0];
+                    } else if (k == K + 1) {
+                        tv = n - 1;
+                        xv = sm.endx[1];
+                    } else {
+                        const long long sl = slot_of(k);
+                        tv = ld_cg(ctau + sl);
+                        xv = ld_cg(cxk + sl);
+                    }
+                    taus[k] = tv;
+                    sm.X[k] = xv;
+                }
+                __syncthreads();
+                for (int k = tid; k <= K + 1; k += blockDim.x) {
+                    CarryT Lv;
+                    if (k == 0) {
+                        Lv = sm.endl[0];
+                    } else if (k == K + 1) {
+                        Lv = sm.endl[1];
+                    } else {
+                        const CarryT w = A::ratio(taus[k] - taus[k - 1], taus[k + 1] - taus[k - 1]);
+                        const CarryT d = A::sub(sm.X[k + 1], sm.X[k - 1]);
+                        const CarryT qq = A::add(sm.X[k - 1], A::mul(w, d));
+                        Lv = A::add(A::mul((CarryT)0.5, qq), A::mul((CarryT)0.5, sm.X[k]));
+                    }
+                    sm.L[k] = Lv;
+                }
+                __syncthreads();
+                bool zdx = false;
+                for (int k = tid; k <= K + 1; k += blockDim.x) {
+                    CarryT sl = (CarryT)0;
+                    if (k <= K) {
+                        const CarryT den = A::sub(sm.X[k + 1], sm.X[k]);
+                        sl = A::div(A::sub(sm.L[k + 1], sm.L[k]), den);
+                        zdx |= (den == (CarryT)0);
+                    }
+                    sm.S[k] = sl;                                      // overwrites tau[k] (and tau[k+1] for fp64): see the barrier below
+                }
+                if (zdx) sm.zero_dx = 1;
+                __syncthreads();
+            }
+        }
+
+        // ---- stream the regions (no block barrier inside) ----------------------------------------
+        int region_knots = 0;
+        bool zero_dx = false, bad = false;
+        const bool last = (e == p.emax);
+        if (e < 0) {
+            sweep_region<InT, CarryT, OutT, true, BAS>(p, sm, reinterpret_cast<const InT *>(p.x) + (long long)sig * n, sig, e,
+                                                       false, false, 0, warp, lane, region_knots, zero_dx, bad);
+        } else if (e == 0) {
+            sweep_region<InT, CarryT, OutT, false, BAS>(p, sm, reinterpret_cast<const InT *>(p.x) + (long long)sig * n, sig, e,
+                                                        dense, last, K, warp, lane, region_knots, zero_dx, bad);
+        } else {
+            sweep_region<CarryT, CarryT, OutT, false, BAS>(p, sm, reinterpret_cast<const CarryT *>(p.carry[(e - 1) & 1]) + (long long)sig * n,
+                                                           sig, e, dense, last, K, warp, lane, region_knots, zero_dx, bad);
+        }
+        if (lane == 0) sm.cnt[warp] = region_knots;
+        if (__any_sync(0xffffffffu, zero_dx) && lane == 0) sm.zero_dx = 1;
+        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.status + sig, kStNonFinite);
+        __syncthreads();
+
+        // ---- end of the item: region counts, stop rule, trend row ---------------------------------
+        int Kn = 0;
+#pragma unroll
+        for (int r = 0; r < kSweepWarps; ++r) Kn += sm.cnt[r];
+        const SweepTable &nxt = p.tab[(e + 1) & 1];
+        if (tid < kSweepWarps) nxt.rcount[(long long)sig * kSweepWarps + tid] = sm.cnt[tid];
+        bool stop_knots = false;
+        if (e < 0) {
+            if (tid == 0 && p.input_knots) p.input_knots[sig] = Kn;
+        } else {
+            stop_knots = (Kn < p.min_extrema);                         // ITD.py:404
+            if (tid == 0) {
+                if (sm.zero_dx) atomicOr(p.status + sig, kStZeroDx);
+                p.knot_counts[(long long)sig * p.rows + e] = Kn;       // what ITD.py:403 prints
+                if (stop_knots || last) {                              // ITD.py:404 / :418
+                    p.stop_kind[sig] = stop_knots ? kStopKnots : kStopIter;
+                    p.n_rows[sig] = e + 1;
+                    p.stop_e[sig] = e;
+                }
+            }
+            if (stop_knots) {
+                // the discarded extraction wrote R_e into row e; the reference returns baselines[e-1] there, i.e. the
+                // INPUT of this extraction (zeros when e == 0)  (ITD.py:410-411)
+                OutT *rot = reinterpret_cast<OutT *>(p.rot) + (long long)sig * p.out_sig_stride + (long long)e * n;
+                const CarryT *src = (e == 0) ? nullptr : reinterpret_cast<const CarryT *>(p.carry[(e - 1) & 1]) + (long long)sig * n;
+                sweep_fill_row<OutT, CarryT>(rot, src, n, e == 0);
+                if (BAS && (p.opts & kOptZeroTail)) {
+                    OutT *bas = reinterpret_cast<OutT *>(p.bas) + (long long)sig * p.out_sig_stride + (long long)e * n;
+                    sweep_fill_row<OutT, CarryT>(bas, nullptr, n, true);
+                }
+            }
+        }
+        __syncthreads();                                               // every thread's global writes are issued
+        if (tid == 0) {
+            __threadfence();
+            // a stopped signal lets every later stage of it through at once (they only zero-fill on request)
+            st_release(p.done + sig, (e >= 0 && (stop_knots || last)) ? kSweepDoneAll : e + 2);
+            if (p.stage_ns) atomicAdd(p.stage_ns + (e + 1), global_ns() - t_start);
+        }
+    }
+}
+
+}  // namespace pyitd

@@ -359,10 +359,10 @@ def test_resident_kernel_fp32_variants(cfg, monkeypatch):
 
 def test_default_path_by_shape():
     from pyitd_b200.itd import get_plan
-    assert get_plan(0, 4096, 65536, _capi.F64, 11, 2, 0).path[0] == "stream"
+    assert get_plan(0, 4096, 65536, _capi.F64, 11, 2, 0).path[0] == "sweep"
     assert get_plan(0, 64, 65536, _capi.F64, 11, 2, 0).path == ("resident", 4)
     assert get_plan(0, 1, 65536, _capi.F64, 11, 2, 0).path[0] == "lookback"
-    assert get_plan(0, 3515, 8192, _capi.F32_MIXED, 7, 2, 0).path[0] == "stream"
+    assert get_plan(0, 3515, 8192, _capi.F32_MIXED, 7, 2, 0).path[0] == "sweep"
     assert get_plan(0, 1, 1 << 22, _capi.F32, 11, 2, 0).path[0] == "strided"
     assert get_plan(0, 2, 1 << 22, _capi.F32, 11, 2, 0).path[0] == "strided"
     assert get_plan(0, 2, 1 << 16, _capi.F32, 11, 2, 0).path[0] == "lookback"

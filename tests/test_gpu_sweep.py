@@ -1,0 +1,181 @@
+"""GPU: the sweep kernel (itd_sweep.cuh) -- the whole decomposition of a batch in ONE persistent launch -- against
+the oracle, bit for bit, through the C ABI.  This is the kernel the headline number of bench.py comes from.
+
+Covered: lengths around the 128-sample span and the eight-region split (including lengths that are not a multiple of
+4: the kernel has no alignment requirement), plateaus / ties / monotone / knot-free stretches, dense (per-warp scratch)
+and sparse (shared-memory table) knot modes and the switch between them inside one decomposition, every stop kind,
+min_extrema, baselines, zero tails, the fp32 variants, one launch per stage vs one launch for everything, the ticket
+scheduler with fewer signals than CTAs and with more, and the full benchmark shape.
+"""
+import numpy as np
+import pytest
+import torch
+
+import pyitd_b200
+from oracle import itd_oracle as o
+from pyitd_b200 import _capi, synth
+from test_gpu_parity import _mixed_batch, check_against_oracle, check_batch_against_c_oracle, gpu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _force_sweep(monkeypatch):
+    monkeypatch.setenv("PYITD_FORCE_PATH", "sweep")
+    pyitd_b200.clear_plan_cache()
+    yield
+    pyitd_b200.clear_plan_cache()
+
+
+def test_sweep_is_the_default_for_big_batches(monkeypatch):
+    monkeypatch.delenv("PYITD_FORCE_PATH")
+    pyitd_b200.clear_plan_cache()
+    from pyitd_b200.itd import get_plan
+    assert get_plan(0, 4096, 65536, _capi.F64, 11, 2, 0).path[0] == "sweep"
+    assert get_plan(0, 3515, 8192, _capi.F32_MIXED, 7, 2, 0).path[0] == "sweep"
+    assert get_plan(0, 200, 4098, _capi.F64, 11, 2, 0).path[0] == "sweep"          # rows need no alignment
+    assert get_plan(0, 64, 65536, _capi.F64, 11, 2, 0).path[0] == "resident"
+    assert get_plan(0, 1, 65536, _capi.F64, 11, 2, 0).path[0] == "lookback"
+
+
+@pytest.mark.parametrize("n", [3, 4, 5, 31, 33, 127, 128, 129, 130, 255, 257, 1023, 1024, 1025, 1026, 1027, 2049, 4100,
+                               8191, 8193, 10007, 16384, 20001])
+def test_lengths_around_spans_and_regions(n):
+    rng = np.random.default_rng(7000 + n)
+    check_against_oracle(_mixed_batch(rng, 13, n), max_iteration=11)
+
+
+@pytest.mark.parametrize("max_iteration", [0, 1, 3, 7, 20])
+def test_iteration_cap(max_iteration):
+    rng = np.random.default_rng(7100)
+    res = check_against_oracle(_mixed_batch(rng, 12, 8192), max_iteration=max_iteration)
+    assert int(res.n_rows.max()) <= max_iteration + 2
+
+
+@pytest.mark.parametrize("min_extrema", [0, 1, 3, 10])
+def test_min_extrema(min_extrema):
+    rng = np.random.default_rng(7200)
+    check_against_oracle(_mixed_batch(rng, 6, 3000), max_iteration=11, min_extrema=min_extrema)
+
+
+def test_dense_to_sparse_switch_inside_one_decomposition():
+    """White noise has ~0.66 N knots on the first level (per-warp scratch mode) and drops below the 2046-knot table
+    within two or three levels (block table mode); a slow sine stays sparse from the start; a zig-zag has a knot on
+    EVERY interior sample (128 knots per span, the scratch capacity)."""
+    rng = np.random.default_rng(7300)
+    n = 40000
+    x = rng.standard_normal((6, n))
+    x[1] = np.sin(np.arange(n) * 0.001)
+    x[2] = np.where(np.arange(n) % 2 == 0, 1.0, -1.0) * (1 + 0.1 * rng.random(n))
+    x[3] = np.cumsum(x[3])
+    x[4, 5000:30000] = np.linspace(0, 3, 25000)            # one region sees no knot at all
+    x[5] = np.round(x[5] * 3) / 3 + 1e-9 * np.arange(n)
+    res = check_against_oracle(x, max_iteration=11)
+    assert int(res.input_knots[2]) == n - 2 and int(res.input_knots[0]) > 2046 > int(res.input_knots[1])
+
+
+def test_zero_tail_and_baselines():
+    rng = np.random.default_rng(7400)
+    x = _mixed_batch(rng, 8, 5000)
+    res = pyitd_b200.decompose(gpu(x), max_iteration=11, return_baselines=True, zero_tail=True)
+    ref = check_against_oracle(x, max_iteration=11)
+    for s in range(x.shape[0]):
+        nr = int(res.n_rows[s])
+        assert torch.equal(res.rotations[s, :nr], ref.rotations[s, :nr])
+        assert float(res.rotations[s, nr:].abs().max() if nr < res.rotations.shape[1] else 0) == 0
+        nb = res.baselines_of(s).shape[0]
+        assert torch.equal(res.baselines_of(s), ref.baselines_of(s))
+        assert float(res.baselines[s, nb:].abs().max() if nb < res.baselines.shape[1] else 0) == 0
+    # without the baselines (bench.py's options): same rows
+    r0 = pyitd_b200.decompose(gpu(x), max_iteration=11)
+    for s in range(x.shape[0]):
+        assert torch.equal(r0.rows_of(s), ref.rows_of(s))
+
+
+def test_fp32_variants():
+    rng = np.random.default_rng(7500)
+    for n in (130, 4096, 9001):
+        x32 = _mixed_batch(rng, 6, n).astype(np.float32)
+        for dt in ("f32_mixed", "f32"):
+            res = pyitd_b200.decompose(gpu(x32), max_iteration=7, dtype=dt, return_baselines=True)
+            for s in range(6):
+                src = x32[s].astype(np.float64) if dt == "f32_mixed" else x32[s]
+                try:
+                    want = o.c_decompose(src, 7)
+                except o.OracleError:
+                    assert int(res.status[s]) != 0
+                    continue
+                assert int(res.status[s]) == 0
+                assert res.rows_of(s).cpu().numpy().tobytes() == want.rotations.astype(np.float32).tobytes(), (dt, n, s)
+                assert res.baselines_of(s).cpu().numpy().tobytes() == want.baselines.astype(np.float32).tobytes(), (dt, n, s)
+
+
+def test_error_statuses():
+    x = np.random.default_rng(7600).standard_normal((5, 3000))
+    x[1] = 3.0                                             # constant: zero delta-X (ITD.py:116 raises ZeroDivisionError)
+    x[3, 100] = np.nan
+    res = pyitd_b200.decompose(gpu(x))
+    st = res.status.cpu().tolist()
+    assert st[0] == 0 and st[2] == 0 and st[4] == 0
+    assert st[1] & _capi.ST_ZERO_DX and st[3] & _capi.ST_NONFINITE
+
+
+@pytest.mark.parametrize("S", [1, 3, 700])
+def test_ticket_scheduler_with_few_and_many_signals(S):
+    """S = 1: every item waits for the previous stage of the same signal; S = 700: more items per stage than resident
+    CTAs (592), stopped signals skipped, ragged stops."""
+    x = synth.eeg_like(S, 6000, seed=50 + S).numpy()
+    x[0] = np.arange(6000.0)                               # stops at once
+    res = pyitd_b200.decompose(gpu(x), max_iteration=11, return_baselines=True)
+    torch.cuda.synchronize()
+    check_batch_against_c_oracle(res, x, 11)
+
+
+def test_one_launch_equals_one_launch_per_stage(monkeypatch):
+    x = synth.eeg_like(40, 16384, seed=77, device="cuda")
+    a = pyitd_b200.decompose(x, max_iteration=11, return_baselines=True, zero_tail=True)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("PYITD_SWEEP_PER_STAGE", "1")
+    b = pyitd_b200.decompose(x, max_iteration=11, return_baselines=True, zero_tail=True)
+    torch.cuda.synchronize()
+    assert torch.equal(a.rotations, b.rotations) and torch.equal(a.baselines, b.baselines)
+    assert torch.equal(a.n_rows, b.n_rows) and torch.equal(a.knot_counts, b.knot_counts)
+    check_batch_against_c_oracle(a, x.cpu().numpy(), 11)
+
+
+def test_benchmark_shape_256_channels_bit_exact():
+    """bench.py's workload shape and generator: 256 channels x 65 536 samples, EVERY channel bit for bit -- rotations,
+    baselines, per-level knot counts, stop kind (ITD.py:351-433) -- with and without the baselines."""
+    from pyitd_b200.itd import get_plan
+    assert get_plan(0, 256, 65536, _capi.F64, 11, 2, _capi.OPT_BASELINES).path[0] == "sweep"
+    xg = synth.eeg_like(256, 65536, seed=1234, device="cuda")
+    res = pyitd_b200.decompose(xg, max_iteration=11, return_baselines=True)
+    torch.cuda.synchronize()
+    check_batch_against_c_oracle(res, xg.cpu().numpy(), 11)
+    assert len(set(res.n_rows.cpu().tolist())) > 2
+    res0 = pyitd_b200.decompose(xg, max_iteration=11)
+    torch.cuda.synchronize()
+    check_batch_against_c_oracle(res0, xg.cpu().numpy(), 11, baselines=False)
+
+
+def test_repeated_calls_and_side_stream():
+    """A plan is reused across calls (ticket / done counters are reset per call) and across streams (the library orders
+    a call after the plan's previous call on another stream)."""
+    x = synth.eeg_like(170, 4096, seed=9, device="cuda")
+    ref = pyitd_b200.decompose(x, max_iteration=11)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    outs = []
+    for i in range(4):
+        if i % 2:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                outs.append(pyitd_b200.decompose(x, max_iteration=11))
+        else:
+            outs.append(pyitd_b200.decompose(x, max_iteration=11))
+    torch.cuda.synchronize()
+    for r in outs:
+        assert torch.equal(r.n_rows, ref.n_rows)
+        for s in (0, 85, 169):
+            assert torch.equal(r.rows_of(s), ref.rows_of(s))
+    check_batch_against_c_oracle(ref, x.cpu().numpy(), 11, baselines=False)
