@@ -951,9 +951,9 @@ static int pyitd_decompose_device_impl(pyitd_plan *pl, const void *x, void *rota
 // ---------------------------------------------------------------------------------------------
 template <typename InT, typename CarryT, typename OutT>
 static cudaError_t sweep_launch_t(const SweepParams &p, bool bas, int *grid_cache, cudaStream_t st) {
-    constexpr size_t smem = sizeof(SweepSmem<CarryT>);
+    constexpr size_t smem = 0;                            // the kernel's shared memory is static
     auto k = bas ? sweep_kernel<InT, CarryT, OutT, true> : sweep_kernel<InT, CarryT, OutT, false>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     if (*grid_cache == 0) {
         int per_sm = 0, dev = 0, sms = 0;

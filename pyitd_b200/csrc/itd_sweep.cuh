@@ -38,10 +38,11 @@ namespace pyitd {
 constexpr int kSweepWarps = 8;
 constexpr int kSweepItems = 4;
 constexpr int kSweepSpan = 32 * kSweepItems;          // samples per warp iteration
-constexpr int kSweepCap = 2048;                       // shared-memory knot table: K + 2 <= kSweepCap
+constexpr int kSweepCap = 2000;                       // shared-memory knot table: K + 2 <= kSweepCap (static shared memory: 48 KB)
 constexpr int kSweepPre = 2, kSweepPost = 3;          // halo slots of a region list
 constexpr int kSweepScratch = kSweepSpan + 8;         // warp-private scratch entries (span knots + 5)
-constexpr int kSweepPrefetch = 6;                     // L2 prefetch distance in spans
+constexpr int kSweepPrefetch = 3;                     // L2 prefetch distance in spans
+enum { kPtrIn = 0, kPtrRot, kPtrBas, kPtrCarry, kPtrGmask, kPtrNmask, kPtrCtau, kPtrCxk, kPtrNtau, kPtrNxk, kSweepPtrs };
 constexpr int kSweepDoneAll = 0x3fffffff;             // done[] value of a signal that has stopped
 static_assert(kSweepWarps * kSweepScratch * 3 <= kSweepCap * 2, "warp scratches + their tau words (8-byte carry) must fit in a table array");
 
@@ -83,6 +84,9 @@ struct SweepSmem {
     int prefix[kSweepWarps + 1];               // knots before each region (prefix[8] = K)
     int cnt[kSweepWarps];                      // next level's knots per region
     CarryT endl[2], endx[2];                   // L_0, L_{K+1} (ITD.py:101-102); X_0 = in[0], X_{K+1} = in[n-1]
+    // the item's base pointers (per signal / per row), computed once per item by one thread: the span loop adds a
+    // sample or word index to them instead of re-deriving sig * stride + e * n every span
+    void *ptr[kSweepPtrs];
     int ticket, zero_dx;
 };
 
@@ -111,12 +115,17 @@ __device__ __forceinline__ T ld_cg(const T *p) {
 // ---------------------------------------------------------------------------------------------
 // one region of one signal, one stage.  XT = element type of the stage's input (the caller's input type for the scan
 // and extraction 0, the carry type afterwards).
+//
+// The span body exists in three flavours per stage kind, chosen per span with warp-uniform branches:
+//   <EDGE, 2>   the spans that hold sample 0 or come within one span of sample n-1: every bound is checked, knot mode
+//               taken from the runtime flag;
+//   <false, 0>  few knots: records from the block's table;      <false, 1>  many knots: records built per span.
+// Non-EDGE spans are followed by a complete span, so their loads, flag words and neighbours need no checks.
 // ---------------------------------------------------------------------------------------------
 template <typename XT, typename CarryT, typename OutT, bool SCAN, bool BAS>
-__device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<CarryT> &sm, const XT *__restrict__ in,
-                                             const int sig, const int e, const bool dense, const bool last,
-                                             const int K, const int warp, const int lane, int &region_knots,
-                                             bool &zero_dx, bool &bad) {
+__device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<CarryT> &sm, const bool dense,
+                                             const bool last, const int K, const int warp, const int lane,
+                                             int &region_knots, bool &zero_dx, bool &bad) {
     using A = Arith<CarryT>;
     constexpr int ITEMS = kSweepItems, SPAN = kSweepSpan;
     const int n = p.n;
@@ -125,164 +134,182 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
     region_knots = 0;
     if (sp0 >= sp1) return;
 
-    const SweepTable &cur = p.tab[e & 1];                    // (unused by the scan)
-    const SweepTable &nxt = p.tab[(e + 1) & 1];
-    const unsigned *gmask = cur.mask + (long long)sig * p.mstride;
-    const int *ctau = cur.tau + (long long)sig * p.kstride + (long long)warp * p.rs;
-    const CarryT *cxk = reinterpret_cast<const CarryT *>(cur.xk) + (long long)sig * p.kstride + (long long)warp * p.rs;
-    unsigned *nmask = nxt.mask + (long long)sig * p.mstride;
-    int *ntau = nxt.tau + (long long)sig * p.kstride + (long long)warp * p.rs + kSweepPre;
-    CarryT *nxk = reinterpret_cast<CarryT *>(nxt.xk) + (long long)sig * p.kstride + (long long)warp * p.rs + kSweepPre;
-    const long long row = (long long)sig * p.out_sig_stride + (long long)e * n;
-    OutT *rot = SCAN ? nullptr : reinterpret_cast<OutT *>(p.rot) + row;
-    OutT *bas = (SCAN || !BAS) ? nullptr : reinterpret_cast<OutT *>(p.bas) + row;
-    CarryT *carry = SCAN ? nullptr : reinterpret_cast<CarryT *>(p.carry[e & 1]) + (long long)sig * n;
+    // item base pointers come from shared memory where they are used (no registers held across the span loop)
+    auto in_p = [&]() { return reinterpret_cast<const XT *>(sm.ptr[kPtrIn]); };
+    auto rot_p = [&]() { return reinterpret_cast<OutT *>(sm.ptr[kPtrRot]); };
+    auto bas_p = [&]() { return reinterpret_cast<OutT *>(sm.ptr[kPtrBas]); };
+    auto carry_p = [&]() { return reinterpret_cast<CarryT *>(sm.ptr[kPtrCarry]); };
+    auto gmask_p = [&]() { return reinterpret_cast<const unsigned *>(sm.ptr[kPtrGmask]); };
+    auto nmask_p = [&]() { return reinterpret_cast<unsigned *>(sm.ptr[kPtrNmask]); };
+    const int roff = warp * p.rs;                             // this region's list inside the signal's knot arrays
 
-    // knot records: few knots -> the block's table by global rank; many knots -> this warp's scratch
-    const CarryT *Xp = dense ? sm.X + warp * kSweepScratch : sm.X;
-    const CarryT *Lp = dense ? sm.L + warp * kSweepScratch : sm.L;
-    const CarryT *Sp = dense ? sm.S + warp * kSweepScratch : sm.S;
-    CarryT *Xw = sm.X + warp * kSweepScratch, *Lw = sm.L + warp * kSweepScratch, *Sw = sm.S + warp * kSweepScratch;
-    int *tw = sm.tauw() + warp * kSweepScratch;
+    const int wsc = warp * kSweepScratch;                     // this warp's scratch inside the table arrays
+    int *tw = sm.tauw() + wsc;
     const int gbase0 = SCAN ? 0 : sm.prefix[warp];            // global rank of the last knot before the region
     const unsigned le_mask = 0xffffffffu >> (31 - lane);
 
     int pos = 0;                 // knots of this region's list consumed so far
     int npos = 0;                // next-level knots of this region found so far
+    CarryT bleft = (CarryT)0;    // value left of the span (previous span's last B, or the previous region's)
 
     // ---- first span's samples and flag words ---------------------------------------------------
-    XT xc[ITEMS], xn[ITEMS];
-    uint4 mc = make_uint4(0, 0, 0, 0), mn = make_uint4(0, 0, 0, 0);
-    {
-        const int t0 = sp0 * SPAN;
+    XT xc[ITEMS];
+    uint4 mc = make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int r = 0; r < ITEMS; ++r) {
-            const int t = t0 + r * 32 + lane;
-            xc[r] = (t < n) ? ld_cg(in + t) : (XT)0;
-        }
-        if (!SCAN) mc = ld_cg(reinterpret_cast<const uint4 *>(gmask + sp0 * ITEMS));
+    for (int r = 0; r < ITEMS; ++r) {
+        const int t = sp0 * SPAN + r * 32 + lane;
+        xc[r] = (t < n) ? ld_cg(in_p() + t) : (XT)0;
     }
-    CarryT bleft = (CarryT)0;    // value left of the span (previous span's last B, or the previous region's)
-    CarryT xleft0 = (CarryT)0;   // x just before the region
-    if (sp0 > 0) xleft0 = (CarryT)ld_cg(in + sp0 * SPAN - 1);
+    if (!SCAN) mc = ld_cg(reinterpret_cast<const uint4 *>(gmask_p() + sp0 * ITEMS));
 
-    auto span_body = [&](auto edge_tag, const int sp) {
-        constexpr bool EDGE = decltype(edge_tag)::value;
-        const int t0 = sp * SPAN;
-        // ---- the next span's loads first: they are in flight during this span's arithmetic ----
-        {
-            const int tn = t0 + SPAN;
-#pragma unroll
-            for (int r = 0; r < ITEMS; ++r) {
-                const int t = tn + r * 32 + lane;
-                xn[r] = (t < n) ? ld_cg(in + t) : (XT)0;
-            }
-            if (!SCAN && sp + 1 < p.spans) mn = ld_cg(reinterpret_cast<const uint4 *>(gmask + (sp + 1) * ITEMS));
-            const long long tp = (long long)t0 + (long long)kSweepPrefetch * SPAN + lane * (128 / (int)sizeof(XT));
-            if (lane < SPAN * (int)sizeof(XT) / 128 && tp < n) prefetch_l2(in + tp);
+    // warp-private knot records of one span (many knots): scratch[i] = region list slot pos + i = the knot with global
+    // rank g0 + i, g0 = gbase0 + pos - 1; scratch[1] is the last knot before the span.  L for i in [1, cnt+3], slope for
+    // i in [1, cnt+2]  (ITD.py:100-110, :116)
+    auto build_scratch = [&](const int cnt) {
+        const int *ctau = reinterpret_cast<const int *>(sm.ptr[kPtrCtau]) + roff + pos;
+        const CarryT *cxk = reinterpret_cast<const CarryT *>(sm.ptr[kPtrCxk]) + roff + pos;
+        const int g0 = gbase0 + pos - 1;
+        const int m = cnt + 5;
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) {
+            tw[i] = ld_cg(ctau + i);
+            sm.X[wsc + i] = ld_cg(cxk + i);
         }
-        unsigned mw[ITEMS] = {mc.x, mc.y, mc.z, mc.w};
+        if (lane < 2 && pos + 512 + 64 < p.rs) {
+            prefetch_l2(ctau + 512 + lane * 32);
+            prefetch_l2(cxk + 512 + lane * 16);
+        }
+        __syncwarp();
+        // the end knots 0 and K+1 (and the unused ranks beyond them) are rare: one warp-uniform test per span
+        const bool clip = (g0 + 1 <= 0) || (g0 + cnt + 3 >= K + 1);
+        for (int i = 1 + lane; i <= cnt + 3; i += 32) {
+            const int g = g0 + i;
+            CarryT Lv;
+            if (clip && g <= 0) {
+                Lv = sm.endl[0];
+            } else if (clip && g >= K + 1) {
+                Lv = sm.endl[1];
+            } else {
+                const int tl = tw[i - 1];
+                const CarryT w = A::ratio(tw[i] - tl, tw[i + 1] - tl);
+                const CarryT xl = sm.X[wsc + i - 1];
+                const CarryT d = A::sub(sm.X[wsc + i + 1], xl);
+                const CarryT qq = A::add(xl, A::mul(w, d));
+                Lv = A::add(A::mul((CarryT)0.5, qq), A::mul((CarryT)0.5, sm.X[wsc + i]));
+            }
+            sm.L[wsc + i] = Lv;
+        }
+        __syncwarp();
+        for (int i = 1 + lane; i <= cnt + 2; i += 32) {
+            const int g = g0 + i;
+            CarryT sl = (CarryT)0;
+            if (!clip || (g >= 0 && g <= K)) {
+                const CarryT den = A::sub(sm.X[wsc + i + 1], sm.X[wsc + i]);
+                sl = A::div(A::sub(sm.L[wsc + i + 1], sm.L[wsc + i]), den);
+                zero_dx |= (den == (CarryT)0);
+            }
+            sm.S[wsc + i] = sl;
+        }
+        __syncwarp();
+    };
+
+    auto span_body = [&](auto edge_tag, auto mode_tag, const int sp) {
+        constexpr bool EDGE = decltype(edge_tag)::value;
+        constexpr int MODE = decltype(mode_tag)::value;
+        const bool is_dense = (MODE == 2) ? dense : (MODE == 1);
+        const int t0 = sp * SPAN;
+        const int tend = t0 + SPAN;                            // first sample after the span
+        const bool have_right = !EDGE || tend <= n - 1;
+        // ---- early loads: the span's right neighbour (one broadcast load) and the next span's flag words ----
+        XT xr = (XT)0;
+        uint4 mn = make_uint4(0, 0, 0, 0);
+        if (have_right) xr = ld_cg(in_p() + tend);
+        if (!SCAN && (!EDGE || sp + 1 < p.spans)) mn = ld_cg(reinterpret_cast<const uint4 *>(gmask_p() + (sp + 1) * ITEMS));
+        if (sp + kSweepPrefetch < sp1 && lane < SPAN * (int)sizeof(XT) / 128)
+            prefetch_l2(in_p() + t0 + kSweepPrefetch * SPAN + lane * (128 / (int)sizeof(XT)));
+
+        const unsigned mw[ITEMS] = {mc.x, mc.y, mc.z, mc.w};
         int wpre[ITEMS];
         wpre[0] = 0;
 #pragma unroll
         for (int r = 1; r < ITEMS; ++r) wpre[r] = wpre[r - 1] + __popc(mw[r - 1]);
         const int cnt = SCAN ? 0 : wpre[ITEMS - 1] + __popc(mw[ITEMS - 1]);
-        const int tend = t0 + SPAN;                            // first sample after the span
-        const bool have_right = !EDGE || tend <= n - 1;
         const int fright = (!SCAN && have_right) ? (int)(mn.x & 1u) : 0;
 
-        int ibase = 0;
+        int ib = 0;                                            // index of the record of the last knot before the span
         if (!SCAN) {
-            if (dense) {
-                // ---- knot records of this span from the region's list: scratch[i] = list slot pos + i, i.e. the
-                // knot with global rank g0 + i, g0 = gbase0 + pos - 1; scratch[1] is the last knot before the span.
-                // L for i in [1, cnt+3], slope for i in [1, cnt+2]  (ITD.py:100-110, :116)
-                const int g0 = gbase0 + pos - 1;
-                const int m = cnt + 5;
-                __syncwarp();
-                for (int i = lane; i < m; i += 32) {
-                    tw[i] = ld_cg(ctau + pos + i);
-                    Xw[i] = ld_cg(cxk + pos + i);
-                }
-                if (lane < 2 && pos + 512 + 64 < p.rs) {
-                    prefetch_l2(ctau + pos + 512 + lane * 32);
-                    prefetch_l2(cxk + pos + 512 + lane * 16);
-                }
-                __syncwarp();
-                for (int i = 1 + lane; i <= cnt + 3; i += 32) {
-                    const int g = g0 + i;
-                    CarryT Lv = (CarryT)0;
-                    if (g <= 0) {
-                        Lv = sm.endl[0];
-                    } else if (g >= K + 1) {
-                        Lv = sm.endl[1];
-                    } else {
-                        const CarryT w = A::ratio(tw[i] - tw[i - 1], tw[i + 1] - tw[i - 1]);
-                        const CarryT d = A::sub(Xw[i + 1], Xw[i - 1]);
-                        const CarryT qq = A::add(Xw[i - 1], A::mul(w, d));
-                        Lv = A::add(A::mul((CarryT)0.5, qq), A::mul((CarryT)0.5, Xw[i]));
-                    }
-                    Lw[i] = Lv;
-                }
-                __syncwarp();
-                for (int i = 1 + lane; i <= cnt + 2; i += 32) {
-                    const int g = g0 + i;
-                    CarryT sl = (CarryT)0;
-                    if (g >= 0 && g <= K) {
-                        const CarryT den = A::sub(Xw[i + 1], Xw[i]);
-                        sl = A::div(A::sub(Lw[i + 1], Lw[i]), den);
-                        zero_dx |= (den == (CarryT)0);
-                    }
-                    Sw[i] = sl;
-                }
-                __syncwarp();
-                ibase = 1;
+            if (is_dense) {
+                build_scratch(cnt);
+                ib = wsc + 1;
             } else {
-                ibase = gbase0 + pos;
+                ib = gbase0 + pos;
             }
         }
 
         // ---- B, R for the span ------------------------------------------------------------------
         CarryT b[ITEMS];
+        if (SCAN) {
 #pragma unroll
-        for (int r = 0; r < ITEMS; ++r) {
-            const int t = t0 + r * 32 + lane;
-            const CarryT xv = (CarryT)xc[r];
-            if (SCAN) {
-                b[r] = xv;
-                if (!EDGE || t < n) bad |= !isfinite(xv);
-            } else {
-                const int j = ibase + wpre[r] + __popc(mw[r] & le_mask);
-                CarryT bv = A::add(Lp[j], A::mul(Sp[j], A::sub(xv, Xp[j])));      // ITD.py:115-117
-                if (EDGE && t >= n - 1) bv = (CarryT)0;                            // ITD.py:112 (and the padding lanes)
-                if (!EDGE || t < n) {
-                    const CarryT rr = A::sub(xv, bv);                              // ITD.py:119
-                    __stcs(rot + t, (OutT)(last ? A::add(rr, bv) : rr));           // ITD.py:420 on the last extraction
-                    carry[t] = bv;
-                    if (BAS) __stcs(bas + t, last ? (OutT)0 : (OutT)bv);           // ITD.py:424
+            for (int r = 0; r < ITEMS; ++r) {
+                b[r] = (CarryT)xc[r];
+                if (!EDGE || t0 + r * 32 + lane < n) bad |= !isfinite(b[r]);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < ITEMS; ++r) {
+                const int j = ib + wpre[r] + __popc(mw[r] & le_mask);
+                const CarryT xv = (CarryT)xc[r];
+                b[r] = A::add(sm.L[j], A::mul(sm.S[j], A::sub(xv, sm.X[j])));     // ITD.py:115-117
+                if (EDGE && t0 + r * 32 + lane >= n - 1) b[r] = (CarryT)0;        // ITD.py:112 (and the padding lanes)
+            }
+            OutT *rot = rot_p() + t0 + lane;
+            CarryT *carry = carry_p() + t0 + lane;
+            OutT *bas = BAS ? bas_p() + t0 + lane : nullptr;
+            if (!last) {
+#pragma unroll
+                for (int r = 0; r < ITEMS; ++r) {
+                    if (!EDGE || t0 + r * 32 + lane < n) {
+                        __stcs(rot + r * 32, (OutT)A::sub((CarryT)xc[r], b[r]));             // ITD.py:119
+                        __stwb(carry + r * 32, b[r]);
+                        if (BAS) __stcs(bas + r * 32, (OutT)b[r]);
+                    }
                 }
-                b[r] = bv;
+            } else {
+#pragma unroll
+                for (int r = 0; r < ITEMS; ++r) {
+                    if (!EDGE || t0 + r * 32 + lane < n) {
+                        const CarryT rr = A::sub((CarryT)xc[r], b[r]);
+                        __stcs(rot + r * 32, (OutT)A::add(rr, b[r]));                        // ITD.py:420
+                        __stwb(carry + r * 32, b[r]);
+                        if (BAS) __stcs(bas + r * 32, (OutT)0);                              // ITD.py:424
+                    }
+                }
             }
         }
-        // left / right neighbours of the span
+        // left neighbour of the region's first span
         if (sp == sp0 && sp0 > 0) {
-            if (SCAN) {
-                bleft = xleft0;
-            } else {
-                bleft = A::add(Lp[ibase], A::mul(Sp[ibase], A::sub(xleft0, Xp[ibase])));
+            const CarryT xl = (CarryT)ld_cg(in_p() + t0 - 1);
+            bleft = SCAN ? xl : A::add(sm.L[ib], A::mul(sm.S[ib], A::sub(xl, sm.X[ib])));
+        }
+        // ---- the next span's samples: in flight during the extrema code below -------------------------
+        {
+            const XT *nx = in_p() + tend + lane;
+#pragma unroll
+            for (int r = 0; r < ITEMS; ++r) {
+                if (EDGE)
+                    xc[r] = (tend + r * 32 + lane < n) ? ld_cg(nx + r * 32) : (XT)0;
+                else
+                    xc[r] = ld_cg(nx + r * 32);
             }
         }
         CarryT bright = (CarryT)0;
-        if (have_right && (!EDGE || tend < n - 1)) {
-            const CarryT xr = (CarryT)shfl_idx(xn[0], 0);
+        if (have_right) {
             if (SCAN) {
-                bright = xr;
-            } else {
-                const int j = ibase + cnt + fright;
-                bright = A::add(Lp[j], A::mul(Sp[j], A::sub(xr, Xp[j])));
+                bright = (CarryT)xr;
+            } else if (!EDGE || tend < n - 1) {                                  // B[n-1] is 0 (ITD.py:112)
+                const int j = ib + cnt + fright;
+                bright = A::add(sm.L[j], A::mul(sm.S[j], A::sub((CarryT)xr, sm.X[j])));
             }
-        } else if (SCAN && have_right) {
-            bright = (CarryT)shfl_idx(xn[0], 0);                                   // x[n-1] itself (B[n-1] is 0)
         }
 
         // ---- extrema of B (of x for the scan): the next level's flag words and knots -------------
@@ -292,17 +319,19 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
             unsigned v = fw[0];
 #pragma unroll
             for (int r = 1; r < ITEMS; ++r) v = (lane == r) ? fw[r] : v;
-            nmask[sp * ITEMS + lane] = v;
+            __stwb(nmask_p() + sp * ITEMS + lane, v);
         }
         if (newc) {
-            const unsigned lt_mask = (1u << lane) - 1u;
-            int pre = npos;
+            int *ntau = reinterpret_cast<int *>(sm.ptr[kPtrNtau]) + roff + kSweepPre + npos;
+            CarryT *nxk = reinterpret_cast<CarryT *>(sm.ptr[kPtrNxk]) + roff + kSweepPre + npos;
+            const unsigned lt_mask = le_mask >> 1;
+            int pre = 0;
 #pragma unroll
             for (int r = 0; r < ITEMS; ++r) {
                 if ((fw[r] >> lane) & 1u) {
                     const int rank = pre + __popc(fw[r] & lt_mask);
-                    ntau[rank] = t0 + r * 32 + lane;
-                    nxk[rank] = b[r];
+                    __stwb(ntau + rank, t0 + r * 32 + lane);
+                    __stwb(nxk + rank, b[r]);
                 }
                 pre += __popc(fw[r]);
             }
@@ -310,17 +339,25 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
         npos += newc;
         pos += cnt;
         bleft = shfl_idx(b[ITEMS - 1], 31);
-#pragma unroll
-        for (int r = 0; r < ITEMS; ++r) xc[r] = xn[r];
         mc = mn;
     };
 
-    for (int sp = sp0; sp < sp1; ++sp) {
-        // EDGE: the span holds sample 0, or sample n-1 is in it or right behind it (B[n-1] = 0, no knot after n-2)
-        if (sp == 0 || (sp + 1) * SPAN >= n - 1)
-            span_body(std::true_type{}, sp);
-        else
-            span_body(std::false_type{}, sp);
+    // EDGE: the span holds sample 0, or it is not followed by a complete span (the last two spans of the signal)
+    const int fast_end = min(sp1, n / SPAN - 1);
+    int sp = sp0;
+    while (sp < sp1) {
+        if (sp == 0 || sp >= fast_end) {
+            span_body(std::true_type{}, std::integral_constant<int, 2>{}, sp);
+            ++sp;
+            continue;
+        }
+        if (SCAN || !dense) {
+#pragma unroll 1
+            for (; sp < fast_end; ++sp) span_body(std::false_type{}, std::integral_constant<int, 0>{}, sp);
+        } else {
+#pragma unroll 1
+            for (; sp < fast_end; ++sp) span_body(std::false_type{}, std::integral_constant<int, 1>{}, sp);
+        }
     }
     region_knots = npos;
 }
@@ -350,8 +387,7 @@ __device__ __forceinline__ void sweep_fill_row(OutT *dst, const CarryT *src, int
 template <typename InT, typename CarryT, typename OutT, bool BAS>
 __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepParams p) {
     using A = Arith<CarryT>;
-    extern __shared__ __align__(16) unsigned char smem_sweep_raw[];
-    SweepSmem<CarryT> &sm = *reinterpret_cast<SweepSmem<CarryT> *>(smem_sweep_raw);
+    __shared__ SweepSmem<CarryT> sm;        // static: every shared-memory access is a compile-time offset
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = p.n, S = p.S;
     const long long n_items = (long long)(p.stage_last - p.stage_first + 1) * S;
@@ -389,9 +425,26 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
             continue;
         }
 
-        // ---- per-item setup: region prefix, end values ------------------------------------------
+        // ---- per-item setup: base pointers, region prefix, end values ------------------------------
+        if (tid == 64) {
+            const long long koff = (long long)sig * p.kstride, moff = (long long)sig * p.mstride;
+            const long long row = (long long)sig * p.out_sig_stride + (long long)e * n;
+            const SweepTable &ct = p.tab[e & 1], &nt = p.tab[(e + 1) & 1];
+            sm.ptr[kPtrIn] = (e <= 0) ? (void *)(reinterpret_cast<const InT *>(p.x) + (long long)sig * n)
+                                      : (void *)(reinterpret_cast<CarryT *>(p.carry[(e - 1) & 1]) + (long long)sig * n);
+            sm.ptr[kPtrRot] = reinterpret_cast<OutT *>(p.rot) + row;
+            sm.ptr[kPtrBas] = BAS ? reinterpret_cast<OutT *>(p.bas) + row : nullptr;
+            sm.ptr[kPtrCarry] = reinterpret_cast<CarryT *>(p.carry[e & 1]) + (long long)sig * n;
+            sm.ptr[kPtrGmask] = ct.mask + moff;
+            sm.ptr[kPtrNmask] = nt.mask + moff;
+            sm.ptr[kPtrCtau] = ct.tau + koff;
+            sm.ptr[kPtrCxk] = reinterpret_cast<CarryT *>(ct.xk) + koff;
+            sm.ptr[kPtrNtau] = nt.tau + koff;
+            sm.ptr[kPtrNxk] = reinterpret_cast<CarryT *>(nt.xk) + koff;
+        }
         int K = 0;
         bool dense = false;
+        if (e < 0) __syncthreads();
         if (e >= 0) {
             const SweepTable &cur = p.tab[e & 1];
             if (tid == 0) {
@@ -511,14 +564,11 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
         bool zero_dx = false, bad = false;
         const bool last = (e == p.emax);
         if (e < 0) {
-            sweep_region<InT, CarryT, OutT, true, BAS>(p, sm, reinterpret_cast<const InT *>(p.x) + (long long)sig * n, sig, e,
-                                                       false, false, 0, warp, lane, region_knots, zero_dx, bad);
-        } else if (e == 0) {
-            sweep_region<InT, CarryT, OutT, false, BAS>(p, sm, reinterpret_cast<const InT *>(p.x) + (long long)sig * n, sig, e,
-                                                        dense, last, K, warp, lane, region_knots, zero_dx, bad);
+            sweep_region<InT, CarryT, OutT, true, BAS>(p, sm, false, false, 0, warp, lane, region_knots, zero_dx, bad);
+        } else if (std::is_same<InT, CarryT>::value || e > 0) {
+            sweep_region<CarryT, CarryT, OutT, false, BAS>(p, sm, dense, last, K, warp, lane, region_knots, zero_dx, bad);
         } else {
-            sweep_region<CarryT, CarryT, OutT, false, BAS>(p, sm, reinterpret_cast<const CarryT *>(p.carry[(e - 1) & 1]) + (long long)sig * n,
-                                                           sig, e, dense, last, K, warp, lane, region_knots, zero_dx, bad);
+            sweep_region<InT, CarryT, OutT, false, BAS>(p, sm, dense, last, K, warp, lane, region_knots, zero_dx, bad);
         }
         if (lane == 0) sm.cnt[warp] = region_knots;
         if (__any_sync(0xffffffffu, zero_dx) && lane == 0) sm.zero_dx = 1;
