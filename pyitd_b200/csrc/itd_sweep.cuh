@@ -42,9 +42,12 @@ constexpr int kSweepCap = 2000;                       // shared-memory knot tabl
 constexpr int kSweepPre = 2, kSweepPost = 3;          // halo slots of a region list
 constexpr int kSweepScratch = kSweepSpan + 8;         // warp-private scratch entries (span knots + 5)
 constexpr int kSweepPrefetch = 3;                     // L2 prefetch distance in spans
+constexpr int kSweepRatioMax = 40;                    // exact index ratios a / b for b <= 40 come from a table (many-knot items)
+constexpr int kSweepRatioOff = kSweepWarps * kSweepScratch;              // ... which lives in X behind the warp scratches
+constexpr int kSweepProbeKnots = 3;                   // extractions with at most this many knots are probed first
+static_assert(kSweepRatioOff + kSweepRatioMax * (kSweepRatioMax + 1) / 2 <= kSweepCap, "ratio table must fit behind the scratches");
 enum { kPtrIn = 0, kPtrRot, kPtrBas, kPtrCarry, kPtrGmask, kPtrNmask, kPtrCtau, kPtrCxk, kPtrNtau, kPtrNxk, kSweepPtrs };
 constexpr int kSweepDoneAll = 0x3fffffff;             // done[] value of a signal that has stopped
-static_assert(kSweepWarps * kSweepScratch * 3 <= kSweepCap * 2, "warp scratches + their tau words (8-byte carry) must fit in a table array");
 
 struct SweepTable {
     int *tau;            // [S, 8 * rs]  region r at r * rs: kSweepPre halo slots, the region's knots in order, kSweepPost halo slots
@@ -75,12 +78,6 @@ template <typename CarryT>
 struct SweepSmem {
     // few knots: {X, L, S}[global rank]; many knots: warp w's scratch at w * kSweepScratch in each array
     CarryT X[kSweepCap], L[kSweepCap], S[kSweepCap];
-    // many knots only: tau of the scratch entries; with an 8-byte carry they fit in the part of X the warp scratches
-    // leave free, a 4-byte carry gets an array of its own (its tables are half the size anyway)
-    int tau_extra[sizeof(CarryT) == 4 ? kSweepWarps * kSweepScratch : 1];
-    __device__ __forceinline__ int *tauw() {
-        return sizeof(CarryT) == 4 ? tau_extra : reinterpret_cast<int *>(X + kSweepWarps * kSweepScratch);
-    }
     int prefix[kSweepWarps + 1];               // knots before each region (prefix[8] = K)
     int cnt[kSweepWarps];                      // next level's knots per region
     CarryT endl[2], endx[2];                   // L_0, L_{K+1} (ITD.py:101-102); X_0 = in[0], X_{K+1} = in[n-1]
@@ -122,12 +119,18 @@ __device__ __forceinline__ T ld_cg(const T *p) {
 //   <false, 0>  few knots: records from the block's table;      <false, 1>  many knots: records built per span.
 // Non-EDGE spans are followed by a complete span, so their loads, flag words and neighbours need no checks.
 // ---------------------------------------------------------------------------------------------
-template <typename XT, typename CarryT, typename OutT, bool SCAN, bool BAS>
+// KIND: kLevel = one extraction; kScan = the extrema-compaction pass over the raw input; kProbe = extraction e of a signal
+// with at most kSweepProbeKnots knots, run WITHOUT storing B or the next level's knots: it writes the candidate trend
+// row (X_e) into row e and only counts the extrema of B_e.  Two thirds of such extractions are the discarded last one
+// (ITD.py:404-411), which then costs one read and one write per sample instead of a full level plus a row copy.
+enum { kLevel = 0, kScan = 1, kProbe = 2 };
+template <typename XT, typename CarryT, typename OutT, int KIND, bool BAS>
 __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<CarryT> &sm, const bool dense,
                                              const bool last, const int K, const int warp, const int lane,
                                              int &region_knots, bool &zero_dx, bool &bad) {
     using A = Arith<CarryT>;
     constexpr int ITEMS = kSweepItems, SPAN = kSweepSpan;
+    constexpr bool SCAN = (KIND == kScan), PROBE = (KIND == kProbe);
     const int n = p.n;
     const int sp0 = warp * p.spw;
     const int sp1 = min(sp0 + p.spw, p.spans);
@@ -144,7 +147,6 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
     const int roff = warp * p.rs;                             // this region's list inside the signal's knot arrays
 
     const int wsc = warp * kSweepScratch;                     // this warp's scratch inside the table arrays
-    int *tw = sm.tauw() + wsc;
     const int gbase0 = SCAN ? 0 : sm.prefix[warp];            // global rank of the last knot before the region
     const unsigned le_mask = 0xffffffffu >> (31 - lane);
 
@@ -163,52 +165,61 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
     if (!SCAN) mc = ld_cg(reinterpret_cast<const uint4 *>(gmask_p() + sp0 * ITEMS));
 
     // warp-private knot records of one span (many knots): scratch[i] = region list slot pos + i = the knot with global
-    // rank g0 + i, g0 = gbase0 + pos - 1; scratch[1] is the last knot before the span.  L for i in [1, cnt+3], slope for
-    // i in [1, cnt+2]  (ITD.py:100-110, :116)
+    // rank g0 + i, g0 = gbase0 + pos - 1; scratch[1] is the last knot before the span.  Records {X, L, slope} are needed
+    // for i in [1, cnt+2]  (ITD.py:100-110, :116).  One knot per lane, 32 consecutive list entries per round straight
+    // into registers, neighbours by shuffle: lanes 1..29 of a round own a complete record, so a round advances by 29.
     auto build_scratch = [&](const int cnt) {
         const int *ctau = reinterpret_cast<const int *>(sm.ptr[kPtrCtau]) + roff + pos;
         const CarryT *cxk = reinterpret_cast<const CarryT *>(sm.ptr[kPtrCxk]) + roff + pos;
         const int g0 = gbase0 + pos - 1;
-        const int m = cnt + 5;
-        __syncwarp();
-        for (int i = lane; i < m; i += 32) {
-            tw[i] = ld_cg(ctau + i);
-            sm.X[wsc + i] = ld_cg(cxk + i);
+        // the end knots 0 and K+1 (and the unused ranks beyond them) are rare: one warp-uniform test per span
+        const bool clip = (g0 + 1 <= 0) || (g0 + cnt + 3 >= K + 1);
+        const CarryT *rtab = sm.X + kSweepRatioOff;                // RN(a / b), b <= kSweepRatioMax (filled per dense item)
+        __syncwarp();                                              // the previous span's lookups are done
+        for (int i0 = 0; i0 + 1 <= cnt + 2; i0 += 29) {
+            const int i = i0 + lane;
+            int tv = 0;
+            CarryT xv = (CarryT)0;
+            if (i <= cnt + 4) {
+                tv = ld_cg(ctau + i);
+                xv = ld_cg(cxk + i);
+            }
+            const int tl = __shfl_up_sync(0xffffffffu, tv, 1), tr = __shfl_down_sync(0xffffffffu, tv, 1);
+            const CarryT xl = __shfl_up_sync(0xffffffffu, xv, 1), xr = __shfl_down_sync(0xffffffffu, xv, 1);
+            const int g = g0 + i;
+            const bool mine = (lane >= 1) && (lane <= 30) && (i <= cnt + 3);          // this lane's L is used
+            // ITD.py:108: (tau_k - tau_{k-1}) / (tau_{k+1} - tau_{k-1}), int64 -> float64 true division
+            int a = tv - tl, bb = tr - tl;
+            if (!mine) {
+                a = 0;
+                bb = 1;
+            }
+            // (halo slots beyond the end knots hold zeros: their gaps are not positive and take the division path; the
+            // table index is clamped rather than guarded because the compiler turns the guarded load into a select)
+            const bool tab_ok = (unsigned)(bb - 1) < (unsigned)kSweepRatioMax && (unsigned)a < (unsigned)bb;
+            CarryT w = rtab[tab_ok ? (bb * (bb - 1) >> 1) + a : 0];
+            if (!tab_ok) w = A::ratio(a, bb);
+            const CarryT d = A::sub(xr, xl);
+            const CarryT qq = A::add(xl, A::mul(w, d));
+            CarryT Lv = A::add(A::mul((CarryT)0.5, qq), A::mul((CarryT)0.5, xv));
+            if (clip) {
+                if (g <= 0) Lv = sm.endl[0];
+                if (g >= K + 1) Lv = sm.endl[1];
+            }
+            const CarryT Ln = __shfl_down_sync(0xffffffffu, Lv, 1);
+            const CarryT den = A::sub(xr, xv);                                       // ITD.py:116
+            const CarryT sl = A::div(A::sub(Ln, Lv), den);
+            if (lane >= 1 && lane <= 29 && i <= cnt + 2) {
+                const bool valid = !clip || (g >= 0 && g <= K);
+                zero_dx |= valid && (den == (CarryT)0);
+                sm.X[wsc + i] = xv;
+                sm.L[wsc + i] = Lv;
+                sm.S[wsc + i] = valid ? sl : (CarryT)0;
+            }
         }
         if (lane < 2 && pos + 512 + 64 < p.rs) {
             prefetch_l2(ctau + 512 + lane * 32);
             prefetch_l2(cxk + 512 + lane * 16);
-        }
-        __syncwarp();
-        // the end knots 0 and K+1 (and the unused ranks beyond them) are rare: one warp-uniform test per span
-        const bool clip = (g0 + 1 <= 0) || (g0 + cnt + 3 >= K + 1);
-        for (int i = 1 + lane; i <= cnt + 3; i += 32) {
-            const int g = g0 + i;
-            CarryT Lv;
-            if (clip && g <= 0) {
-                Lv = sm.endl[0];
-            } else if (clip && g >= K + 1) {
-                Lv = sm.endl[1];
-            } else {
-                const int tl = tw[i - 1];
-                const CarryT w = A::ratio(tw[i] - tl, tw[i + 1] - tl);
-                const CarryT xl = sm.X[wsc + i - 1];
-                const CarryT d = A::sub(sm.X[wsc + i + 1], xl);
-                const CarryT qq = A::add(xl, A::mul(w, d));
-                Lv = A::add(A::mul((CarryT)0.5, qq), A::mul((CarryT)0.5, sm.X[wsc + i]));
-            }
-            sm.L[wsc + i] = Lv;
-        }
-        __syncwarp();
-        for (int i = 1 + lane; i <= cnt + 2; i += 32) {
-            const int g = g0 + i;
-            CarryT sl = (CarryT)0;
-            if (!clip || (g >= 0 && g <= K)) {
-                const CarryT den = A::sub(sm.X[wsc + i + 1], sm.X[wsc + i]);
-                sl = A::div(A::sub(sm.L[wsc + i + 1], sm.L[wsc + i]), den);
-                zero_dx |= (den == (CarryT)0);
-            }
-            sm.S[wsc + i] = sl;
         }
         __syncwarp();
     };
@@ -263,25 +274,32 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
                 if (EDGE && t0 + r * 32 + lane >= n - 1) b[r] = (CarryT)0;        // ITD.py:112 (and the padding lanes)
             }
             OutT *rot = rot_p() + t0 + lane;
-            CarryT *carry = carry_p() + t0 + lane;
-            OutT *bas = BAS ? bas_p() + t0 + lane : nullptr;
-            if (!last) {
+            if (PROBE) {
+                // candidate trend row: the input of this extraction (ITD.py:410-411)
 #pragma unroll
-                for (int r = 0; r < ITEMS; ++r) {
-                    if (!EDGE || t0 + r * 32 + lane < n) {
-                        __stcs(rot + r * 32, (OutT)A::sub((CarryT)xc[r], b[r]));             // ITD.py:119
-                        __stwb(carry + r * 32, b[r]);
-                        if (BAS) __stcs(bas + r * 32, (OutT)b[r]);
-                    }
-                }
+                for (int r = 0; r < ITEMS; ++r)
+                    if (!EDGE || t0 + r * 32 + lane < n) __stcs(rot + r * 32, (OutT)xc[r]);
             } else {
+                CarryT *carry = carry_p() + t0 + lane;
+                OutT *bas = BAS ? bas_p() + t0 + lane : nullptr;
+                if (!last) {
 #pragma unroll
-                for (int r = 0; r < ITEMS; ++r) {
-                    if (!EDGE || t0 + r * 32 + lane < n) {
-                        const CarryT rr = A::sub((CarryT)xc[r], b[r]);
-                        __stcs(rot + r * 32, (OutT)A::add(rr, b[r]));                        // ITD.py:420
-                        __stwb(carry + r * 32, b[r]);
-                        if (BAS) __stcs(bas + r * 32, (OutT)0);                              // ITD.py:424
+                    for (int r = 0; r < ITEMS; ++r) {
+                        if (!EDGE || t0 + r * 32 + lane < n) {
+                            __stcs(rot + r * 32, (OutT)A::sub((CarryT)xc[r], b[r]));         // ITD.py:119
+                            __stwb(carry + r * 32, b[r]);
+                            if (BAS) __stcs(bas + r * 32, (OutT)b[r]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < ITEMS; ++r) {
+                        if (!EDGE || t0 + r * 32 + lane < n) {
+                            const CarryT rr = A::sub((CarryT)xc[r], b[r]);
+                            __stcs(rot + r * 32, (OutT)A::add(rr, b[r]));                    // ITD.py:420
+                            __stwb(carry + r * 32, b[r]);
+                            if (BAS) __stcs(bas + r * 32, (OutT)0);                          // ITD.py:424
+                        }
                     }
                 }
             }
@@ -315,13 +333,13 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
         // ---- extrema of B (of x for the scan): the next level's flag words and knots -------------
         unsigned fw[ITEMS];
         const int newc = span_extrema<EDGE, ITEMS, CarryT>(b, bleft, bright, lane, t0, n, fw);
-        if (lane < ITEMS) {
+        if (!PROBE && lane < ITEMS) {
             unsigned v = fw[0];
 #pragma unroll
             for (int r = 1; r < ITEMS; ++r) v = (lane == r) ? fw[r] : v;
             __stwb(nmask_p() + sp * ITEMS + lane, v);
         }
-        if (newc) {
+        if (!PROBE && newc) {
             int *ntau = reinterpret_cast<int *>(sm.ptr[kPtrNtau]) + roff + kSweepPre + npos;
             CarryT *nxk = reinterpret_cast<CarryT *>(sm.ptr[kPtrNxk]) + roff + kSweepPre + npos;
             const unsigned lt_mask = le_mask >> 1;
@@ -351,7 +369,7 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
             ++sp;
             continue;
         }
-        if (SCAN || !dense) {
+        if (SCAN || PROBE || !dense) {
 #pragma unroll 1
             for (; sp < fast_end; ++sp) span_body(std::false_type{}, std::integral_constant<int, 0>{}, sp);
         } else {
@@ -484,6 +502,12 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
                 return (long long)r * p.rs + kSweepPre + (g - 1 - sm.prefix[r]);
             };
             if (dense) {
+                // ---- exact index ratios RN(a / b), 0 <= a < b <= kSweepRatioMax (ITD.py:108), behind the warp scratches ----
+                for (int q = tid; q < kSweepRatioMax * (kSweepRatioMax + 1) / 2; q += blockDim.x) {
+                    int bb = 1;
+                    while ((bb * (bb + 1) >> 1) <= q) ++bb;               // q = bb (bb - 1) / 2 + a, a < bb
+                    sm.X[kSweepRatioOff + q] = A::ratio(q - (bb * (bb - 1) >> 1), bb);
+                }
                 // ---- halo slots of every region list: the two knots before and the three after the region ----
                 if (tid < kSweepWarps * (kSweepPre + kSweepPost)) {
                     const int r = tid / (kSweepPre + kSweepPost), h = tid % (kSweepPre + kSweepPost);
@@ -563,12 +587,26 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
         int region_knots = 0;
         bool zero_dx = false, bad = false;
         const bool last = (e == p.emax);
-        if (e < 0) {
-            sweep_region<InT, CarryT, OutT, true, BAS>(p, sm, false, false, 0, warp, lane, region_knots, zero_dx, bad);
+        // an extraction with at most kSweepProbeKnots knots is probably the discarded last one: probe it first
+        bool probed_stop = false;
+        if (e >= 1 && !last && K <= kSweepProbeKnots) {
+            sweep_region<CarryT, CarryT, OutT, kProbe, BAS>(p, sm, false, false, K, warp, lane, region_knots, zero_dx, bad);
+            if (lane == 0) sm.cnt[warp] = region_knots;
+            __syncthreads();
+            int kp = 0;
+#pragma unroll
+            for (int r = 0; r < kSweepWarps; ++r) kp += sm.cnt[r];
+            probed_stop = (kp < p.min_extrema);
+            __syncthreads();
+        }
+        if (probed_stop) {
+            // row e already holds the trend row; the region counts of the probe are the ones to report
+        } else if (e < 0) {
+            sweep_region<InT, CarryT, OutT, kScan, BAS>(p, sm, false, false, 0, warp, lane, region_knots, zero_dx, bad);
         } else if (std::is_same<InT, CarryT>::value || e > 0) {
-            sweep_region<CarryT, CarryT, OutT, false, BAS>(p, sm, dense, last, K, warp, lane, region_knots, zero_dx, bad);
+            sweep_region<CarryT, CarryT, OutT, kLevel, BAS>(p, sm, dense, last, K, warp, lane, region_knots, zero_dx, bad);
         } else {
-            sweep_region<InT, CarryT, OutT, false, BAS>(p, sm, dense, last, K, warp, lane, region_knots, zero_dx, bad);
+            sweep_region<InT, CarryT, OutT, kLevel, BAS>(p, sm, dense, last, K, warp, lane, region_knots, zero_dx, bad);
         }
         if (lane == 0) sm.cnt[warp] = region_knots;
         if (__any_sync(0xffffffffu, zero_dx) && lane == 0) sm.zero_dx = 1;
@@ -595,16 +633,16 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
                     p.stop_e[sig] = e;
                 }
             }
-            if (stop_knots) {
+            if (stop_knots && !probed_stop) {
                 // the discarded extraction wrote R_e into row e; the reference returns baselines[e-1] there, i.e. the
                 // INPUT of this extraction (zeros when e == 0)  (ITD.py:410-411)
                 OutT *rot = reinterpret_cast<OutT *>(p.rot) + (long long)sig * p.out_sig_stride + (long long)e * n;
                 const CarryT *src = (e == 0) ? nullptr : reinterpret_cast<const CarryT *>(p.carry[(e - 1) & 1]) + (long long)sig * n;
                 sweep_fill_row<OutT, CarryT>(rot, src, n, e == 0);
-                if (BAS && (p.opts & kOptZeroTail)) {
-                    OutT *bas = reinterpret_cast<OutT *>(p.bas) + (long long)sig * p.out_sig_stride + (long long)e * n;
-                    sweep_fill_row<OutT, CarryT>(bas, nullptr, n, true);
-                }
+            }
+            if (stop_knots && BAS && (p.opts & kOptZeroTail)) {
+                OutT *bas = reinterpret_cast<OutT *>(p.bas) + (long long)sig * p.out_sig_stride + (long long)e * n;
+                sweep_fill_row<OutT, CarryT>(bas, nullptr, n, true);
             }
         }
         __syncthreads();                                               // every thread's global writes are issued
