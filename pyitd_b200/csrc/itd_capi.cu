@@ -71,7 +71,7 @@ struct pyitd_plan {
     // many signals: the whole decomposition in one persistent launch (itd_sweep.cuh).  `stream` stays set when the shape
     // allows it: the single-level entry points (extract_level, find_knots, ...) keep using those kernels.
     bool sweep = false;
-    int sw_spans = 0, sw_spw = 0, sw_rs = 0, sw_grid = 0;
+    int sw_spans = 0, sw_spw = 0, sw_rs = 0, sw_grid[2] = {0, 0};
     int *sw_ticket = nullptr, *sw_done = nullptr, *sw_rcount[2] = {nullptr, nullptr};
     unsigned long long *sw_stage_ns = nullptr;
     int strided_cap = 0;      // test hook: upper bound on the persistent grid (PYITD_STRIDED_CTAS)
@@ -974,7 +974,6 @@ static cudaError_t sweep_launch_t(const SweepParams &p, bool bas, int *grid_cach
     k<<<(unsigned)g, kSweepWarps * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
-
 static int run_sweep(pyitd_plan *pl, const void *x, void *rotations, void *baselines, int32_t *n_rows,
                      int32_t *knot_counts, int32_t *input_knots, int *sk, int32_t *status, cudaStream_t st) {
     const int stages = pl->emax + 2;                        // the scan + extractions 0 .. emax
@@ -1012,15 +1011,20 @@ static int run_sweep(pyitd_plan *pl, const void *x, void *rotations, void *basel
     sp.rows = pl->rows;
     sp.min_extrema = pl->min_extrema;
     sp.opts = pl->opts;
+    // L2 prefetch distance of the sample stream in spans: three short spans ahead on levels with few knots, two of the
+    // longer spans of the first levels (a line prefetched too early is evicted again before its span: 39 % extra DRAM
+    // reads measured on level 0 at distance 6, profiles/r2/ncu_sweep_v1_metrics.txt)
+    sp.pf_sparse = getenv("PYITD_SWEEP_PF_SPARSE") ? atoi(getenv("PYITD_SWEEP_PF_SPARSE")) : 3;
+    sp.pf_dense = getenv("PYITD_SWEEP_PF_DENSE") ? atoi(getenv("PYITD_SWEEP_PF_DENSE")) : 2;
     auto launch = [&](int first, int last, int ticket_slot) -> cudaError_t {
         sp.stage_first = first;
         sp.stage_last = last;
         sp.ticket = pl->sw_ticket + ticket_slot;
         const bool bas = baselines != nullptr;
         switch (pl->dtype) {
-            case PYITD_F64: return sweep_launch_t<double, double, double>(sp, bas, &pl->sw_grid, st);
-            case PYITD_F32_MIXED: return sweep_launch_t<float, double, float>(sp, bas, &pl->sw_grid, st);
-            default: return sweep_launch_t<float, float, float>(sp, bas, &pl->sw_grid, st);
+            case PYITD_F64: return sweep_launch_t<double, double, double>(sp, bas, pl->sw_grid, st);
+            case PYITD_F32_MIXED: return sweep_launch_t<float, double, float>(sp, bas, pl->sw_grid, st);
+            default: return sweep_launch_t<float, float, float>(sp, bas, pl->sw_grid, st);
         }
     };
     if (int rc = mark(pl, st)) return rc;

@@ -21,9 +21,11 @@
 //     is done ONE THREAD PER KNOT:
 //       - few knots (K + 2 <= kSweepCap): by the whole block, once per item, into a shared-memory table
 //         {X_k, L_k, s_k} indexed by global rank (three block barriers per signal-level instead of one per tile);
-//       - many knots (the first two or three levels): per warp and per span into a warp-private scratch, from the
-//         region's own list, whose two slots before and three slots after the region's knots are filled with the
-//         neighbouring regions' knots ("halo") by 40 threads at the start of the item.
+//       - many knots (the first two or three levels): per warp, for as many consecutive spans of its region as fit a
+//         warp-private table of 250 records (3 spans on level 0 of the benchmark, 10 on level 1, 30 on level 2), 32
+//         knots at a time with every lane busy, from the region's own list, whose two slots before and three slots
+//         after the region's knots are filled with the neighbouring regions' knots ("halo") by 40 threads at the start
+//         of the item.  The spans of such a chunk then stream exactly like spans of a few-knot level.
 //
 // Same arithmetic, same operation order, -fmad=false: bit-identical to the reference in fp64.
 #pragma once
@@ -40,12 +42,9 @@ constexpr int kSweepItems = 4;
 constexpr int kSweepSpan = 32 * kSweepItems;          // samples per warp iteration
 constexpr int kSweepCap = 2000;                       // shared-memory knot table: K + 2 <= kSweepCap (static shared memory: 48 KB)
 constexpr int kSweepPre = 2, kSweepPost = 3;          // halo slots of a region list
-constexpr int kSweepScratch = kSweepSpan + 8;         // warp-private scratch entries (span knots + 5)
-constexpr int kSweepPrefetch = 3;                     // L2 prefetch distance in spans
-constexpr int kSweepRatioMax = 40;                    // exact index ratios a / b for b <= 40 come from a table (many-knot items)
-constexpr int kSweepRatioOff = kSweepWarps * kSweepScratch;              // ... which lives in X behind the warp scratches
+constexpr int kSweepScratch = kSweepCap / kSweepWarps;      // warp-private table entries of a many-knot item (>= span knots + 5)
 constexpr int kSweepProbeKnots = 3;                   // extractions with at most this many knots are probed first
-static_assert(kSweepRatioOff + kSweepRatioMax * (kSweepRatioMax + 1) / 2 <= kSweepCap, "ratio table must fit behind the scratches");
+static_assert(kSweepScratch >= kSweepSpan + 5, "a span's knots + 5 must fit a warp table");
 enum { kPtrIn = 0, kPtrRot, kPtrBas, kPtrCarry, kPtrGmask, kPtrNmask, kPtrCtau, kPtrCxk, kPtrNtau, kPtrNxk, kSweepPtrs };
 constexpr int kSweepDoneAll = 0x3fffffff;             // done[] value of a signal that has stopped
 
@@ -72,12 +71,14 @@ struct SweepParams {
     int stage_first, stage_last;   // stages of this launch: -1 (scan) .. emax
     int emax, rows, min_extrema;
     unsigned opts;
+    int pf_sparse, pf_dense;       // L2 prefetch distance of the sample stream in spans (0: none), few / many knots
 };
 
 template <typename CarryT>
 struct SweepSmem {
     // few knots: {X, L, S}[global rank]; many knots: warp w's scratch at w * kSweepScratch in each array
-    CarryT X[kSweepCap], L[kSweepCap], S[kSweepCap];
+    static constexpr int kCap = kSweepCap;
+    CarryT X[kCap], L[kCap], S[kCap];
     int prefix[kSweepWarps + 1];               // knots before each region (prefix[8] = K)
     int cnt[kSweepWarps];                      // next level's knots per region
     CarryT endl[2], endx[2];                   // L_0, L_{K+1} (ITD.py:101-102); X_0 = in[0], X_{K+1} = in[n-1]
@@ -168,60 +169,73 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
     // rank g0 + i, g0 = gbase0 + pos - 1; scratch[1] is the last knot before the span.  Records {X, L, slope} are needed
     // for i in [1, cnt+2]  (ITD.py:100-110, :116).  One knot per lane, 32 consecutive list entries per round straight
     // into registers, neighbours by shuffle: lanes 1..29 of a round own a complete record, so a round advances by 29.
-    auto build_scratch = [&](const int cnt) {
+    // ---- many knots: warp-private records for a CHUNK of consecutive spans -----------------------------------------
+    // As many spans of this region as fit the warp's table (kSweepScratch entries) get their records in one go: the
+    // list entries arrive with independent coalesced loads, L and the slopes are computed 32 knots at a time with
+    // every lane busy, and the spans of the chunk then stream like spans of a few-knot level.  table[i] = region list
+    // slot cbase + i = the knot with global rank g0 + i, g0 = gbase0 + cbase - 1; table[1] is the last knot before the
+    // chunk.  L for i in [1, tot+3], slope for i in [1, tot+2]  (ITD.py:100-110, :116)
+    int chunk_left = 0, cbase = 0;
+    auto build_chunk = [&](const int sp) {
+        // plan: the next m <= 32 spans, tot knots, tot + 5 <= kSweepScratch (one span always fits: 128 + 5)
+        const int nsp = min(32, sp1 - sp);
+        uint4 w4 = make_uint4(0, 0, 0, 0);
+        if (lane < nsp) w4 = ld_cg(reinterpret_cast<const uint4 *>(gmask_p()) + sp + lane);
+        int pre = __popc(w4.x) + __popc(w4.y) + __popc(w4.z) + __popc(w4.w);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= o) pre += v;
+        }
+        const int m = __popc(__ballot_sync(0xffffffffu, lane < nsp && pre + 5 <= kSweepScratch));
+        const int tot = __shfl_sync(0xffffffffu, pre, m - 1);
         const int *ctau = reinterpret_cast<const int *>(sm.ptr[kPtrCtau]) + roff + pos;
         const CarryT *cxk = reinterpret_cast<const CarryT *>(sm.ptr[kPtrCxk]) + roff + pos;
+        int *tw = reinterpret_cast<int *>(sm.S + wsc);               // tau words live in S's storage until S is computed
         const int g0 = gbase0 + pos - 1;
-        // the end knots 0 and K+1 (and the unused ranks beyond them) are rare: one warp-uniform test per span
-        const bool clip = (g0 + 1 <= 0) || (g0 + cnt + 3 >= K + 1);
-        const CarryT *rtab = sm.X + kSweepRatioOff;                // RN(a / b), b <= kSweepRatioMax (filled per dense item)
-        __syncwarp();                                              // the previous span's lookups are done
-        for (int i0 = 0; i0 + 1 <= cnt + 2; i0 += 29) {
-            const int i = i0 + lane;
-            int tv = 0;
-            CarryT xv = (CarryT)0;
-            if (i <= cnt + 4) {
-                tv = ld_cg(ctau + i);
-                xv = ld_cg(cxk + i);
-            }
-            const int tl = __shfl_up_sync(0xffffffffu, tv, 1), tr = __shfl_down_sync(0xffffffffu, tv, 1);
-            const CarryT xl = __shfl_up_sync(0xffffffffu, xv, 1), xr = __shfl_down_sync(0xffffffffu, xv, 1);
-            const int g = g0 + i;
-            const bool mine = (lane >= 1) && (lane <= 30) && (i <= cnt + 3);          // this lane's L is used
-            // ITD.py:108: (tau_k - tau_{k-1}) / (tau_{k+1} - tau_{k-1}), int64 -> float64 true division
-            int a = tv - tl, bb = tr - tl;
-            if (!mine) {
-                a = 0;
-                bb = 1;
-            }
-            // (halo slots beyond the end knots hold zeros: their gaps are not positive and take the division path; the
-            // table index is clamped rather than guarded because the compiler turns the guarded load into a select)
-            const bool tab_ok = (unsigned)(bb - 1) < (unsigned)kSweepRatioMax && (unsigned)a < (unsigned)bb;
-            CarryT w = rtab[tab_ok ? (bb * (bb - 1) >> 1) + a : 0];
-            if (!tab_ok) w = A::ratio(a, bb);
-            const CarryT d = A::sub(xr, xl);
-            const CarryT qq = A::add(xl, A::mul(w, d));
-            CarryT Lv = A::add(A::mul((CarryT)0.5, qq), A::mul((CarryT)0.5, xv));
-            if (clip) {
-                if (g <= 0) Lv = sm.endl[0];
-                if (g >= K + 1) Lv = sm.endl[1];
-            }
-            const CarryT Ln = __shfl_down_sync(0xffffffffu, Lv, 1);
-            const CarryT den = A::sub(xr, xv);                                       // ITD.py:116
-            const CarryT sl = A::div(A::sub(Ln, Lv), den);
-            if (lane >= 1 && lane <= 29 && i <= cnt + 2) {
-                const bool valid = !clip || (g >= 0 && g <= K);
-                zero_dx |= valid && (den == (CarryT)0);
-                sm.X[wsc + i] = xv;
-                sm.L[wsc + i] = Lv;
-                sm.S[wsc + i] = valid ? sl : (CarryT)0;
-            }
+        __syncwarp();                                                // the previous chunk's lookups are done
+        for (int i = lane; i < tot + 5; i += 32) {
+            tw[i] = ld_cg(ctau + i);
+            sm.X[wsc + i] = ld_cg(cxk + i);
         }
-        if (lane < 2 && pos + 512 + 64 < p.rs) {
-            prefetch_l2(ctau + 512 + lane * 32);
-            prefetch_l2(cxk + 512 + lane * 16);
+        if (lane < 12 && pos + tot + 5 + 3 * kSweepScratch < p.rs) {   // the next chunk's entries towards L2
+            if (lane < 4) prefetch_l2(ctau + tot + 5 + kSweepScratch / 2 + lane * 32);
+            else prefetch_l2(cxk + tot + 5 + kSweepScratch / 2 + (lane - 4) * 16);
         }
         __syncwarp();
+        // the end knots 0 and K+1 (and the unused ranks beyond them) are rare: one warp-uniform test per chunk
+        const bool clip = (g0 + 1 <= 0) || (g0 + tot + 3 >= K + 1);
+        for (int i = 1 + lane; i <= tot + 3; i += 32) {
+            const int g = g0 + i;
+            CarryT Lv;
+            if (clip && g <= 0) {
+                Lv = sm.endl[0];
+            } else if (clip && g >= K + 1) {
+                Lv = sm.endl[1];
+            } else {
+                const int tl = tw[i - 1];
+                const CarryT w = A::ratio(tw[i] - tl, tw[i + 1] - tl);
+                const CarryT xl = sm.X[wsc + i - 1];
+                const CarryT d = A::sub(sm.X[wsc + i + 1], xl);
+                const CarryT qq = A::add(xl, A::mul(w, d));
+                Lv = A::add(A::mul((CarryT)0.5, qq), A::mul((CarryT)0.5, sm.X[wsc + i]));
+            }
+            sm.L[wsc + i] = Lv;
+        }
+        __syncwarp();
+        for (int i = 1 + lane; i <= tot + 2; i += 32) {
+            const int g = g0 + i;
+            CarryT sl = (CarryT)0;
+            if (!clip || (g >= 0 && g <= K)) {
+                const CarryT den = A::sub(sm.X[wsc + i + 1], sm.X[wsc + i]);
+                sl = A::div(A::sub(sm.L[wsc + i + 1], sm.L[wsc + i]), den);
+                zero_dx |= (den == (CarryT)0);
+            }
+            sm.S[wsc + i] = sl;
+        }
+        __syncwarp();
+        chunk_left = m;
+        cbase = pos;
     };
 
     auto span_body = [&](auto edge_tag, auto mode_tag, const int sp) {
@@ -236,8 +250,11 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
         uint4 mn = make_uint4(0, 0, 0, 0);
         if (have_right) xr = ld_cg(in_p() + tend);
         if (!SCAN && (!EDGE || sp + 1 < p.spans)) mn = ld_cg(reinterpret_cast<const uint4 *>(gmask_p() + (sp + 1) * ITEMS));
-        if (sp + kSweepPrefetch < sp1 && lane < SPAN * (int)sizeof(XT) / 128)
-            prefetch_l2(in_p() + t0 + kSweepPrefetch * SPAN + lane * (128 / (int)sizeof(XT)));
+        {
+            const int pf = is_dense ? p.pf_dense : p.pf_sparse;
+            if (pf > 0 && sp + pf < sp1 && lane < SPAN * (int)sizeof(XT) / 128)
+                prefetch_l2(in_p() + t0 + pf * SPAN + lane * (128 / (int)sizeof(XT)));
+        }
 
         const unsigned mw[ITEMS] = {mc.x, mc.y, mc.z, mc.w};
         int wpre[ITEMS];
@@ -250,8 +267,9 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
         int ib = 0;                                            // index of the record of the last knot before the span
         if (!SCAN) {
             if (is_dense) {
-                build_scratch(cnt);
-                ib = wsc + 1;
+                if (chunk_left == 0) build_chunk(sp);
+                --chunk_left;
+                ib = wsc + 1 + (pos - cbase);
             } else {
                 ib = gbase0 + pos;
             }
@@ -402,6 +420,7 @@ __device__ __forceinline__ void sweep_fill_row(OutT *dst, const CarryT *src, int
 // ---------------------------------------------------------------------------------------------
 // sweep_kernel
 // ---------------------------------------------------------------------------------------------
+// (an 80-register build, 3 CTAs per SM, was measured stage by stage against this one: no stage gains, profiles/r2/README.md)
 template <typename InT, typename CarryT, typename OutT, bool BAS>
 __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepParams p) {
     using A = Arith<CarryT>;
@@ -491,7 +510,7 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
             }
             __syncthreads();
             K = sm.prefix[kSweepWarps];
-            dense = (K + 2 > kSweepCap);
+            dense = (K + 2 > SweepSmem<CarryT>::kCap);
             const int *ctau = cur.tau + (long long)sig * p.kstride;
             const CarryT *cxk = reinterpret_cast<const CarryT *>(cur.xk) + (long long)sig * p.kstride;
             // list slot of the interior knot with global rank g (1 <= g <= K)
@@ -502,12 +521,6 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
                 return (long long)r * p.rs + kSweepPre + (g - 1 - sm.prefix[r]);
             };
             if (dense) {
-                // ---- exact index ratios RN(a / b), 0 <= a < b <= kSweepRatioMax (ITD.py:108), behind the warp scratches ----
-                for (int q = tid; q < kSweepRatioMax * (kSweepRatioMax + 1) / 2; q += blockDim.x) {
-                    int bb = 1;
-                    while ((bb * (bb + 1) >> 1) <= q) ++bb;               // q = bb (bb - 1) / 2 + a, a < bb
-                    sm.X[kSweepRatioOff + q] = A::ratio(q - (bb * (bb - 1) >> 1), bb);
-                }
                 // ---- halo slots of every region list: the two knots before and the three after the region ----
                 if (tid < kSweepWarps * (kSweepPre + kSweepPost)) {
                     const int r = tid / (kSweepPre + kSweepPost), h = tid % (kSweepPre + kSweepPost);
