@@ -969,7 +969,7 @@ static cudaError_t sweep_launch_t(const SweepParams &p, bool bas, int *grid_cach
         *grid_cache = per_sm * sms;
     }
     long long g = *grid_cache;
-    const long long items = (long long)(p.stage_last - p.stage_first + 1) * p.S;
+    const long long items = p.depth_first ? (long long)p.S : (long long)(p.stage_last - p.stage_first + 1) * p.S;
     if (g > items) g = items;
     k<<<(unsigned)g, kSweepWarps * 32, smem, st>>>(p);
     return cudaGetLastError();
@@ -1016,6 +1016,10 @@ static int run_sweep(pyitd_plan *pl, const void *x, void *rotations, void *basel
     // reads measured on level 0 at distance 6, profiles/r2/ncu_sweep_v1_metrics.txt)
     sp.pf_sparse = getenv("PYITD_SWEEP_PF_SPARSE") ? atoi(getenv("PYITD_SWEEP_PF_SPARSE")) : 3;
     sp.pf_dense = getenv("PYITD_SWEEP_PF_DENSE") ? atoi(getenv("PYITD_SWEEP_PF_DENSE")) : 2;
+    // short signals: signal-major order keeps each CTA's carry / flags / knot lists in L2 between its stages (all
+    // resident CTAs' carries must fit comfortably: 592 CTAs x n x carry bytes <= 48 MB, i.e. n <= ~10 000 fp64 samples)
+    sp.depth_first = ((size_t)pl->n * pl->carry_elem * 592 <= ((size_t)48 << 20)) ? 1 : 0;
+    if (const char *env = getenv("PYITD_SWEEP_DEPTH")) sp.depth_first = atoi(env) ? 1 : 0;
     auto launch = [&](int first, int last, int ticket_slot) -> cudaError_t {
         sp.stage_first = first;
         sp.stage_last = last;

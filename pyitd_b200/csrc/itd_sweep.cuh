@@ -72,6 +72,11 @@ struct SweepParams {
     int emax, rows, min_extrema;
     unsigned opts;
     int pf_sparse, pf_dense;       // L2 prefetch distance of the sample stream in spans (0: none), few / many knots
+    // item order.  0: stage-major tickets (every signal's stage e before any signal's stage e + 1; an item waits for its
+    // signal's previous stage through done[]).  1: a ticket is a SIGNAL and the CTA runs all of its stages back to back:
+    // the carry, flag words and knot lists it reads were written by the same CTA a few microseconds earlier and are
+    // still in L2 -- for short signals (framed audio), where all resident CTAs' working sets fit there.
+    int depth_first;
 };
 
 template <typename CarryT>
@@ -427,21 +432,39 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
     __shared__ SweepSmem<CarryT> sm;        // static: every shared-memory access is a compile-time offset
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = p.n, S = p.S;
-    const long long n_items = (long long)(p.stage_last - p.stage_first + 1) * S;
+    const bool depth = p.depth_first != 0;
+    const long long n_items = depth ? (long long)S : (long long)(p.stage_last - p.stage_first + 1) * S;
+    int d_sig = -1, d_e = 0;                                   // depth-first cursor: the signal this CTA is working through
+    // after an item: the next stage of the same signal, or (signal finished) a new ticket
+    auto advance = [&](const int e, const bool stopped) {
+        if (e == p.stage_last || (stopped && !(p.opts & kOptZeroTail))) d_sig = -1;
+        else d_e = e + 1;
+    };
 
     for (;;) {
         __syncthreads();                                       // everyone is done with the previous item's shared state
-        if (tid == 0) sm.ticket = atomicAdd(p.ticket, 1);
-        __syncthreads();
-        const long long t = sm.ticket;
-        if (t >= n_items) break;
-        const int e = p.stage_first + (int)(t / S);            // -1: scan
-        const int sig = (int)(t % S);
+        int e, sig;
+        if (!depth || d_sig < 0) {
+            if (tid == 0) sm.ticket = atomicAdd(p.ticket, 1);
+            __syncthreads();
+            const long long t = sm.ticket;
+            if (t >= n_items) break;
+            if (depth) {
+                d_sig = (int)t;
+                d_e = p.stage_first;
+            }
+            e = p.stage_first + (int)(t / S);                  // -1: scan
+            sig = (int)(t % S);
+        }
+        if (depth) {
+            e = d_e;
+            sig = d_sig;
+        }
         unsigned long long t_start = 0;
         if (p.stage_ns && tid == 0) t_start = global_ns();
 
         // ---- wait for the previous stage of this signal ----------------------------------------
-        if (e >= 0) {
+        if (e >= 0 && (!depth || e == p.stage_first)) {
             if (tid == 0) {
                 while (ld_acquire(p.done + sig) < e + 1) __nanosleep(200);
                 __threadfence();
@@ -459,6 +482,7 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
                     sweep_fill_row<OutT, CarryT>(bas, nullptr, n, true);
                 }
             }
+            advance(e, true);
             continue;
         }
 
@@ -665,6 +689,7 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
             st_release(p.done + sig, (e >= 0 && (stop_knots || last)) ? kSweepDoneAll : e + 2);
             if (p.stage_ns) atomicAdd(p.stage_ns + (e + 1), global_ns() - t_start);
         }
+        advance(e, e >= 0 && (stop_knots || last));
     }
 }
 

@@ -143,6 +143,35 @@ def test_one_launch_equals_one_launch_per_stage(monkeypatch):
     check_batch_against_c_oracle(a, x.cpu().numpy(), 11)
 
 
+@pytest.mark.parametrize("depth", ["0", "1"])
+def test_item_order_does_not_change_results(depth, monkeypatch):
+    """Stage-major tickets (an item waits for its signal's previous stage) and signal-major tickets (a CTA runs all
+    stages of a signal back to back: the default for short signals) must give the same bytes; both against the oracle."""
+    monkeypatch.setenv("PYITD_SWEEP_DEPTH", depth)
+    rng = np.random.default_rng(7700)
+    for S, n in ((700, 2048), (9, 8192), (37, 20000)):
+        x = _mixed_batch(rng, S, n)
+        res = pyitd_b200.decompose(gpu(x), max_iteration=7, return_baselines=True, zero_tail=True)
+        torch.cuda.synchronize()
+        rot, n_rows, counts, status, bas = o.c_decompose_batch(x, 7, want_baselines=True)
+        ok = status == 0
+        assert (res.status.cpu().numpy() != 0).tolist() == (~ok).tolist()
+        assert res.n_rows.cpu().numpy()[ok].tolist() == n_rows[ok].tolist()
+        got = res.rotations.cpu().numpy()
+        for s_ in np.flatnonzero(ok):
+            nr = int(n_rows[s_])
+            assert got[s_, :nr].tobytes() == rot[s_, :nr].tobytes(), (depth, S, n, s_)
+            assert float(np.abs(got[s_, nr:]).max() if nr < got.shape[1] else 0) == 0
+    # config 4's shape (framed audio, fp32 in / out around an fp64 carry)
+    fr = synth.audio_frames(seconds=30.0)
+    r = pyitd_b200.decompose(gpu(fr), max_iteration=7, dtype="f32_mixed", return_baselines=True)
+    torch.cuda.synchronize()
+    for s_ in (0, 7, fr.shape[0] - 1):
+        want = o.c_decompose(fr[s_].astype(np.float64), 7)
+        assert r.rows_of(s_).cpu().numpy().tobytes() == want.rotations.astype(np.float32).tobytes()
+        assert r.baselines_of(s_).cpu().numpy().tobytes() == want.baselines.astype(np.float32).tobytes()
+
+
 def test_benchmark_shape_256_channels_bit_exact():
     """bench.py's workload shape and generator: 256 channels x 65 536 samples, EVERY channel bit for bit -- rotations,
     baselines, per-level knot counts, stop kind (ITD.py:351-433) -- with and without the baselines."""
