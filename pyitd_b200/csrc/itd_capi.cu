@@ -1015,11 +1015,17 @@ static int run_sweep(pyitd_plan *pl, const void *x, void *rotations, void *basel
     // longer spans of the first levels (a line prefetched too early is evicted again before its span: 39 % extra DRAM
     // reads measured on level 0 at distance 6, profiles/r2/ncu_sweep_v1_metrics.txt)
     sp.pf_sparse = getenv("PYITD_SWEEP_PF_SPARSE") ? atoi(getenv("PYITD_SWEEP_PF_SPARSE")) : 3;
+    sp.pf_scan = getenv("PYITD_SWEEP_PF_SCAN") ? atoi(getenv("PYITD_SWEEP_PF_SCAN")) : 4;
     sp.pf_dense = getenv("PYITD_SWEEP_PF_DENSE") ? atoi(getenv("PYITD_SWEEP_PF_DENSE")) : 2;
     // short signals: signal-major order keeps each CTA's carry / flags / knot lists in L2 between its stages (all
     // resident CTAs' carries must fit comfortably: 592 CTAs x n x carry bytes <= 48 MB, i.e. n <= ~10 000 fp64 samples)
     sp.depth_first = ((size_t)pl->n * pl->carry_elem * 592 <= ((size_t)48 << 20)) ? 1 : 0;
     if (const char *env = getenv("PYITD_SWEEP_DEPTH")) sp.depth_first = atoi(env) ? 1 : 0;
+    // PYITD_SWEEP_FUSED_SCAN=1: no scan stage -- extraction 0 finds the knots of the raw input inside its chunk builds and the
+    // input's knot lists never exist (-5.7 GB of DRAM traffic per 4096 x 65536 step).  Bit-identical, but level 0 is
+    // issue-bound and the extra stencil work costs more than the scan stage it replaces (3.18 ms vs 0.75 + 2.07 ms,
+    // profiles/r2/README.md), so the separate stage stays the default.
+    sp.fused_scan = (getenv("PYITD_SWEEP_FUSED_SCAN") && atoi(getenv("PYITD_SWEEP_FUSED_SCAN"))) ? 1 : 0;
     auto launch = [&](int first, int last, int ticket_slot) -> cudaError_t {
         sp.stage_first = first;
         sp.stage_last = last;
@@ -1035,13 +1041,15 @@ static int run_sweep(pyitd_plan *pl, const void *x, void *rotations, void *basel
     if (pl->timing || getenv("PYITD_SWEEP_PER_STAGE")) {
         // measurement mode: one launch per stage, so that every stage can be timed (and profiled) on its own
         for (int s = 0; s < stages; ++s) {
-            CU(launch(s - 1, s - 1, s));
-            pl->launches++;
+            if (s > 0 || !sp.fused_scan) {                 // (the event list keeps its scan slot: zero length without one)
+                CU(launch(s - 1, s - 1, s));
+                pl->launches++;
+            }
             if (int rc = mark(pl, st)) return rc;
         }
         return 0;
     }
-    CU(launch(-1, pl->emax, 0));
+    CU(launch(sp.fused_scan ? 0 : -1, pl->emax, 0));
     pl->launches = 1;
     return mark(pl, st);
 }

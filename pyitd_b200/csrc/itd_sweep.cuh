@@ -71,12 +71,14 @@ struct SweepParams {
     int stage_first, stage_last;   // stages of this launch: -1 (scan) .. emax
     int emax, rows, min_extrema;
     unsigned opts;
+    int pf_scan;                   // ... of the input scan inside extraction 0
     int pf_sparse, pf_dense;       // L2 prefetch distance of the sample stream in spans (0: none), few / many knots
     // item order.  0: stage-major tickets (every signal's stage e before any signal's stage e + 1; an item waits for its
     // signal's previous stage through done[]).  1: a ticket is a SIGNAL and the CTA runs all of its stages back to back:
     // the carry, flag words and knot lists it reads were written by the same CTA a few microseconds earlier and are
     // still in L2 -- for short signals (framed audio), where all resident CTAs' working sets fit there.
     int depth_first;
+    int fused_scan;                // 1: no scan stage (stage_first >= 0): extraction 0 finds the input's knots itself (kFirst)
 };
 
 template <typename CarryT>
@@ -90,6 +92,8 @@ struct SweepSmem {
     // the item's base pointers (per signal / per row), computed once per item by one thread: the span loop adds a
     // sample or word index to them instead of re-deriving sig * stride + e * n every span
     void *ptr[kSweepPtrs];
+    int keep[kSweepWarps][2];                  // extraction 0 without a scan stage: tau of a chunk's last two elements
+    int knots_in[kSweepWarps];                 // ... and the input knots each warp found in its own spans
     int ticket, zero_dx;
 };
 
@@ -129,18 +133,23 @@ __device__ __forceinline__ T ld_cg(const T *p) {
 // with at most kSweepProbeKnots knots, run WITHOUT storing B or the next level's knots: it writes the candidate trend
 // row (X_e) into row e and only counts the extrema of B_e.  Two thirds of such extractions are the discarded last one
 // (ITD.py:404-411), which then costs one read and one write per sample instead of a full level plus a row copy.
-enum { kLevel = 0, kScan = 1, kProbe = 2 };
+// kFirst = extraction 0 WITHOUT a separate scan stage: each warp finds the knots of the raw input itself (3-point stencil,
+// ITD.py:44-59 on x and -x) while it builds the record table of a chunk, straight into shared memory -- the input's
+// knot lists (0.56 knots per sample on the benchmark: 12 B written and 12 B read per knot) never exist, and the
+// stage that read the input just to find them is gone.
+enum { kLevel = 0, kScan = 1, kProbe = 2, kFirst = 3 };
 template <typename XT, typename CarryT, typename OutT, int KIND, bool BAS>
 __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<CarryT> &sm, const bool dense,
                                              const bool last, const int K, const int warp, const int lane,
-                                             int &region_knots, bool &zero_dx, bool &bad) {
+                                             int &region_knots, int &input_knots, bool &zero_dx, bool &bad) {
     using A = Arith<CarryT>;
     constexpr int ITEMS = kSweepItems, SPAN = kSweepSpan;
-    constexpr bool SCAN = (KIND == kScan), PROBE = (KIND == kProbe);
+    constexpr bool SCAN = (KIND == kScan), PROBE = (KIND == kProbe), FIRST = (KIND == kFirst);
     const int n = p.n;
     const int sp0 = warp * p.spw;
     const int sp1 = min(sp0 + p.spw, p.spans);
     region_knots = 0;
+    input_knots = 0;
     if (sp0 >= sp1) return;
 
     // item base pointers come from shared memory where they are used (no registers held across the span loop)
@@ -168,12 +177,8 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
         const int t = sp0 * SPAN + r * 32 + lane;
         xc[r] = (t < n) ? ld_cg(in_p() + t) : (XT)0;
     }
-    if (!SCAN) mc = ld_cg(reinterpret_cast<const uint4 *>(gmask_p() + sp0 * ITEMS));
+    if (!SCAN && !FIRST) mc = ld_cg(reinterpret_cast<const uint4 *>(gmask_p() + sp0 * ITEMS));
 
-    // warp-private knot records of one span (many knots): scratch[i] = region list slot pos + i = the knot with global
-    // rank g0 + i, g0 = gbase0 + pos - 1; scratch[1] is the last knot before the span.  Records {X, L, slope} are needed
-    // for i in [1, cnt+2]  (ITD.py:100-110, :116).  One knot per lane, 32 consecutive list entries per round straight
-    // into registers, neighbours by shuffle: lanes 1..29 of a round own a complete record, so a round advances by 29.
     // ---- many knots: warp-private records for a CHUNK of consecutive spans -----------------------------------------
     // As many spans of this region as fit the warp's table (kSweepScratch entries) get their records in one go: the
     // list entries arrive with independent coalesced loads, L and the slopes are computed 32 knots at a time with
@@ -243,6 +248,162 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
         cbase = pos;
     };
 
+    // ---- extraction 0 without a scan stage: the chunk's records from the raw input ---------------------------------
+    // The element sequence of a signal is: the end knot at sample 0, its interior knots, the end knot at sample n-1.
+    // table[0..1] = the two elements before the chunk's first knot, table[2 .. tot+1] = the knots of the chunk's spans,
+    // table[tot+2 .. tot+4] = the three elements after them; -1 marks "no such element".  A chunk takes spans while
+    // their knots fit the table; the first span that does not (or the spans behind the region) supplies the three
+    // elements after it and is scanned again by the next chunk.  Flag words of every scanned span go to the mask array
+    // the span loop reads (through L2).
+    int ctot = 0;                                                    // knots of the current chunk
+    auto scan_span = [&](const int s, CarryT (&v)[ITEMS], unsigned (&fw)[ITEMS], const bool check) -> int {
+        const int t0 = s * SPAN;
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+            const int t = t0 + r * 32 + lane;
+            v[r] = (t < n) ? (CarryT)ld_cg(in_p() + t) : (CarryT)0;
+            if (check && t < n) bad |= !isfinite(v[r]);
+        }
+        const CarryT vl = (t0 > 0) ? (CarryT)ld_cg(in_p() + t0 - 1) : (CarryT)0;
+        const CarryT vr = (t0 + SPAN <= n - 1) ? (CarryT)ld_cg(in_p() + t0 + SPAN) : (CarryT)0;
+        if (check && lane < SPAN * (int)sizeof(XT) / 128) {          // the scan runs ahead of the span loop: keep DRAM busy
+            const long long tp = (long long)t0 + p.pf_scan * SPAN + lane * (128 / (int)sizeof(XT));
+            if (tp < n) prefetch_l2(in_p() + tp);
+        }
+        const int c = span_extrema<true, ITEMS, CarryT>(v, vl, vr, lane, t0, n, fw);
+        if (lane < ITEMS) {
+            unsigned w = fw[0];
+#pragma unroll
+            for (int r = 1; r < ITEMS; ++r) w = (lane == r) ? fw[r] : w;
+            __stwb(reinterpret_cast<unsigned *>(sm.ptr[kPtrGmask]) + s * ITEMS + lane, w);
+        }
+        return c;
+    };
+    auto build_chunk_first = [&](const int sp) {
+        int *tw = reinterpret_cast<int *>(sm.S + wsc);               // tau words live in S's storage until S is computed
+        CarryT *tx = sm.X + wsc;
+        const unsigned lt_mask = le_mask >> 1;
+        __syncwarp();                                                // the previous chunk's lookups are done
+        // ---- the two elements before the chunk
+        if (sp == sp0) {
+            int found = 0;
+            for (int s = sp0 - 1; s >= 0 && found < 2; --s) {
+                CarryT v[ITEMS];
+                unsigned fw[ITEMS];
+                const int c = scan_span(s, v, fw, false);
+                if (c) {
+                    int above = 0;                                   // knots of the span in higher words
+#pragma unroll
+                    for (int r = ITEMS - 1; r >= 0; --r) {
+                        if ((fw[r] >> lane) & 1u) {
+                            const int rtop = above + __popc(fw[r] & ~le_mask);      // knots of the span behind mine
+                            if (rtop < 2 - found) {
+                                tw[1 - found - rtop] = s * SPAN + r * 32 + lane;
+                                tx[1 - found - rtop] = v[r];
+                            }
+                        }
+                        above += __popc(fw[r]);
+                    }
+                    found += min(c, 2 - found);
+                }
+            }
+            if (found < 2 && lane == 0) {                            // ran into the start of the signal
+                tw[1 - found] = 0;
+                tx[1 - found] = sm.endx[0];
+                if (found == 0) {
+                    tw[0] = -1;
+                    tx[0] = (CarryT)0;
+                }
+            }
+        } else {
+            const int t0v = sm.keep[warp][0], t1v = sm.keep[warp][1];   // (the slopes have overwritten the tau words)
+            const CarryT x0v = tx[ctot], x1v = tx[ctot + 1];
+            __syncwarp();
+            if (lane == 0) {
+                tw[0] = t0v;
+                tw[1] = t1v;
+                tx[0] = x0v;
+                tx[1] = x1v;
+            }
+        }
+        // ---- the chunk's spans, then the three elements after them
+        int tot = 0, m = 0, post = 0;
+        for (int s = sp; s < p.spans; ++s) {
+            CarryT v[ITEMS];
+            unsigned fw[ITEMS];
+            const int c = scan_span(s, v, fw, s < sp1);
+            const bool own = (post == 0) && (s < sp1) && (tot + c + 5 <= kSweepScratch);
+            const int room = own ? c : 3 - post;                     // knots of this span that enter the table
+            if (c) {
+                int pre = 0;
+#pragma unroll
+                for (int r = 0; r < ITEMS; ++r) {
+                    if ((fw[r] >> lane) & 1u) {
+                        const int rank = pre + __popc(fw[r] & lt_mask);
+                        if (rank < room) {
+                            tw[2 + tot + (own ? 0 : post) + rank] = s * SPAN + r * 32 + lane;
+                            tx[2 + tot + (own ? 0 : post) + rank] = v[r];
+                        }
+                    }
+                    pre += __popc(fw[r]);
+                }
+            }
+            if (own) {
+                tot += c;
+                ++m;
+            } else {
+                post += min(c, 3 - post);
+                if (post >= 3) break;
+            }
+        }
+        if (post < 3 && lane == 0) {                                 // ran into the end of the signal
+            tw[2 + tot + post] = n - 1;
+            tx[2 + tot + post] = sm.endx[1];
+            for (int q = post + 1; q < 3; ++q) {
+                tw[2 + tot + q] = -1;
+                tx[2 + tot + q] = (CarryT)0;
+            }
+        }
+        __syncwarp();
+        // ---- L for entries [1, tot+3], slopes for [1, tot+2]  (ITD.py:100-110, :116).  The slopes overwrite the tau
+        // words, so which entries start a real segment is noted (one bit per round) while tau is still intact.
+        unsigned seg_ok = 0;
+        for (int i = 1 + lane, k = 0; i <= tot + 3; i += 32, ++k) {
+            const int ti = tw[i];
+            CarryT Lv = (CarryT)0;
+            if (ti == 0) {
+                Lv = sm.endl[0];
+            } else if (ti == n - 1) {
+                Lv = sm.endl[1];
+            } else if (ti > 0) {
+                const int tl = tw[i - 1];
+                const CarryT w = A::ratio(ti - tl, tw[i + 1] - tl);
+                const CarryT xl = tx[i - 1];
+                const CarryT d = A::sub(tx[i + 1], xl);
+                const CarryT qq = A::add(xl, A::mul(w, d));
+                Lv = A::add(A::mul((CarryT)0.5, qq), A::mul((CarryT)0.5, tx[i]));
+            }
+            if (ti >= 0 && ti != n - 1 && i <= tot + 2 && tw[i + 1] >= 0) seg_ok |= 1u << k;
+            sm.L[wsc + i] = Lv;
+        }
+        if (lane < 2) sm.keep[warp][lane] = tw[tot + lane];          // the next chunk's first two entries
+        __syncwarp();
+        for (int i = 1 + lane, k = 0; i <= tot + 2; i += 32, ++k) {
+            CarryT sl = (CarryT)0;
+            if ((seg_ok >> k) & 1u) {
+                const CarryT den = A::sub(tx[i + 1], tx[i]);
+                sl = A::div(A::sub(sm.L[wsc + i + 1], sm.L[wsc + i]), den);
+                zero_dx |= (den == (CarryT)0);
+            }
+            sm.S[wsc + i] = sl;
+        }
+        __syncwarp();
+        chunk_left = m;
+        cbase = pos;
+        ctot = tot;
+        input_knots += tot;
+    };
+
     auto span_body = [&](auto edge_tag, auto mode_tag, const int sp) {
         constexpr bool EDGE = decltype(edge_tag)::value;
         constexpr int MODE = decltype(mode_tag)::value;
@@ -250,6 +411,15 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
         const int t0 = sp * SPAN;
         const int tend = t0 + SPAN;                            // first sample after the span
         const bool have_right = !EDGE || tend <= n - 1;
+        // ---- many knots: a new chunk's records first (extraction 0 without a scan stage also produces the flag words)
+        if (!SCAN && is_dense && chunk_left == 0) {
+            if (FIRST) {
+                build_chunk_first(sp);
+                mc = ld_cg(reinterpret_cast<const uint4 *>(gmask_p() + sp * ITEMS));       // just written (through L2)
+            } else {
+                build_chunk(sp);
+            }
+        }
         // ---- early loads: the span's right neighbour (one broadcast load) and the next span's flag words ----
         XT xr = (XT)0;
         uint4 mn = make_uint4(0, 0, 0, 0);
@@ -272,7 +442,6 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
         int ib = 0;                                            // index of the record of the last knot before the span
         if (!SCAN) {
             if (is_dense) {
-                if (chunk_left == 0) build_chunk(sp);
                 --chunk_left;
                 ib = wsc + 1 + (pos - cbase);
             } else {
@@ -464,7 +633,7 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
         if (p.stage_ns && tid == 0) t_start = global_ns();
 
         // ---- wait for the previous stage of this signal ----------------------------------------
-        if (e >= 0 && (!depth || e == p.stage_first)) {
+        if (e >= 0 && !(e == 0 && p.fused_scan) && (!depth || e == p.stage_first)) {
             if (tid == 0) {
                 while (ld_acquire(p.done + sig) < e + 1) __nanosleep(200);
                 __threadfence();
@@ -508,11 +677,13 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
         if (e < 0) __syncthreads();
         if (e >= 0) {
             const SweepTable &cur = p.tab[e & 1];
+            const bool first_fused = (e == 0) && p.fused_scan;
             if (tid == 0) {
                 int run = 0;
                 for (int r = 0; r < kSweepWarps; ++r) {
                     sm.prefix[r] = run;
-                    run += ld_cg(cur.rcount + (long long)sig * kSweepWarps + r);
+                    // (extraction 0 without a scan stage: the knots are not known yet; it always runs in chunk mode)
+                    run += first_fused ? kSweepCap : ld_cg(cur.rcount + (long long)sig * kSweepWarps + r);
                 }
                 sm.prefix[kSweepWarps] = run;
                 sm.zero_dx = 0;
@@ -546,7 +717,7 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
             };
             if (dense) {
                 // ---- halo slots of every region list: the two knots before and the three after the region ----
-                if (tid < kSweepWarps * (kSweepPre + kSweepPost)) {
+                if (!first_fused && tid < kSweepWarps * (kSweepPre + kSweepPost)) {
                     const int r = tid / (kSweepPre + kSweepPost), h = tid % (kSweepPre + kSweepPost);
                     const int c = sm.prefix[r + 1] - sm.prefix[r];
                     const int j = (h < kSweepPre) ? h - kSweepPre : c + (h - kSweepPre);       // local index in region r
@@ -627,7 +798,8 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
         // an extraction with at most kSweepProbeKnots knots is probably the discarded last one: probe it first
         bool probed_stop = false;
         if (e >= 1 && !last && K <= kSweepProbeKnots) {
-            sweep_region<CarryT, CarryT, OutT, kProbe, BAS>(p, sm, false, false, K, warp, lane, region_knots, zero_dx, bad);
+            int unused = 0;
+            sweep_region<CarryT, CarryT, OutT, kProbe, BAS>(p, sm, false, false, K, warp, lane, region_knots, unused, zero_dx, bad);
             if (lane == 0) sm.cnt[warp] = region_knots;
             __syncthreads();
             int kp = 0;
@@ -636,14 +808,18 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
             probed_stop = (kp < p.min_extrema);
             __syncthreads();
         }
+        int knots_in = 0;
         if (probed_stop) {
             // row e already holds the trend row; the region counts of the probe are the ones to report
         } else if (e < 0) {
-            sweep_region<InT, CarryT, OutT, kScan, BAS>(p, sm, false, false, 0, warp, lane, region_knots, zero_dx, bad);
+            sweep_region<InT, CarryT, OutT, kScan, BAS>(p, sm, false, false, 0, warp, lane, region_knots, knots_in, zero_dx, bad);
+        } else if (e == 0 && p.fused_scan) {
+            sweep_region<InT, CarryT, OutT, kFirst, BAS>(p, sm, true, last, K, warp, lane, region_knots, knots_in, zero_dx, bad);
+            if (lane == 0) sm.knots_in[warp] = knots_in;
         } else if (std::is_same<InT, CarryT>::value || e > 0) {
-            sweep_region<CarryT, CarryT, OutT, kLevel, BAS>(p, sm, dense, last, K, warp, lane, region_knots, zero_dx, bad);
+            sweep_region<CarryT, CarryT, OutT, kLevel, BAS>(p, sm, dense, last, K, warp, lane, region_knots, knots_in, zero_dx, bad);
         } else {
-            sweep_region<InT, CarryT, OutT, kLevel, BAS>(p, sm, dense, last, K, warp, lane, region_knots, zero_dx, bad);
+            sweep_region<InT, CarryT, OutT, kLevel, BAS>(p, sm, dense, last, K, warp, lane, region_knots, knots_in, zero_dx, bad);
         }
         if (lane == 0) sm.cnt[warp] = region_knots;
         if (__any_sync(0xffffffffu, zero_dx) && lane == 0) sm.zero_dx = 1;
@@ -661,6 +837,11 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
             if (tid == 0 && p.input_knots) p.input_knots[sig] = Kn;
         } else {
             stop_knots = (Kn < p.min_extrema);                         // ITD.py:404
+            if (tid == 0 && e == 0 && p.fused_scan && p.input_knots) {
+                int kin = 0;
+                for (int r = 0; r < kSweepWarps; ++r) kin += sm.knots_in[r];
+                p.input_knots[sig] = kin;
+            }
             if (tid == 0) {
                 if (sm.zero_dx) atomicOr(p.status + sig, kStZeroDx);
                 p.knot_counts[(long long)sig * p.rows + e] = Kn;       // what ITD.py:403 prints

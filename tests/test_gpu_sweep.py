@@ -131,6 +131,21 @@ def test_ticket_scheduler_with_few_and_many_signals(S):
     check_batch_against_c_oracle(res, x, 11)
 
 
+@pytest.mark.parametrize("n", [5, 129, 1000, 4100, 8192, 20001, 40000])
+def test_separate_scan_stage_equals_scan_fused_into_extraction_0(n, monkeypatch):
+    """PYITD_SWEEP_FUSED_SCAN=1: extraction 0 finds the knots of the raw input itself, chunk by chunk, straight into shared
+    memory (no scan stage, no knot lists of the input).  Same bytes as with the separate scan stage (the default)."""
+    rng = np.random.default_rng(7800 + n)
+    x = _mixed_batch(rng, 13, n)
+    a = check_against_oracle(x, max_iteration=11)
+    monkeypatch.setenv("PYITD_SWEEP_FUSED_SCAN", "1")
+    b = check_against_oracle(x, max_iteration=11)
+    for s_ in range(x.shape[0]):
+        if int(a.status[s_]) == 0:
+            assert torch.equal(a.rows_of(s_), b.rows_of(s_)) and torch.equal(a.baselines_of(s_), b.baselines_of(s_))
+    assert torch.equal(a.input_knots, b.input_knots) and torch.equal(a.status, b.status)
+
+
 def test_one_launch_equals_one_launch_per_stage(monkeypatch):
     x = synth.eeg_like(40, 16384, seed=77, device="cuda")
     a = pyitd_b200.decompose(x, max_iteration=11, return_baselines=True, zero_tail=True)
