@@ -70,6 +70,12 @@ def lib() -> ctypes.CDLL:
     L.pyitd_plan_workspace_bytes.argtypes = [vp]
     L.pyitd_plan_launches.restype = ci
     L.pyitd_plan_launches.argtypes = [vp]
+    if hasattr(L, "pyitd_has_feature"):
+        L.pyitd_has_feature.restype = ci
+        L.pyitd_has_feature.argtypes = [ctypes.c_char_p]
+    if hasattr(L, "pyitd_plan_sweep_stats"):           # (absent from older builds used in A/B measurements)
+        L.pyitd_plan_sweep_stats.restype = ci
+        L.pyitd_plan_sweep_stats.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     L.pyitd_plan_path.restype = ci
     L.pyitd_plan_path.argtypes = [vp, ctypes.POINTER(ci)]
     L.pyitd_plan_set_groups.restype = ci
@@ -110,6 +116,12 @@ def lib() -> ctypes.CDLL:
     return L
 
 
+def has_feature(name: str) -> bool:
+    """Optional code paths of the loaded build (see pyitd_has_feature in the header)."""
+    L = lib()
+    return bool(hasattr(L, "pyitd_has_feature") and L.pyitd_has_feature(name.encode()))
+
+
 def check(rc: int, what: str) -> None:
     if rc == 0:
         return
@@ -147,6 +159,12 @@ class Plan:
     @property
     def launches(self) -> int:
         return int(self._L.pyitd_plan_launches(self.handle))
+
+    def sweep_stats(self) -> tuple[int, int]:
+        """(pairs of extractions fused into one item, counting passes without a fused pass) of the last call."""
+        a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+        check(self._L.pyitd_plan_sweep_stats(self.handle, ctypes.byref(a), ctypes.byref(b)), "pyitd_plan_sweep_stats")
+        return int(a.value), int(b.value)
 
     @property
     def path(self) -> tuple[str, int]:

@@ -73,6 +73,10 @@ struct pyitd_plan {
     bool sweep = false;
     int sw_spans = 0, sw_spw = 0, sw_rs = 0, sw_grid[2] = {0, 0};
     int *sw_ticket = nullptr, *sw_done = nullptr, *sw_rcount[2] = {nullptr, nullptr};
+    // fused pairs of extractions (itd_sweep.cuh): per-CTA scratch for the knots of the baseline between the two
+    int sw_mid_ctas = 0, *sw_mid_tau = nullptr;
+    void *sw_mid_xk = nullptr;
+    unsigned *sw_mid_mask = nullptr;
     unsigned long long *sw_stage_ns = nullptr;
     int strided_cap = 0;      // test hook: upper bound on the persistent grid (PYITD_STRIDED_CTAS)
     // whole-decomposition-on-chip kernel (itd_resident.cuh): one cluster per signal, one launch per batch
@@ -602,9 +606,21 @@ static int ensure_workspace(pyitd_plan *pl, cudaStream_t st) {
     const int ls_div = getenv("PYITD_LS_DIV") ? (atoi(getenv("PYITD_LS_DIV")) > 1 ? atoi(getenv("PYITD_LS_DIV")) : 16) : 16;   // experiment hook (n/16 measured best: profiles/r1/s5/ls_probe2.log)
     pl->lscap = (ls_on && (pl->stream || pl->strided)) ? (int)((pl->n / ls_div) & ~1ll) : 0;   // even: float rows stay 16-byte aligned
     const size_t b_ls = pl->lscap ? align_up((size_t)pl->S * (size_t)(pl->lscap + 4) * 2 * pl->carry_elem) : 0;
-    const size_t b_sweep = pl->sweep ? align_up((size_t)(pl->rows + 4) * sizeof(int)) + align_up((size_t)pl->S * sizeof(int)) +
+    // sweep path: ticket slots, done[] + sel[] (one memset clears both), region counts, stage clocks, and the per-CTA scratch of
+    // the fused pairs (PYITD_SWEEP_FUSE=0 turns them off): 4 CTAs per SM is the kernel's launch bound
+    int mid_ctas = 0;
+    if (pl->sweep && !(getenv("PYITD_SWEEP_FUSE") && atoi(getenv("PYITD_SWEEP_FUSE")) == 0)) {
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+        mid_ctas = 4 * sms;
+        if ((long long)mid_ctas > pl->S) mid_ctas = (int)pl->S;
+    }
+    const size_t mid_list = (size_t)kSweepWarps * (size_t)pl->sw_rs;
+    const size_t b_mid = align_up((size_t)mid_ctas * mid_list * sizeof(int)) + align_up((size_t)mid_ctas * mid_list * pl->carry_elem) +
+                         align_up((size_t)mid_ctas * (size_t)mstride * sizeof(unsigned));
+    const size_t b_sweep = pl->sweep ? align_up((size_t)(pl->rows + 4) * sizeof(int)) + align_up((size_t)pl->S * 2 * sizeof(int)) +
                                            2 * align_up((size_t)pl->S * kSweepWarps * sizeof(int)) +
-                                           align_up((size_t)(pl->rows + 2) * sizeof(unsigned long long))
+                                           align_up((size_t)(pl->rows + 2) * sizeof(unsigned long long)) + b_mid
                                      : 0;
     size_t total = 2 * b_carry + 2 * (b_tau + b_xk + b_tbase + b_sig + b_endl + b_mask) + b_desc + 3 * b_sig + 2 * b_group + b_stage + b_ls + b_sweep;
     pl->ws_bytes = total;
@@ -647,9 +663,15 @@ static int ensure_workspace(pyitd_plan *pl, cudaStream_t st) {
     pl->ls = b_ls ? take(b_ls) : nullptr;
     if (pl->sweep) {
         pl->sw_ticket = (int *)take(align_up((size_t)(pl->rows + 4) * sizeof(int)));
-        pl->sw_done = (int *)take(align_up((size_t)pl->S * sizeof(int)));
+        pl->sw_done = (int *)take(align_up((size_t)pl->S * 2 * sizeof(int)));              // done[S], sel[S]
         for (int i = 0; i < 2; ++i) pl->sw_rcount[i] = (int *)take(align_up((size_t)pl->S * kSweepWarps * sizeof(int)));
         pl->sw_stage_ns = (unsigned long long *)take(align_up((size_t)(pl->rows + 2) * sizeof(unsigned long long)));
+        pl->sw_mid_ctas = mid_ctas;
+        if (mid_ctas) {
+            pl->sw_mid_tau = (int *)take(align_up((size_t)mid_ctas * mid_list * sizeof(int)));
+            pl->sw_mid_xk = take(align_up((size_t)mid_ctas * mid_list * pl->carry_elem));
+            pl->sw_mid_mask = (unsigned *)take(align_up((size_t)mid_ctas * (size_t)mstride * sizeof(unsigned)));
+        }
     }
     // the mask rows are padded to 4 words: the padding (and everything else) starts out as "no knot"
     // on the CALLER's stream: a cudaStreamNonBlocking stream is not ordered after the legacy default stream, so a
@@ -978,7 +1000,7 @@ static int run_sweep(pyitd_plan *pl, const void *x, void *rotations, void *basel
                      int32_t *knot_counts, int32_t *input_knots, int *sk, int32_t *status, cudaStream_t st) {
     const int stages = pl->emax + 2;                        // the scan + extractions 0 .. emax
     CU(cudaMemsetAsync(pl->sw_ticket, 0, (size_t)(pl->rows + 4) * sizeof(int), st));
-    CU(cudaMemsetAsync(pl->sw_done, 0, (size_t)pl->S * sizeof(int), st));
+    CU(cudaMemsetAsync(pl->sw_done, 0, (size_t)pl->S * 2 * sizeof(int), st));
     SweepParams sp = {};
     sp.x = x;
     sp.carry[0] = pl->carry[0];
@@ -995,6 +1017,18 @@ static int run_sweep(pyitd_plan *pl, const void *x, void *rotations, void *basel
     sp.kstride = pl->table[0].kstride;
     sp.mstride = pl->table[0].mstride;
     sp.done = pl->sw_done;
+    sp.stats = pl->sw_ticket + pl->rows + 2;               // (zeroed with the ticket slots)
+    sp.mid_tau = pl->sw_mid_tau;
+    sp.mid_xk = pl->sw_mid_xk;
+    sp.mid_mask = pl->sw_mid_mask;
+    sp.mid_ctas = pl->sw_mid_ctas;
+    // PYITD_SWEEP_FUSE=0: every extraction is an item of its own (the round-2 v6 behaviour); thresholds: itd_sweep.cuh
+    sp.fuse = pl->sw_mid_ctas > 0 ? 1 : 0;                 // (short signals: decided below, with the item order)
+    sp.fuse_min_a = getenv("PYITD_SWEEP_FUSE_MIN_A") ? atoi(getenv("PYITD_SWEEP_FUSE_MIN_A")) : kSweepFuseMinA;
+    sp.fuse_max_a = getenv("PYITD_SWEEP_FUSE_MAX_A") ? atoi(getenv("PYITD_SWEEP_FUSE_MAX_A")) : kSweepFuseMaxA;
+    sp.fuse_min_b = getenv("PYITD_SWEEP_FUSE_MIN_B") ? atoi(getenv("PYITD_SWEEP_FUSE_MIN_B")) : kSweepFuseMinB;
+    if (sp.fuse_min_a <= kSweepProbeKnots) sp.fuse_min_a = kSweepProbeKnots + 1;
+    if (sp.fuse_min_b < 1) sp.fuse_min_b = 1;
     sp.stop_e = pl->stop_e;
     sp.stop_kind = sk;
     sp.n_rows = n_rows;
@@ -1017,15 +1051,27 @@ static int run_sweep(pyitd_plan *pl, const void *x, void *rotations, void *basel
     sp.pf_sparse = getenv("PYITD_SWEEP_PF_SPARSE") ? atoi(getenv("PYITD_SWEEP_PF_SPARSE")) : 3;
     sp.pf_scan = getenv("PYITD_SWEEP_PF_SCAN") ? atoi(getenv("PYITD_SWEEP_PF_SCAN")) : 4;
     sp.pf_dense = getenv("PYITD_SWEEP_PF_DENSE") ? atoi(getenv("PYITD_SWEEP_PF_DENSE")) : 2;
+    sp.pf_count = getenv("PYITD_SWEEP_PF_COUNT") ? atoi(getenv("PYITD_SWEEP_PF_COUNT")) : 3;
+    sp.pf_fused = getenv("PYITD_SWEEP_PF_FUSED") ? atoi(getenv("PYITD_SWEEP_PF_FUSED")) : 2;
     // short signals: signal-major order keeps each CTA's carry / flags / knot lists in L2 between its stages (all
     // resident CTAs' carries must fit comfortably: 592 CTAs x n x carry bytes <= 48 MB, i.e. n <= ~10 000 fp64 samples)
     sp.depth_first = ((size_t)pl->n * pl->carry_elem * 592 <= ((size_t)48 << 20)) ? 1 : 0;
     if (const char *env = getenv("PYITD_SWEEP_DEPTH")) sp.depth_first = atoi(env) ? 1 : 0;
+    // signal-major order keeps the carry in L2 between a signal's extractions: a fused pair saves no DRAM traffic there and its
+    // counting pass only adds instructions (config 4: 1.12 -> 1.51 ms with pairs).  PYITD_SWEEP_FUSE=2 forces them on.
+    if (sp.depth_first && !(getenv("PYITD_SWEEP_FUSE") && atoi(getenv("PYITD_SWEEP_FUSE")) == 2)) sp.fuse = 0;
     // PYITD_SWEEP_FUSED_SCAN=1: no scan stage -- extraction 0 finds the knots of the raw input inside its chunk builds and the
     // input's knot lists never exist (-5.7 GB of DRAM traffic per 4096 x 65536 step).  Bit-identical, but level 0 is
     // issue-bound and the extra stencil work costs more than the scan stage it replaces (3.18 ms vs 0.75 + 2.07 ms,
     // profiles/r2/README.md), so the separate stage stays the default.
+    // Round 2, later: the variant costs 5000 SASS instructions inside the one kernel every stage runs from, and removing it
+    // from the default build made the whole step 0.1 - 0.25 ms faster: it is compiled only with -DPYITD_SWEEP_WITH_FUSED_SCAN
+    // (pyitd_has_feature("sweep_fused_scan")), and the switch is ignored otherwise.
+#ifdef PYITD_SWEEP_WITH_FUSED_SCAN
     sp.fused_scan = (getenv("PYITD_SWEEP_FUSED_SCAN") && atoi(getenv("PYITD_SWEEP_FUSED_SCAN"))) ? 1 : 0;
+#else
+    sp.fused_scan = 0;
+#endif
     auto launch = [&](int first, int last, int ticket_slot) -> cudaError_t {
         sp.stage_first = first;
         sp.stage_last = last;
@@ -1052,6 +1098,26 @@ static int run_sweep(pyitd_plan *pl, const void *x, void *rotations, void *basel
     CU(launch(sp.fused_scan ? 0 : -1, pl->emax, 0));
     pl->launches = 1;
     return mark(pl, st);
+}
+
+extern "C" int pyitd_has_feature(const char *name) {
+    if (!name) return 0;
+    if (!strcmp(name, "sweep_fused_pairs")) return 1;
+#ifdef PYITD_SWEEP_WITH_FUSED_SCAN
+    if (!strcmp(name, "sweep_fused_scan")) return 1;
+#endif
+    return 0;
+}
+
+extern "C" int pyitd_plan_sweep_stats(pyitd_plan *pl, int64_t *fused_pairs, int64_t *unfused_counts) {
+    if (!pl || !fused_pairs || !unfused_counts) return fail(PYITD_E_INVALID, "null argument");
+    if (!pl->sweep || !pl->ws) return fail(PYITD_E_INVALID, "the plan has not run the sweep kernel");
+    DeviceGuard guard(pl->device);
+    int v[2] = {0, 0};
+    CU(cudaMemcpy(v, pl->sw_ticket + pl->rows + 2, sizeof(v), cudaMemcpyDeviceToHost));      // waits for the device
+    *fused_pairs = v[0];
+    *unfused_counts = v[1];
+    return 0;
 }
 
 extern "C" int pyitd_plan_set_groups(pyitd_plan *pl, int groups) {

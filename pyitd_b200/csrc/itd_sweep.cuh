@@ -43,9 +43,13 @@ constexpr int kSweepSpan = 32 * kSweepItems;          // samples per warp iterat
 constexpr int kSweepCap = 2000;                       // shared-memory knot table: K + 2 <= kSweepCap (static shared memory: 48 KB)
 constexpr int kSweepPre = 2, kSweepPost = 3;          // halo slots of a region list
 constexpr int kSweepScratch = kSweepCap / kSweepWarps;      // warp-private table entries of a many-knot item (>= span knots + 5)
+// fused pairs: extraction e with kSweepFuseMinA <= K and K + 2 <= kSweepFuseMaxA first COUNTS the knots of its baseline;
+// with at least kSweepFuseMinB of them (and both tables fitting the block's arrays) extractions e and e + 1 run as one pass
+constexpr int kSweepFuseMinA = 12, kSweepFuseMaxA = 1400, kSweepFuseMinB = 4;
 constexpr int kSweepProbeKnots = 3;                   // extractions with at most this many knots are probed first
 static_assert(kSweepScratch >= kSweepSpan + 5, "a span's knots + 5 must fit a warp table");
-enum { kPtrIn = 0, kPtrRot, kPtrBas, kPtrCarry, kPtrGmask, kPtrNmask, kPtrCtau, kPtrCxk, kPtrNtau, kPtrNxk, kSweepPtrs };
+enum { kPtrIn = 0, kPtrRot, kPtrBas, kPtrCarry, kPtrGmask, kPtrNmask, kPtrCtau, kPtrCxk, kPtrNtau, kPtrNxk,
+       kPtrRot2, kPtrBas2, kPtrGmask2, kSweepPtrs };
 constexpr int kSweepDoneAll = 0x3fffffff;             // done[] value of a signal that has stopped
 
 struct SweepTable {
@@ -57,13 +61,22 @@ struct SweepTable {
 
 struct SweepParams {
     const void *x;       // [S, N] input type
-    void *carry[2];      // [S, N] carry type: extraction e reads carry[(e - 1) & 1] (x for e == 0), writes carry[e & 1]
-    SweepTable tab[2];   // extraction e reads tab[e & 1] (written by the scan for e == 0), writes tab[(e + 1) & 1]
+    // Ping-pong, selected PER SIGNAL by a bit that travels with done[] (0 for extraction 0, flipped by every item that
+    // completes an extraction or a fused pair of extractions): the item reads the knots of its input from tab[sel] and the input itself (e >= 1) from
+    // carry[sel ^ 1]; it writes the last baseline it computes to carry[sel] and that baseline's knots to tab[sel ^ 1].
+    void *carry[2];      // [S, N] carry type
+    SweepTable tab[2];
+    // fused pair (e, e + 1): the knots of B_e live only between the two passes of one item, in the CTA's own scratch
+    int *mid_tau;        // [mid_ctas, 8 * rs]
+    void *mid_xk;        // [mid_ctas, 8 * rs] carry type
+    unsigned *mid_mask;  // [mid_ctas, mstride]
+    int mid_ctas;        // CTAs the scratch was sized for (0: no fused pairs)
+    int *stats;          // [2] pairs of extractions fused; counting passes that did not end in a fused pass
     void *rot, *bas;     // [S, rows, N] output type; bas may be null
     long long out_sig_stride;
     long long kstride, mstride;
     int *ticket;         // [1]  zeroed before the launch
-    int *done;           // [S]  stages completed: 1 after the scan, e + 2 after extraction e
+    int *done;           // [S]  stages completed: 1 after the scan, e + 2 after extraction e; bit 30: the table selector
     int *stop_e, *stop_kind, *n_rows, *knot_counts, *status, *input_knots;
     unsigned long long *stage_ns;   // optional [rows + 1]: CTA-nanoseconds spent per stage (index stage + 1)
     int S, n;
@@ -73,11 +86,14 @@ struct SweepParams {
     unsigned opts;
     int pf_scan;                   // ... of the input scan inside extraction 0
     int pf_sparse, pf_dense;       // L2 prefetch distance of the sample stream in spans (0: none), few / many knots
+    int pf_count, pf_fused;        // ... of the two passes of a fused pair (the counting pass writes next to nothing)
     // item order.  0: stage-major tickets (every signal's stage e before any signal's stage e + 1; an item waits for its
     // signal's previous stage through done[]).  1: a ticket is a SIGNAL and the CTA runs all of its stages back to back:
     // the carry, flag words and knot lists it reads were written by the same CTA a few microseconds earlier and are
     // still in L2 -- for short signals (framed audio), where all resident CTAs' working sets fit there.
     int depth_first;
+    int fuse;                      // 1: pairs of few-knot extractions run as one item that never stores the baseline between them
+    int fuse_min_a, fuse_max_a, fuse_min_b;   // thresholds (kSweepFuse*; experiment hooks)
     int fused_scan;                // 1: no scan stage (stage_first >= 0): extraction 0 finds the input's knots itself (kFirst)
 };
 
@@ -87,6 +103,9 @@ struct SweepSmem {
     static constexpr int kCap = kSweepCap;
     CarryT X[kCap], L[kCap], S[kCap];
     int prefix[kSweepWarps + 1];               // knots before each region (prefix[8] = K)
+    int prefix2[kSweepWarps + 1];              // fused pair: the same for the knots of B_e
+    CarryT endl2[2], endx2[2];                 // ... and its end values
+    CarryT bend[4];                            // B_e at samples 0, 1, n-2, n-1 (written by the counting pass)
     int cnt[kSweepWarps];                      // next level's knots per region
     CarryT endl[2], endx[2];                   // L_0, L_{K+1} (ITD.py:101-102); X_0 = in[0], X_{K+1} = in[n-1]
     // the item's base pointers (per signal / per row), computed once per item by one thread: the span loop adds a
@@ -94,7 +113,10 @@ struct SweepSmem {
     void *ptr[kSweepPtrs];
     int keep[kSweepWarps][2];                  // extraction 0 without a scan stage: tau of a chunk's last two elements
     int knots_in[kSweepWarps];                 // ... and the input knots each warp found in its own spans
-    int ticket, zero_dx;
+    int ticket, zero_dx, dn;
+    // the item's scalars, parked here while the warps stream (reloaded afterwards: no register is held across the span loops)
+    int it_e, it_sig, it_sel, it_de, it_dsig, it_flags, it_k2;
+    unsigned long long t_start;
 };
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
@@ -137,14 +159,18 @@ __device__ __forceinline__ T ld_cg(const T *p) {
 // ITD.py:44-59 on x and -x) while it builds the record table of a chunk, straight into shared memory -- the input's
 // knot lists (0.56 knots per sample on the benchmark: 12 B written and 12 B read per knot) never exist, and the
 // stage that read the input just to find them is gone.
-enum { kLevel = 0, kScan = 1, kProbe = 2, kFirst = 3 };
+// kCount = extraction e run for its knots only (flag words, lists and counts of B_e are written; R_e and B_e are not): the
+// first pass of a fused pair.  kRecomp = B_e recomputed into row e + 1 (the trend row when a fused pair's second
+// extraction turns out to be the discarded one).
+enum { kLevel = 0, kScan = 1, kProbe = 2, kFirst = 3, kCount = 4, kRecomp = 5 };
 template <typename XT, typename CarryT, typename OutT, int KIND, bool BAS>
 __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<CarryT> &sm, const bool dense,
                                              const bool last, const int K, const int warp, const int lane,
                                              int &region_knots, int &input_knots, bool &zero_dx, bool &bad) {
     using A = Arith<CarryT>;
     constexpr int ITEMS = kSweepItems, SPAN = kSweepSpan;
-    constexpr bool SCAN = (KIND == kScan), PROBE = (KIND == kProbe), FIRST = (KIND == kFirst);
+    constexpr bool SCAN = (KIND == kScan), FIRST = (KIND == kFirst), COUNT = (KIND == kCount), RECOMP = (KIND == kRecomp);
+    constexpr bool PROBE = (KIND == kProbe) || RECOMP;               // no flag words, lists or carry are written
     const int n = p.n;
     const int sp0 = warp * p.spw;
     const int sp1 = min(sp0 + p.spw, p.spans);
@@ -426,7 +452,7 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
         if (have_right) xr = ld_cg(in_p() + tend);
         if (!SCAN && (!EDGE || sp + 1 < p.spans)) mn = ld_cg(reinterpret_cast<const uint4 *>(gmask_p() + (sp + 1) * ITEMS));
         {
-            const int pf = is_dense ? p.pf_dense : p.pf_sparse;
+            const int pf = COUNT ? p.pf_count : is_dense ? p.pf_dense : p.pf_sparse;
             if (pf > 0 && sp + pf < sp1 && lane < SPAN * (int)sizeof(XT) / 128)
                 prefetch_l2(in_p() + t0 + pf * SPAN + lane * (128 / (int)sizeof(XT)));
         }
@@ -464,13 +490,20 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
                 const CarryT xv = (CarryT)xc[r];
                 b[r] = A::add(sm.L[j], A::mul(sm.S[j], A::sub(xv, sm.X[j])));     // ITD.py:115-117
                 if (EDGE && t0 + r * 32 + lane >= n - 1) b[r] = (CarryT)0;        // ITD.py:112 (and the padding lanes)
+                if (COUNT && EDGE) {                                              // the end values of the next extraction's input
+                    const int t = t0 + r * 32 + lane;
+                    if (t <= 1) sm.bend[t] = b[r];
+                    if (t == n - 2 || t == n - 1) sm.bend[t - (n - 4)] = b[r];
+                }
             }
             OutT *rot = rot_p() + t0 + lane;
             if (PROBE) {
-                // candidate trend row: the input of this extraction (ITD.py:410-411)
+                // candidate trend row: the input of this extraction (ITD.py:410-411); kRecomp: its baseline
 #pragma unroll
                 for (int r = 0; r < ITEMS; ++r)
-                    if (!EDGE || t0 + r * 32 + lane < n) __stcs(rot + r * 32, (OutT)xc[r]);
+                    if (!EDGE || t0 + r * 32 + lane < n) __stcs(rot + r * 32, RECOMP ? (OutT)b[r] : (OutT)xc[r]);
+            } else if (COUNT) {
+                // nothing is stored: only the knots of B_e are wanted
             } else {
                 CarryT *carry = carry_p() + t0 + lane;
                 OutT *bas = BAS ? bas_p() + t0 + lane : nullptr;
@@ -572,6 +605,163 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
     region_knots = npos;
 }
 
+// ---------------------------------------------------------------------------------------------
+// one region of one signal, TWO extractions at once (few knots in both: records from the block's two tables).
+// Reads X_e once; writes R_e, R_{e+1} and B_{e+1}; B_e exists only in registers: 40 bytes per sample (8 for the
+// counting pass that found B_e's knots + 32 here) instead of 48 for two separate extractions.
+//   B_e[t]     = L_k + s_k (X_e[t] - X_k)           table A at index prefix[warp]  + knots of X_e at or before t
+//   B_{e+1}[t] = L'_k + s'_k (B_e[t] - X'_k)        table B at index offB + prefix2[warp] + knots of B_e at or before t
+// (ITD.py:115-119 twice); the extrema of B_{e+1} are the knots of extraction e + 2.
+// ---------------------------------------------------------------------------------------------
+template <typename CarryT, typename OutT, bool BAS>
+__device__ __forceinline__ void sweep_region_fused(const SweepParams &p, SweepSmem<CarryT> &sm, const int offB,
+                                                   const int warp, const int lane, int &region_knots) {
+    using A = Arith<CarryT>;
+    constexpr int ITEMS = kSweepItems, SPAN = kSweepSpan;
+    const int n = p.n;
+    const int sp0 = warp * p.spw;
+    const int sp1 = min(sp0 + p.spw, p.spans);
+    region_knots = 0;
+    if (sp0 >= sp1) return;
+    auto in_p = [&]() { return reinterpret_cast<const CarryT *>(sm.ptr[kPtrIn]); };
+    auto gmask_p = [&]() { return reinterpret_cast<const unsigned *>(sm.ptr[kPtrGmask]); };
+    auto gmask2_p = [&]() { return reinterpret_cast<const unsigned *>(sm.ptr[kPtrGmask2]); };
+    const int roff = warp * p.rs;
+    const int gA = sm.prefix[warp], gB = offB + sm.prefix2[warp];
+    const unsigned le_mask = 0xffffffffu >> (31 - lane);
+    auto recA = [&](const int j, const CarryT v) { return A::add(sm.L[j], A::mul(sm.S[j], A::sub(v, sm.X[j]))); };
+
+    int posA = 0, posB = 0, npos = 0;
+    CarryT bleft = (CarryT)0;                                        // B_{e+1} left of the span
+    CarryT xc[ITEMS];
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+        const int t = sp0 * SPAN + r * 32 + lane;
+        xc[r] = (t < n) ? ld_cg(in_p() + t) : (CarryT)0;
+    }
+    uint4 mc = ld_cg(reinterpret_cast<const uint4 *>(gmask_p() + sp0 * ITEMS));
+    uint4 mc2 = ld_cg(reinterpret_cast<const uint4 *>(gmask2_p() + sp0 * ITEMS));
+
+    auto span_body = [&](auto edge_tag, const int sp) {
+        constexpr bool EDGE = decltype(edge_tag)::value;
+        const int t0 = sp * SPAN, tend = t0 + SPAN;
+        const bool have_right = !EDGE || tend <= n - 1;
+        CarryT xr = (CarryT)0;
+        uint4 mn = make_uint4(0, 0, 0, 0), mn2 = make_uint4(0, 0, 0, 0);
+        if (have_right) xr = ld_cg(in_p() + tend);
+        if (!EDGE || sp + 1 < p.spans) {
+            mn = ld_cg(reinterpret_cast<const uint4 *>(gmask_p() + (sp + 1) * ITEMS));
+            mn2 = ld_cg(reinterpret_cast<const uint4 *>(gmask2_p() + (sp + 1) * ITEMS));
+        }
+        if (p.pf_fused > 0 && sp + p.pf_fused < sp1 && lane < SPAN * (int)sizeof(CarryT) / 128)
+            prefetch_l2(in_p() + t0 + p.pf_fused * SPAN + lane * (128 / (int)sizeof(CarryT)));
+
+        const unsigned mw[ITEMS] = {mc.x, mc.y, mc.z, mc.w}, mw2[ITEMS] = {mc2.x, mc2.y, mc2.z, mc2.w};
+        int wpre[ITEMS], wpre2[ITEMS];
+        wpre[0] = wpre2[0] = 0;
+#pragma unroll
+        for (int r = 1; r < ITEMS; ++r) {
+            wpre[r] = wpre[r - 1] + __popc(mw[r - 1]);
+            wpre2[r] = wpre2[r - 1] + __popc(mw2[r - 1]);
+        }
+        const int cnt = wpre[ITEMS - 1] + __popc(mw[ITEMS - 1]), cnt2 = wpre2[ITEMS - 1] + __popc(mw2[ITEMS - 1]);
+        const int fright = have_right ? (int)(mn.x & 1u) : 0, fright2 = have_right ? (int)(mn2.x & 1u) : 0;
+        const int ibA = gA + posA, ibB = gB + posB;
+
+        // ---- extraction e: B_e in registers, R_e to its row
+        CarryT b[ITEMS];
+        {
+            OutT *rot = reinterpret_cast<OutT *>(sm.ptr[kPtrRot]) + t0 + lane;
+            OutT *bas = BAS ? reinterpret_cast<OutT *>(sm.ptr[kPtrBas]) + t0 + lane : nullptr;
+#pragma unroll
+            for (int r = 0; r < ITEMS; ++r) {
+                b[r] = recA(ibA + wpre[r] + __popc(mw[r] & le_mask), xc[r]);
+                if (EDGE && t0 + r * 32 + lane >= n - 1) b[r] = (CarryT)0;       // ITD.py:112 (and the padding lanes)
+                if (!EDGE || t0 + r * 32 + lane < n) {
+                    __stcs(rot + r * 32, (OutT)A::sub(xc[r], b[r]));              // ITD.py:119
+                    if (BAS) __stcs(bas + r * 32, (OutT)b[r]);
+                }
+            }
+        }
+        // left neighbour of the region's first span (both levels), then the next span's samples
+        if (sp == sp0 && sp0 > 0) bleft = recA(ibB, recA(ibA, ld_cg(in_p() + t0 - 1)));
+        {
+            const CarryT *nx = in_p() + tend + lane;
+#pragma unroll
+            for (int r = 0; r < ITEMS; ++r) {
+                if (EDGE)
+                    xc[r] = (tend + r * 32 + lane < n) ? ld_cg(nx + r * 32) : (CarryT)0;
+                else
+                    xc[r] = ld_cg(nx + r * 32);
+            }
+        }
+        // ---- extraction e + 1 on B_e: R_{e+1} to its row, B_{e+1} to the carry
+        CarryT b2[ITEMS];
+        {
+            OutT *rot2 = reinterpret_cast<OutT *>(sm.ptr[kPtrRot2]) + t0 + lane;
+            OutT *bas2 = BAS ? reinterpret_cast<OutT *>(sm.ptr[kPtrBas2]) + t0 + lane : nullptr;
+            CarryT *carry = reinterpret_cast<CarryT *>(sm.ptr[kPtrCarry]) + t0 + lane;
+#pragma unroll
+            for (int r = 0; r < ITEMS; ++r) {
+                b2[r] = recA(ibB + wpre2[r] + __popc(mw2[r] & le_mask), b[r]);
+                if (EDGE && t0 + r * 32 + lane >= n - 1) b2[r] = (CarryT)0;
+                if (!EDGE || t0 + r * 32 + lane < n) {
+                    __stcs(rot2 + r * 32, (OutT)A::sub(b[r], b2[r]));
+                    __stwb(carry + r * 32, b2[r]);
+                    if (BAS) __stcs(bas2 + r * 32, (OutT)b2[r]);
+                }
+            }
+        }
+        CarryT bright = (CarryT)0;
+        if (have_right && (!EDGE || tend < n - 1))                               // both baselines end with 0 (ITD.py:112)
+            bright = recA(ibB + cnt2 + fright2, recA(ibA + cnt + fright, xr));
+
+        // ---- extrema of B_{e+1}: the flag words and knots of extraction e + 2
+        unsigned fw[ITEMS];
+        const int newc = span_extrema<EDGE, ITEMS, CarryT>(b2, bleft, bright, lane, t0, n, fw);
+        if (lane < ITEMS) {
+            unsigned v = fw[0];
+#pragma unroll
+            for (int r = 1; r < ITEMS; ++r) v = (lane == r) ? fw[r] : v;
+            __stwb(reinterpret_cast<unsigned *>(sm.ptr[kPtrNmask]) + sp * ITEMS + lane, v);
+        }
+        if (newc) {
+            int *ntau = reinterpret_cast<int *>(sm.ptr[kPtrNtau]) + roff + kSweepPre + npos;
+            CarryT *nxk = reinterpret_cast<CarryT *>(sm.ptr[kPtrNxk]) + roff + kSweepPre + npos;
+            const unsigned lt_mask = le_mask >> 1;
+            int pre = 0;
+#pragma unroll
+            for (int r = 0; r < ITEMS; ++r) {
+                if ((fw[r] >> lane) & 1u) {
+                    const int rank = pre + __popc(fw[r] & lt_mask);
+                    __stwb(ntau + rank, t0 + r * 32 + lane);
+                    __stwb(nxk + rank, b2[r]);
+                }
+                pre += __popc(fw[r]);
+            }
+        }
+        npos += newc;
+        posA += cnt;
+        posB += cnt2;
+        bleft = shfl_idx(b2[ITEMS - 1], 31);
+        mc = mn;
+        mc2 = mn2;
+    };
+
+    const int fast_end = min(sp1, n / SPAN - 1);
+    int sp = sp0;
+    while (sp < sp1) {
+        if (sp == 0 || sp >= fast_end) {
+            span_body(std::true_type{}, sp);
+            ++sp;
+            continue;
+        }
+#pragma unroll 1
+        for (; sp < fast_end; ++sp) span_body(std::false_type{}, sp);
+    }
+    region_knots = npos;
+}
+
 // zero or copy one output row (the knot-stop trend row, zero tails)
 template <typename OutT, typename CarryT>
 __device__ __forceinline__ void sweep_fill_row(OutT *dst, const CarryT *src, int n, bool zero) {
@@ -591,6 +781,14 @@ __device__ __forceinline__ void sweep_fill_row(OutT *dst, const CarryT *src, int
     }
 }
 
+// The scan-free extraction 0 (kFirst) is an experiment that lost (profiles/r2/README.md): it is compiled only with
+// -DPYITD_SWEEP_WITH_FUSED_SCAN (5000 SASS instructions that the default build does not carry).
+#ifdef PYITD_SWEEP_WITH_FUSED_SCAN
+__device__ __forceinline__ bool kFusedScan(const SweepParams &p) { return p.fused_scan != 0; }
+#else
+__device__ __forceinline__ constexpr bool kFusedScan(const SweepParams &) { return false; }
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // sweep_kernel
 // ---------------------------------------------------------------------------------------------
@@ -603,11 +801,69 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
     const int n = p.n, S = p.S;
     const bool depth = p.depth_first != 0;
     const long long n_items = depth ? (long long)S : (long long)(p.stage_last - p.stage_first + 1) * S;
-    int d_sig = -1, d_e = 0;                                   // depth-first cursor: the signal this CTA is working through
+    int d_sig = -1, d_e = 0, d_sel = 0;                        // depth-first cursor: the signal this CTA is working through
     // after an item: the next stage of the same signal, or (signal finished) a new ticket
-    auto advance = [&](const int e, const bool stopped) {
-        if (e == p.stage_last || (stopped && !(p.opts & kOptZeroTail))) d_sig = -1;
+    auto advance = [&](const int e, const bool stopped) {       // e: the last extraction this item completed
+        if (e >= p.stage_last || (stopped && !(p.opts & kOptZeroTail))) d_sig = -1;
         else d_e = e + 1;
+    };
+
+    // ---- the block's knot table {X, L, S}[off .. off + Kc + 1], one thread per knot (few knots) -----------------------
+    // lists: the signal's region lists; pre: knots before each region; el / ex: L and X at the two end knots
+    auto build_table = [&](const int off, const int Kc, const int *ctau, const CarryT *cxk, const int *pre,
+                           const CarryT *el, const CarryT *ex) {
+        auto slot_of = [&](const int g) -> long long {              // list slot of the interior knot with global rank g
+            int r = 0;
+#pragma unroll
+            for (int q = 1; q < kSweepWarps; ++q) r += (pre[q] < g) ? 1 : 0;
+            return (long long)r * p.rs + kSweepPre + (g - 1 - pre[r]);
+        };
+        int *taus = reinterpret_cast<int *>(sm.S + off);              // tau lives in S's storage until S is computed
+        for (int k = tid; k <= Kc + 1; k += blockDim.x) {
+            int tv;
+            CarryT xv;
+            if (k == 0) {
+                tv = 0;
+                xv = ex[0];
+            } else if (k == Kc + 1) {
+                tv = n - 1;
+                xv = ex[1];
+            } else {
+                const long long sl = slot_of(k);
+                tv = ld_cg(ctau + sl);
+                xv = ld_cg(cxk + sl);
+            }
+            taus[k] = tv;
+            sm.X[off + k] = xv;
+        }
+        __syncthreads();
+        for (int k = tid; k <= Kc + 1; k += blockDim.x) {
+            CarryT Lv;
+            if (k == 0) {
+                Lv = el[0];
+            } else if (k == Kc + 1) {
+                Lv = el[1];
+            } else {
+                const CarryT w = A::ratio(taus[k] - taus[k - 1], taus[k + 1] - taus[k - 1]);
+                const CarryT d = A::sub(sm.X[off + k + 1], sm.X[off + k - 1]);
+                const CarryT qq = A::add(sm.X[off + k - 1], A::mul(w, d));
+                Lv = A::add(A::mul((CarryT)0.5, qq), A::mul((CarryT)0.5, sm.X[off + k]));
+            }
+            sm.L[off + k] = Lv;
+        }
+        __syncthreads();
+        bool zdx = false;
+        for (int k = tid; k <= Kc + 1; k += blockDim.x) {
+            CarryT sl = (CarryT)0;
+            if (k <= Kc) {
+                const CarryT den = A::sub(sm.X[off + k + 1], sm.X[off + k]);
+                sl = A::div(A::sub(sm.L[off + k + 1], sm.L[off + k]), den);
+                zdx |= (den == (CarryT)0);
+            }
+            sm.S[off + k] = sl;                                    // overwrites tau words: see the barrier above
+        }
+        if (zdx) sm.zero_dx = 1;
+        __syncthreads();
     };
 
     for (;;) {
@@ -629,16 +885,23 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
             e = d_e;
             sig = d_sig;
         }
-        unsigned long long t_start = 0;
-        if (p.stage_ns && tid == 0) t_start = global_ns();
+        if (p.stage_ns && tid == 0) sm.t_start = global_ns();
 
         // ---- wait for the previous stage of this signal ----------------------------------------
-        if (e >= 0 && !(e == 0 && p.fused_scan) && (!depth || e == p.stage_first)) {
+        bool already = false;
+        if (e >= 0 && !(e == 0 && kFusedScan(p)) && (!depth || e == p.stage_first)) {
             if (tid == 0) {
-                while (ld_acquire(p.done + sig) < e + 1) __nanosleep(200);
+                int dn;
+                while (((dn = ld_acquire(p.done + sig)) & kSweepDoneAll) < e + 1) __nanosleep(200);
                 __threadfence();
+                sm.dn = dn;
             }
             __syncthreads();
+            // extraction e was the second of a fused pair (e - 1, e), or the signal has stopped
+            already = ((sm.dn & kSweepDoneAll) >= e + 2);
+            d_sel = (sm.dn >> 30) & 1;
+        } else if (e <= 0) {
+            d_sel = (e < 0) ? 1 : 0;                           // the scan writes tab[0]
         }
         const int se = (e >= 0) ? ld_cg(p.stop_e + sig) : kStopOpen;
         if (e > se) {
@@ -654,30 +917,44 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
             advance(e, true);
             continue;
         }
+        if (already) {
+            advance(e, se <= e);
+            continue;
+        }
 
         // ---- per-item setup: base pointers, region prefix, end values ------------------------------
+        // d_sel: which table holds the knots of this item's input (see SweepParams): it travels with done[] (bit 30) in
+        // stage-major order and in a register in signal-major order.  Everything the item needs later is parked in shared
+        // memory: nothing but e, sig and K stays in registers across the span loops.
         if (tid == 64) {
+            const int tsel = d_sel;
+            sm.it_e = e;
+            sm.it_sig = sig;
+            sm.it_sel = d_sel;
+            sm.it_de = d_e;
+            sm.it_dsig = d_sig;
             const long long koff = (long long)sig * p.kstride, moff = (long long)sig * p.mstride;
+            const SweepTable &cur = p.tab[tsel], &nxt = p.tab[tsel ^ 1];
+            const CarryT *x_in = reinterpret_cast<const CarryT *>(p.carry[tsel ^ 1]) + (long long)sig * n;     // X_e, e >= 1
             const long long row = (long long)sig * p.out_sig_stride + (long long)e * n;
-            const SweepTable &ct = p.tab[e & 1], &nt = p.tab[(e + 1) & 1];
-            sm.ptr[kPtrIn] = (e <= 0) ? (void *)(reinterpret_cast<const InT *>(p.x) + (long long)sig * n)
-                                      : (void *)(reinterpret_cast<CarryT *>(p.carry[(e - 1) & 1]) + (long long)sig * n);
+            sm.ptr[kPtrIn] = (e <= 0) ? (void *)(reinterpret_cast<const InT *>(p.x) + (long long)sig * n) : (void *)x_in;
             sm.ptr[kPtrRot] = reinterpret_cast<OutT *>(p.rot) + row;
             sm.ptr[kPtrBas] = BAS ? reinterpret_cast<OutT *>(p.bas) + row : nullptr;
-            sm.ptr[kPtrCarry] = reinterpret_cast<CarryT *>(p.carry[e & 1]) + (long long)sig * n;
-            sm.ptr[kPtrGmask] = ct.mask + moff;
-            sm.ptr[kPtrNmask] = nt.mask + moff;
-            sm.ptr[kPtrCtau] = ct.tau + koff;
-            sm.ptr[kPtrCxk] = reinterpret_cast<CarryT *>(ct.xk) + koff;
-            sm.ptr[kPtrNtau] = nt.tau + koff;
-            sm.ptr[kPtrNxk] = reinterpret_cast<CarryT *>(nt.xk) + koff;
+            sm.ptr[kPtrCarry] = reinterpret_cast<CarryT *>(p.carry[tsel]) + (long long)sig * n;
+            sm.ptr[kPtrGmask] = cur.mask + moff;
+            sm.ptr[kPtrNmask] = nxt.mask + moff;
+            sm.ptr[kPtrCtau] = cur.tau + koff;
+            sm.ptr[kPtrCxk] = reinterpret_cast<CarryT *>(cur.xk) + koff;
+            sm.ptr[kPtrNtau] = nxt.tau + koff;
+            sm.ptr[kPtrNxk] = reinterpret_cast<CarryT *>(nxt.xk) + koff;
         }
         int K = 0;
-        bool dense = false;
+        bool dense = false, can_fuse = false;
         if (e < 0) __syncthreads();
         if (e >= 0) {
-            const SweepTable &cur = p.tab[e & 1];
-            const bool first_fused = (e == 0) && p.fused_scan;
+            const bool first_fused = (e == 0) && kFusedScan(p);
+            const SweepTable &cur = p.tab[d_sel];
+            const long long koff = (long long)sig * p.kstride;
             if (tid == 0) {
                 int run = 0;
                 for (int r = 0; r < kSweepWarps; ++r) {
@@ -695,8 +972,8 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
                     const InT *xi = reinterpret_cast<const InT *>(p.x) + (long long)sig * n;
                     a0 = (CarryT)xi[0]; a1 = (CarryT)xi[1]; z0 = (CarryT)xi[n - 2]; z1 = (CarryT)xi[n - 1];
                 } else {
-                    const CarryT *xi = reinterpret_cast<const CarryT *>(p.carry[(e - 1) & 1]) + (long long)sig * n;
-                    a0 = ld_cg(xi); a1 = ld_cg(xi + 1); z0 = ld_cg(xi + n - 2); z1 = ld_cg(xi + n - 1);
+                    const CarryT *x_in = reinterpret_cast<const CarryT *>(p.carry[d_sel ^ 1]) + (long long)sig * n;
+                    a0 = ld_cg(x_in); a1 = ld_cg(x_in + 1); z0 = ld_cg(x_in + n - 2); z1 = ld_cg(x_in + n - 1);
                 }
                 sm.endl[0] = mean2<CarryT>(a0, a1);
                 sm.endl[1] = mean2<CarryT>(z0, z1);
@@ -706,17 +983,23 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
             __syncthreads();
             K = sm.prefix[kSweepWarps];
             dense = (K + 2 > SweepSmem<CarryT>::kCap);
-            const int *ctau = cur.tau + (long long)sig * p.kstride;
-            const CarryT *cxk = reinterpret_cast<const CarryT *>(cur.xk) + (long long)sig * p.kstride;
-            // list slot of the interior knot with global rank g (1 <= g <= K)
-            auto slot_of = [&](const int g) -> long long {
-                int r = 0;
-#pragma unroll
-                for (int q = 1; q < kSweepWarps; ++q) r += (sm.prefix[q] < g) ? 1 : 0;
-                return (long long)r * p.rs + kSweepPre + (g - 1 - sm.prefix[r]);
-            };
+#ifdef PYITD_SWEEP_NO_FUSE_CODE
+            can_fuse = false;
+#else
+            can_fuse = p.fuse && !dense && e >= 1 && K >= p.fuse_min_a && K + 2 <= p.fuse_max_a && e + 1 < p.emax &&
+                       e + 1 <= p.stage_last && (int)blockIdx.x < p.mid_ctas;
+#endif
+            const int *ctau = cur.tau + koff;
+            const CarryT *cxk = reinterpret_cast<const CarryT *>(cur.xk) + koff;
             if (dense) {
                 // ---- halo slots of every region list: the two knots before and the three after the region ----
+                // list slot of the interior knot with global rank g (1 <= g <= K)
+                auto slot_of = [&](const int g) -> long long {
+                    int r = 0;
+#pragma unroll
+                    for (int q = 1; q < kSweepWarps; ++q) r += (sm.prefix[q] < g) ? 1 : 0;
+                    return (long long)r * p.rs + kSweepPre + (g - 1 - sm.prefix[r]);
+                };
                 if (!first_fused && tid < kSweepWarps * (kSweepPre + kSweepPost)) {
                     const int r = tid / (kSweepPre + kSweepPost), h = tid % (kSweepPre + kSweepPost);
                     const int c = sm.prefix[r + 1] - sm.prefix[r];
@@ -741,63 +1024,17 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
                 }
                 __syncthreads();
             } else {
-                // ---- the block's knot table {X, L, S}[0 .. K+1], one thread per knot ----------------
-                int *taus = reinterpret_cast<int *>(sm.S);            // tau lives in S's storage until S is computed
-                for (int k = tid; k <= K + 1; k += blockDim.x) {
-                    int tv;
-                    CarryT xv;
-                    if (k == 0) {
-                        tv = 0;
-                        xv = sm.endx[0];
-                    } else if (k == K + 1) {
-                        tv = n - 1;
-                        xv = sm.endx[1];
-                    } else {
-                        const long long sl = slot_of(k);
-                        tv = ld_cg(ctau + sl);
-                        xv = ld_cg(cxk + sl);
-                    }
-                    taus[k] = tv;
-                    sm.X[k] = xv;
-                }
-                __syncthreads();
-                for (int k = tid; k <= K + 1; k += blockDim.x) {
-                    CarryT Lv;
-                    if (k == 0) {
-                        Lv = sm.endl[0];
-                    } else if (k == K + 1) {
-                        Lv = sm.endl[1];
-                    } else {
-                        const CarryT w = A::ratio(taus[k] - taus[k - 1], taus[k + 1] - taus[k - 1]);
-                        const CarryT d = A::sub(sm.X[k + 1], sm.X[k - 1]);
-                        const CarryT qq = A::add(sm.X[k - 1], A::mul(w, d));
-                        Lv = A::add(A::mul((CarryT)0.5, qq), A::mul((CarryT)0.5, sm.X[k]));
-                    }
-                    sm.L[k] = Lv;
-                }
-                __syncthreads();
-                bool zdx = false;
-                for (int k = tid; k <= K + 1; k += blockDim.x) {
-                    CarryT sl = (CarryT)0;
-                    if (k <= K) {
-                        const CarryT den = A::sub(sm.X[k + 1], sm.X[k]);
-                        sl = A::div(A::sub(sm.L[k + 1], sm.L[k]), den);
-                        zdx |= (den == (CarryT)0);
-                    }
-                    sm.S[k] = sl;                                      // overwrites tau[k] (and tau[k+1] for fp64): see the barrier below
-                }
-                if (zdx) sm.zero_dx = 1;
-                __syncthreads();
+                build_table(0, K, ctau, cxk, sm.prefix, sm.endl, sm.endx);
             }
         }
 
         // ---- stream the regions (no block barrier inside) ----------------------------------------
         int region_knots = 0;
         bool zero_dx = false, bad = false;
-        const bool last = (e == p.emax);
+        const bool last0 = (e == p.emax);
         // an extraction with at most kSweepProbeKnots knots is probably the discarded last one: probe it first
         bool probed_stop = false;
-        if (e >= 1 && !last && K <= kSweepProbeKnots) {
+        if (e >= 1 && !last0 && !can_fuse && K <= kSweepProbeKnots) {
             int unused = 0;
             sweep_region<CarryT, CarryT, OutT, kProbe, BAS>(p, sm, false, false, K, warp, lane, region_knots, unused, zero_dx, bad);
             if (lane == 0) sm.cnt[warp] = region_knots;
@@ -808,58 +1045,136 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
             probed_stop = (kp < p.min_extrema);
             __syncthreads();
         }
+        // ---- a fused pair: extractions e and e + 1 in two passes over X_e; B_e is never stored -------------------------
+        // pass 1 (kCount) evaluates B_e for its extrema only and leaves their lists and flag words in the CTA's scratch
+        // (8 bytes read per sample); pass 2 reads X_e again and writes R_e, R_{e+1}, B_{e+1} (32 bytes per sample): 40 bytes
+        // for two extractions instead of 48.  ITD.py:79-121 twice; the stop test of extraction e (ITD.py:404) is the
+        // count of pass 1.
+        int fused = 0, K2 = 0;
+        bool counted_stop = false;
+        if (can_fuse) {
+            if (tid == 64) {
+                sm.ptr[kPtrNmask] = p.mid_mask + (long long)blockIdx.x * p.mstride;
+                sm.ptr[kPtrNtau] = p.mid_tau + (long long)blockIdx.x * kSweepWarps * p.rs;
+                sm.ptr[kPtrNxk] = reinterpret_cast<CarryT *>(p.mid_xk) + (long long)blockIdx.x * kSweepWarps * p.rs;
+            }
+            __syncthreads();
+            int unused = 0;
+            sweep_region<CarryT, CarryT, OutT, kCount, BAS>(p, sm, false, false, K, warp, lane, region_knots, unused, zero_dx, bad);
+            if (lane == 0) sm.cnt[warp] = region_knots;
+            __syncthreads();
+            e = sm.it_e, sig = sm.it_sig, d_sel = sm.it_sel, d_e = sm.it_de, d_sig = sm.it_dsig, K = sm.prefix[kSweepWarps];
+#pragma unroll
+            for (int r = 0; r < kSweepWarps; ++r) K2 += sm.cnt[r];
+            if (K2 < p.min_extrema) {
+                counted_stop = true;                                   // extraction e is the discarded last one (ITD.py:404-411)
+                if (tid == 0) atomicAdd(p.stats + 1, 1);
+            } else {
+                const bool go = (K2 >= p.fuse_min_b) && (K + K2 + 4 <= SweepSmem<CarryT>::kCap);
+                if (tid == 0) {
+                    int run = 0;
+                    for (int r = 0; r < kSweepWarps; ++r) {
+                        sm.prefix2[r] = run;
+                        run += sm.cnt[r];
+                    }
+                    sm.prefix2[kSweepWarps] = run;
+                    sm.endl2[0] = mean2<CarryT>(sm.bend[0], sm.bend[1]);       // ITD.py:100-102 on B_e
+                    sm.endl2[1] = mean2<CarryT>(sm.bend[2], sm.bend[3]);
+                    sm.endx2[0] = sm.bend[0];
+                    sm.endx2[1] = sm.bend[3];
+                }
+                if (tid == 64) {
+                    const long long row2 = (long long)sig * p.out_sig_stride + (long long)(e + 1) * n;
+                    const long long koff = (long long)sig * p.kstride, moff = (long long)sig * p.mstride;
+                    const SweepTable &nxt = p.tab[d_sel ^ 1];
+                    sm.ptr[kPtrRot2] = reinterpret_cast<OutT *>(p.rot) + row2;
+                    sm.ptr[kPtrBas2] = BAS ? reinterpret_cast<OutT *>(p.bas) + row2 : nullptr;
+                    sm.ptr[kPtrGmask2] = p.mid_mask + (long long)blockIdx.x * p.mstride;
+                    sm.ptr[kPtrNmask] = nxt.mask + moff;
+                    sm.ptr[kPtrNtau] = nxt.tau + koff;
+                    sm.ptr[kPtrNxk] = reinterpret_cast<CarryT *>(nxt.xk) + koff;
+                }
+                __syncthreads();
+                if (tid == 0) atomicAdd(p.stats + (go ? 0 : 1), 1);
+                if (go) {
+                    build_table(K + 2, K2, p.mid_tau + (long long)blockIdx.x * kSweepWarps * p.rs,
+                                reinterpret_cast<const CarryT *>(p.mid_xk) + (long long)blockIdx.x * kSweepWarps * p.rs, sm.prefix2,
+                                sm.endl2, sm.endx2);
+                    sweep_region_fused<CarryT, OutT, BAS>(p, sm, K + 2, warp, lane, region_knots);
+                    fused = 1;
+                }
+            }
+        }
+        if (tid == 0) {
+            sm.it_flags = fused | (counted_stop ? 2 : 0) | (probed_stop ? 4 : 0);
+            sm.it_k2 = K2;
+        }
         int knots_in = 0;
-        if (probed_stop) {
-            // row e already holds the trend row; the region counts of the probe are the ones to report
+        if (probed_stop || counted_stop || fused) {
+            // probed_stop: row e already holds the trend row; the region counts of the probe / count are the ones to report
         } else if (e < 0) {
             sweep_region<InT, CarryT, OutT, kScan, BAS>(p, sm, false, false, 0, warp, lane, region_knots, knots_in, zero_dx, bad);
-        } else if (e == 0 && p.fused_scan) {
-            sweep_region<InT, CarryT, OutT, kFirst, BAS>(p, sm, true, last, K, warp, lane, region_knots, knots_in, zero_dx, bad);
+        } else if (e == 0 && kFusedScan(p)) {
+            sweep_region<InT, CarryT, OutT, kFirst, BAS>(p, sm, true, last0, K, warp, lane, region_knots, knots_in, zero_dx, bad);
             if (lane == 0) sm.knots_in[warp] = knots_in;
         } else if (std::is_same<InT, CarryT>::value || e > 0) {
-            sweep_region<CarryT, CarryT, OutT, kLevel, BAS>(p, sm, dense, last, K, warp, lane, region_knots, knots_in, zero_dx, bad);
+            sweep_region<CarryT, CarryT, OutT, kLevel, BAS>(p, sm, dense, last0, K, warp, lane, region_knots, knots_in, zero_dx, bad);
         } else {
-            sweep_region<InT, CarryT, OutT, kLevel, BAS>(p, sm, dense, last, K, warp, lane, region_knots, knots_in, zero_dx, bad);
+            sweep_region<InT, CarryT, OutT, kLevel, BAS>(p, sm, dense, last0, K, warp, lane, region_knots, knots_in, zero_dx, bad);
         }
-        if (lane == 0) sm.cnt[warp] = region_knots;
+        if (!counted_stop && lane == 0) sm.cnt[warp] = region_knots;
         if (__any_sync(0xffffffffu, zero_dx) && lane == 0) sm.zero_dx = 1;
         if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.status + sig, kStNonFinite);
         __syncthreads();
 
         // ---- end of the item: region counts, stop rule, trend row ---------------------------------
+        e = sm.it_e, sig = sm.it_sig, d_sel = sm.it_sel, d_e = sm.it_de, d_sig = sm.it_dsig, K = sm.prefix[kSweepWarps];
+        fused = sm.it_flags & 1, counted_stop = (sm.it_flags & 2) != 0, probed_stop = (sm.it_flags & 4) != 0, K2 = sm.it_k2;
+        const bool last = (e == p.emax);
+        const int ee = e + fused;                                      // the last extraction this item completed
         int Kn = 0;
 #pragma unroll
         for (int r = 0; r < kSweepWarps; ++r) Kn += sm.cnt[r];
-        const SweepTable &nxt = p.tab[(e + 1) & 1];
-        if (tid < kSweepWarps) nxt.rcount[(long long)sig * kSweepWarps + tid] = sm.cnt[tid];
+        if (tid < kSweepWarps) p.tab[d_sel ^ 1].rcount[(long long)sig * kSweepWarps + tid] = sm.cnt[tid];
         bool stop_knots = false;
         if (e < 0) {
             if (tid == 0 && p.input_knots) p.input_knots[sig] = Kn;
         } else {
             stop_knots = (Kn < p.min_extrema);                         // ITD.py:404
-            if (tid == 0 && e == 0 && p.fused_scan && p.input_knots) {
+            if (tid == 0 && e == 0 && kFusedScan(p) && p.input_knots) {
                 int kin = 0;
                 for (int r = 0; r < kSweepWarps; ++r) kin += sm.knots_in[r];
                 p.input_knots[sig] = kin;
             }
             if (tid == 0) {
                 if (sm.zero_dx) atomicOr(p.status + sig, kStZeroDx);
-                p.knot_counts[(long long)sig * p.rows + e] = Kn;       // what ITD.py:403 prints
+                if (fused) p.knot_counts[(long long)sig * p.rows + e] = K2;
+                p.knot_counts[(long long)sig * p.rows + ee] = Kn;      // what ITD.py:403 prints
                 if (stop_knots || last) {                              // ITD.py:404 / :418
                     p.stop_kind[sig] = stop_knots ? kStopKnots : kStopIter;
-                    p.n_rows[sig] = e + 1;
-                    p.stop_e[sig] = e;
+                    p.n_rows[sig] = ee + 1;
+                    p.stop_e[sig] = ee;
                 }
             }
-            if (stop_knots && !probed_stop) {
-                // the discarded extraction wrote R_e into row e; the reference returns baselines[e-1] there, i.e. the
-                // INPUT of this extraction (zeros when e == 0)  (ITD.py:410-411)
+            if (stop_knots && !probed_stop && !fused) {
+                // the discarded extraction wrote R_e into row e (nothing after a counting pass); the reference returns
+                // baselines[e-1] there, i.e. the INPUT of this extraction (zeros when e == 0)  (ITD.py:410-411)
                 OutT *rot = reinterpret_cast<OutT *>(p.rot) + (long long)sig * p.out_sig_stride + (long long)e * n;
-                const CarryT *src = (e == 0) ? nullptr : reinterpret_cast<const CarryT *>(p.carry[(e - 1) & 1]) + (long long)sig * n;
-                sweep_fill_row<OutT, CarryT>(rot, src, n, e == 0);
+                const CarryT *x_in = reinterpret_cast<const CarryT *>(p.carry[d_sel ^ 1]) + (long long)sig * n;
+                sweep_fill_row<OutT, CarryT>(rot, (e == 0) ? nullptr : x_in, n, e == 0);
+            }
+            if (stop_knots && fused) {
+                // the second extraction of the pair is the discarded one: row e + 1 is its input B_e, which was never
+                // stored -- evaluate it again from X_e and the first table (rare: one extra read and write of the signal)
+                if (tid == 64) sm.ptr[kPtrRot] = sm.ptr[kPtrRot2];
+                __syncthreads();
+                int u0 = 0, u1 = 0;
+                bool z = false, b = false;
+                sweep_region<CarryT, CarryT, OutT, kRecomp, BAS>(p, sm, false, false, K, warp, lane, u0, u1, z, b);
             }
             if (stop_knots && BAS && (p.opts & kOptZeroTail)) {
-                OutT *bas = reinterpret_cast<OutT *>(p.bas) + (long long)sig * p.out_sig_stride + (long long)e * n;
+                __syncthreads();
+                OutT *bas = reinterpret_cast<OutT *>(p.bas) + (long long)sig * p.out_sig_stride + (long long)ee * n;
                 sweep_fill_row<OutT, CarryT>(bas, nullptr, n, true);
             }
         }
@@ -867,10 +1182,11 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
         if (tid == 0) {
             __threadfence();
             // a stopped signal lets every later stage of it through at once (they only zero-fill on request)
-            st_release(p.done + sig, (e >= 0 && (stop_knots || last)) ? kSweepDoneAll : e + 2);
-            if (p.stage_ns) atomicAdd(p.stage_ns + (e + 1), global_ns() - t_start);
+            st_release(p.done + sig, ((e >= 0 && (stop_knots || last)) ? kSweepDoneAll : ee + 2) | ((d_sel ^ 1) << 30));
+            if (p.stage_ns) atomicAdd(p.stage_ns + (e + 1), global_ns() - sm.t_start);
         }
-        advance(e, e >= 0 && (stop_knots || last));
+        d_sel ^= 1;
+        advance(ee, e >= 0 && (stop_knots || last));
     }
 }
 

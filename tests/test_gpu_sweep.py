@@ -134,7 +134,10 @@ def test_ticket_scheduler_with_few_and_many_signals(S):
 @pytest.mark.parametrize("n", [5, 129, 1000, 4100, 8192, 20001, 40000])
 def test_separate_scan_stage_equals_scan_fused_into_extraction_0(n, monkeypatch):
     """PYITD_SWEEP_FUSED_SCAN=1: extraction 0 finds the knots of the raw input itself, chunk by chunk, straight into shared
-    memory (no scan stage, no knot lists of the input).  Same bytes as with the separate scan stage (the default)."""
+    memory (no scan stage, no knot lists of the input).  Same bytes as with the separate scan stage (the default).
+    The variant lost (profiles/r2/README.md) and is compiled only with -DPYITD_SWEEP_WITH_FUSED_SCAN."""
+    if not _capi.has_feature("sweep_fused_scan"):
+        pytest.skip("this build does not carry the scan-free extraction 0 (make EXTRA=-DPYITD_SWEEP_WITH_FUSED_SCAN)")
     rng = np.random.default_rng(7800 + n)
     x = _mixed_batch(rng, 13, n)
     a = check_against_oracle(x, max_iteration=11)
@@ -223,3 +226,58 @@ def test_repeated_calls_and_side_stream():
         for s in (0, 85, 169):
             assert torch.equal(r.rows_of(s), ref.rows_of(s))
     check_batch_against_c_oracle(ref, x.cpu().numpy(), 11, baselines=False)
+
+
+def _last_plan():
+    from pyitd_b200 import itd as _itd
+    return next(reversed(_itd._PLAN_CACHE.values()))
+
+
+@pytest.mark.parametrize("thr", [None, ("4", "1400", "1"), ("4", "60", "2"), ("200", "1990", "50")])
+@pytest.mark.parametrize("depth", ["0", "1"])
+def test_fused_pairs_equal_single_extractions(thr, depth, monkeypatch):
+    """Two consecutive few-knot extractions run as ONE item (a counting pass for the knots of B_e, then a pass that reads
+    X_e and writes R_e, R_{e+1}, B_{e+1}; B_e is never stored): same bytes as one item per extraction and as the oracle
+    (ITD.py:79-121 applied twice, stop tests ITD.py:404 in between).  The thresholds are moved so that every way out of a
+    pair is taken: fused, the first extraction is the discarded last one (count < min_extrema), the SECOND one is (row
+    e + 1 = B_e recomputed), too few / too many knots for a fused pass (ordinary pass after the count)."""
+    monkeypatch.setenv("PYITD_SWEEP_DEPTH", depth)
+    rng = np.random.default_rng(9100)
+    fused_total = unfused_total = 0
+    for S, n, mi in ((200, 16384, 11), (21, 65536, 11), (300, 2048, 11), (40, 5001, 5), (64, 8192, 20)):
+        x = _mixed_batch(rng, S, n) if n < 10000 else synth.eeg_like(S, n, seed=n + S, device="cpu").numpy()
+        monkeypatch.setenv("PYITD_SWEEP_FUSE", "0")
+        pyitd_b200.clear_plan_cache()
+        a = pyitd_b200.decompose(gpu(x), max_iteration=mi, return_baselines=True, zero_tail=True)
+        torch.cuda.synchronize()
+        assert _last_plan().sweep_stats() == (0, 0)
+        monkeypatch.setenv("PYITD_SWEEP_FUSE", "2")               # (2: also in signal-major order)
+        if thr is not None:
+            for k, v in zip(("MIN_A", "MAX_A", "MIN_B"), thr):
+                monkeypatch.setenv("PYITD_SWEEP_FUSE_" + k, v)
+        pyitd_b200.clear_plan_cache()
+        b = pyitd_b200.decompose(gpu(x), max_iteration=mi, return_baselines=True, zero_tail=True)
+        torch.cuda.synchronize()
+        f, u = _last_plan().sweep_stats()
+        fused_total += f
+        unfused_total += u
+        assert torch.equal(a.status, b.status)
+        ok = (a.status == 0).cpu().numpy()
+        okt = torch.from_numpy(ok).to(a.rotations.device)
+        assert torch.equal(a.rotations[okt], b.rotations[okt]), (S, n)
+        assert torch.equal(a.n_rows[okt], b.n_rows[okt]) and torch.equal(a.stop_kind[okt], b.stop_kind[okt])
+        assert torch.equal(a.knot_counts[okt], b.knot_counts[okt])
+        ab, bb = a.baselines.cpu().numpy(), b.baselines.cpu().numpy()
+        nr, kind = a.n_rows.cpu().numpy(), a.stop_kind.cpu().numpy()
+        for s_ in np.flatnonzero(ok):
+            nb = nr[s_] if kind[s_] == _capi.STOP_ITER else nr[s_] - 1          # the discarded extraction's baseline row is not defined
+            assert ab[s_, :nb].tobytes() == bb[s_, :nb].tobytes(), (S, n, s_)
+            assert not ab[s_, nr[s_]:].any() and not bb[s_, nr[s_]:].any()
+        # and the fused run against the oracle
+        for s_ in list(np.flatnonzero(ok)[:12]):
+            want = o.c_decompose(x[s_], mi)
+            assert b.rows_of(int(s_)).cpu().numpy().tobytes() == want.rotations.tobytes(), (S, n, s_)
+            assert b.baselines_of(int(s_)).cpu().numpy().tobytes() == want.baselines.tobytes(), (S, n, s_)
+    assert fused_total > 0
+    if thr is not None and thr[0] == "4":
+        assert unfused_total > 0
