@@ -96,6 +96,9 @@ PYITD_API int     pyitd_plan_sweep_stats(pyitd_plan *plan, int64_t *fused_pairs,
 #define PYITD_PATH_STRIDED  3
 #define PYITD_PATH_SWEEP    4   /* many signals: ONE persistent launch decomposes the whole batch, every level (ticket-
                                    scheduled (level, signal) items, one CTA per item, carry in HBM) */
+#define PYITD_PATH_COOP     5   /* up to 16 signals shorter than 2^18 samples (the reference's own use, ITD.py:500-503: ONE signal):
+                                   ONE cooperative launch, each signal kept in the shared memory of a group of CTAs, one group
+                                   barrier per extraction */
 PYITD_API int     pyitd_plan_path(const pyitd_plan *plan, int *cluster_size);
 
 /* Stream path only: cut the batch into `groups` contiguous signal ranges (1..16), each with its own launch

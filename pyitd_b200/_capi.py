@@ -168,10 +168,10 @@ class Plan:
 
     @property
     def path(self) -> tuple[str, int]:
-        """('resident' | 'stream' | 'lookback' | 'strided' | 'sweep', CTAs per cluster)."""
+        """('resident' | 'stream' | 'lookback' | 'strided' | 'sweep' | 'coop', CTAs per cluster)."""
         cl = ctypes.c_int(1)
         code = int(self._L.pyitd_plan_path(self.handle, ctypes.byref(cl)))
-        return {0: "lookback", 1: "stream", 2: "resident", 3: "strided", 4: "sweep"}[code], int(cl.value)
+        return {0: "lookback", 1: "stream", 2: "resident", 3: "strided", 4: "sweep", 5: "coop"}[code], int(cl.value)
 
     @property
     def groups(self) -> int:

@@ -16,6 +16,7 @@
 #include "itd_stream.cuh"
 #include "itd_strided.cuh"
 #include "itd_sweep.cuh"
+#include "itd_coop.cuh"
 #include "itd_resident.cuh"
 #include "itd_spline.cuh"
 #include "itd_sift2d.cuh"
@@ -73,6 +74,11 @@ struct pyitd_plan {
     bool sweep = false;
     int sw_spans = 0, sw_spw = 0, sw_rs = 0, sw_grid[2] = {0, 0};
     int *sw_ticket = nullptr, *sw_done = nullptr, *sw_rcount[2] = {nullptr, nullptr};
+    // a handful of signals: the whole decomposition in one cooperative launch with the signal on chip (itd_coop.cuh)
+    bool coop = false;
+    int coop_C = 0, coop_gsz = 0, coop_groups = 0;
+    int *coop_bar = nullptr;
+    void *coop_sum = nullptr;
     // fused pairs of extractions (itd_sweep.cuh): per-CTA scratch for the knots of the baseline between the two
     int sw_mid_ctas = 0, *sw_mid_tau = nullptr;
     void *sw_mid_xk = nullptr;
@@ -558,6 +564,24 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
     bool sweep = !pl->resident && !strided && n_signals >= 160 && n_samples >= 2048;
     if (const char *env = getenv("PYITD_FORCE_PATH")) sweep = !strcmp(env, "sweep");
     pl->sweep = sweep;
+    // up to 16 signals that the look-back kernels would take: one cooperative launch, signal on chip, one group barrier per
+    // extraction (PYITD_FORCE_PATH=lookback keeps the launch chain).  Chunk: about one CTA per SM for one signal.
+    {
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        long long C = (n_samples + sms - 1) / sms;
+        C = ((C + 255) / 256) * 256;
+        if (const char *env = getenv("PYITD_COOP_CHUNK")) {
+            const long long v = atoll(env);
+            if (v >= 256 && v % 256 == 0) C = v;
+        }
+        bool coop = !stream && !pl->resident && !strided && !sweep && n_signals <= 16 && n_samples >= 3 && C <= kCoopMaxChunk;
+        if (const char *env = getenv("PYITD_FORCE_PATH"))
+            coop = !strcmp(env, "coop") && n_signals <= 64 && n_samples >= 3 && C <= kCoopMaxChunk && !pl->resident;
+        pl->coop = coop;
+        pl->coop_C = (int)C;
+        pl->coop_gsz = (int)((n_samples + C - 1) / C);
+    }
     pl->sw_spans = (int)((n_samples + kSweepSpan - 1) / kSweepSpan);
     pl->sw_spw = (pl->sw_spans + kSweepWarps - 1) / kSweepWarps;
     pl->sw_rs = pl->sw_spw * kSweepSpan + 8;
@@ -711,6 +735,7 @@ extern "C" void pyitd_plan_destroy(pyitd_plan *pl) {
     if (pl->gfork) cudaEventDestroy(pl->gfork);
     cudaFree(pl->res_backup);
     cudaFree(pl->res_kind);
+    cudaFree(pl->coop_bar);
     cudaFree(pl->ws);
     delete pl;
 }
@@ -723,6 +748,7 @@ extern "C" int pyitd_plan_path(const pyitd_plan *pl, int *cluster_size) {
     if (cluster_size) *cluster_size = pl->resident ? pl->res_cl : 1;
     if (pl->strided) return PYITD_PATH_STRIDED;
     if (pl->sweep) return PYITD_PATH_SWEEP;
+    if (pl->coop) return PYITD_PATH_COOP;
     return pl->resident ? PYITD_PATH_RESIDENT : (pl->stream ? PYITD_PATH_STREAM : PYITD_PATH_LOOKBACK);
 }
 
@@ -864,6 +890,80 @@ static int run_resident(pyitd_plan *pl, const void *x, void *rotations, void *ba
 static int run_sweep(pyitd_plan *pl, const void *x, void *rotations, void *baselines, int32_t *n_rows,
                      int32_t *knot_counts, int32_t *input_knots, int *sk, int32_t *status, cudaStream_t st);
 
+// ---------------------------------------------------------------------------------------------
+// cooperative kernel: a handful of signals, each kept on chip by a group of CTAs (itd_coop.cuh)
+// ---------------------------------------------------------------------------------------------
+constexpr int kCoopNoFit = 12345;
+template <typename InT, typename CarryT, typename OutT>
+static int coop_launch_t(pyitd_plan *pl, CoopParams &p, bool bas, cudaStream_t st) {
+    auto k = bas ? coop_kernel<InT, CarryT, OutT, true> : coop_kernel<InT, CarryT, OutT, false>;
+    const size_t smem = coop_smem_bytes<CarryT>(pl->coop_C);
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!pl->coop_groups) {
+        int per_sm = 0, sms = 0, can = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kCoopThreads, smem));
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+        cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, pl->device);
+        long long groups = can ? (long long)per_sm * sms / pl->coop_gsz : 0;
+        if (groups > pl->S) groups = pl->S;
+        if (groups < 1) return kCoopNoFit;
+        const size_t b_bar = align_up((size_t)2 * groups * sizeof(int));
+        const size_t b_sum = (size_t)2 * groups * pl->coop_gsz * sizeof(CoopSummary<CarryT>);
+        void *mem = nullptr;
+        cudaError_t ce = cudaMalloc(&mem, b_bar + b_sum);
+        if (ce != cudaSuccess) {
+            cudaGetLastError();
+            return fail(PYITD_E_NOMEM, std::string("cooperative-path scratch allocation failed: ") + cudaGetErrorString(ce));
+        }
+        CU(cudaMemsetAsync(mem, 0, b_bar + b_sum, st));       // the kernel leaves the barrier counters at zero
+        pl->coop_bar = (int *)mem;
+        pl->coop_sum = (char *)mem + b_bar;
+        pl->coop_groups = (int)groups;
+        pl->ws_bytes += b_bar + b_sum;
+    }
+    p.bar = pl->coop_bar;
+    p.sum = pl->coop_sum;
+    p.ngroups = pl->coop_groups;
+    void *args[] = {(void *)&p};
+    CU(cudaLaunchCooperativeKernel((const void *)k, dim3((unsigned)(pl->coop_groups * pl->coop_gsz)), dim3(kCoopThreads), args,
+                                   smem, st));
+    return 0;
+}
+static int run_coop(pyitd_plan *pl, const void *x, void *rotations, void *baselines, int32_t *n_rows,
+                    int32_t *knot_counts, int32_t *input_knots, int32_t *stop_kind, int32_t *status, cudaStream_t st) {
+    CoopParams p = {};
+    p.x = x;
+    p.rot = rotations;
+    p.bas = baselines;
+    p.out_sig_stride = (long long)pl->rows * pl->n;
+    p.n_rows = n_rows;
+    p.knot_counts = knot_counts;
+    p.input_knots = input_knots;
+    p.stop_kind = stop_kind;
+    p.status = status;
+    p.S = (int)pl->S;
+    p.n = pl->n;
+    p.C = pl->coop_C;
+    p.gsz = pl->coop_gsz;
+    p.emax = pl->emax;
+    p.rows = pl->rows;
+    p.min_extrema = pl->min_extrema;
+    p.opts = pl->opts;
+    pl->launches = 0;
+    pl->events_used = 0;
+    if (int rc = mark(pl, st)) return rc;
+    const bool bas = baselines != nullptr;
+    int rc;
+    switch (pl->dtype) {
+        case PYITD_F64: rc = coop_launch_t<double, double, double>(pl, p, bas, st); break;
+        case PYITD_F32_MIXED: rc = coop_launch_t<float, double, float>(pl, p, bas, st); break;
+        default: rc = coop_launch_t<float, float, float>(pl, p, bas, st); break;
+    }
+    if (rc) return rc;
+    pl->launches = 1;
+    return mark(pl, st);
+}
+
 static int pyitd_decompose_device_impl(pyitd_plan *pl, const void *x, void *rotations, void *baselines,
                                       int32_t *n_rows, int32_t *knot_counts, int32_t *input_knots,
                                       int32_t *stop_kind, int32_t *status, void *stream) {
@@ -875,6 +975,11 @@ static int pyitd_decompose_device_impl(pyitd_plan *pl, const void *x, void *rota
     cudaStream_t st = (cudaStream_t)stream;
     if (pl->resident)
         return run_resident(pl, x, rotations, baselines, n_rows, knot_counts, input_knots, stop_kind, status, st);
+    if (pl->coop) {
+        const int rc = run_coop(pl, x, rotations, baselines, n_rows, knot_counts, input_knots, stop_kind, status, st);
+        if (rc != kCoopNoFit) return rc;
+        pl->coop = false;                                  // the device cannot hold a group: the look-back kernels take over
+    }
     if (int rc = ensure_workspace(pl, st)) return rc;
     pl->launches = 0;
     pl->events_used = 0;
@@ -973,10 +1078,14 @@ static int pyitd_decompose_device_impl(pyitd_plan *pl, const void *x, void *rota
 // ---------------------------------------------------------------------------------------------
 template <typename InT, typename CarryT, typename OutT>
 static cudaError_t sweep_launch_t(const SweepParams &p, bool bas, int *grid_cache, cudaStream_t st) {
-    constexpr size_t smem = 0;                            // the kernel's shared memory is static
+    constexpr size_t smem = kSweepDynSmem ? sizeof(SweepSmem<CarryT>) : 0;      // static up to 2000 table entries
     auto k = bas ? sweep_kernel<InT, CarryT, OutT, true> : sweep_kernel<InT, CarryT, OutT, false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
+    if (smem) {
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     if (*grid_cache == 0) {
         int per_sm = 0, dev = 0, sms = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kSweepWarps * 32, smem);

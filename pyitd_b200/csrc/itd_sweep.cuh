@@ -40,12 +40,18 @@ namespace pyitd {
 constexpr int kSweepWarps = 8;
 constexpr int kSweepItems = 4;
 constexpr int kSweepSpan = 32 * kSweepItems;          // samples per warp iteration
-constexpr int kSweepCap = 2000;                       // shared-memory knot table: K + 2 <= kSweepCap (static shared memory: 48 KB)
+#ifndef PYITD_SWEEP_CAP
+#define PYITD_SWEEP_CAP 2240
+#endif
+// shared-memory knot table: K + 2 <= kSweepCap.  Up to 2000 entries the kernel's shared memory is static (48 KB); above, it is
+// dynamic (opt-in size): 2240 entries = 54 KB is the most that still lets four CTAs share an SM.
+constexpr int kSweepCap = PYITD_SWEEP_CAP;
+constexpr bool kSweepDynSmem = (kSweepCap > 2000);
 constexpr int kSweepPre = 2, kSweepPost = 3;          // halo slots of a region list
 constexpr int kSweepScratch = kSweepCap / kSweepWarps;      // warp-private table entries of a many-knot item (>= span knots + 5)
 // fused pairs: extraction e with kSweepFuseMinA <= K and K + 2 <= kSweepFuseMaxA first COUNTS the knots of its baseline;
 // with at least kSweepFuseMinB of them (and both tables fitting the block's arrays) extractions e and e + 1 run as one pass
-constexpr int kSweepFuseMinA = 12, kSweepFuseMaxA = 1400, kSweepFuseMinB = 4;
+constexpr int kSweepFuseMinA = 12, kSweepFuseMaxA = 1640, kSweepFuseMinB = 4;
 constexpr int kSweepProbeKnots = 3;                   // extractions with at most this many knots are probed first
 static_assert(kSweepScratch >= kSweepSpan + 5, "a span's knots + 5 must fit a warp table");
 enum { kPtrIn = 0, kPtrRot, kPtrBas, kPtrCarry, kPtrGmask, kPtrNmask, kPtrCtau, kPtrCxk, kPtrNtau, kPtrNxk,
@@ -796,7 +802,12 @@ __device__ __forceinline__ constexpr bool kFusedScan(const SweepParams &) { retu
 template <typename InT, typename CarryT, typename OutT, bool BAS>
 __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepParams p) {
     using A = Arith<CarryT>;
+#if PYITD_SWEEP_CAP > 2000
+    extern __shared__ __align__(16) unsigned char sweep_smem_raw[];
+    SweepSmem<CarryT> &sm = *reinterpret_cast<SweepSmem<CarryT> *>(sweep_smem_raw);
+#else
     __shared__ SweepSmem<CarryT> sm;        // static: every shared-memory access is a compile-time offset
+#endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = p.n, S = p.S;
     const bool depth = p.depth_first != 0;

@@ -361,11 +361,12 @@ def test_default_path_by_shape():
     from pyitd_b200.itd import get_plan
     assert get_plan(0, 4096, 65536, _capi.F64, 11, 2, 0).path[0] == "sweep"
     assert get_plan(0, 64, 65536, _capi.F64, 11, 2, 0).path == ("resident", 4)
-    assert get_plan(0, 1, 65536, _capi.F64, 11, 2, 0).path[0] == "lookback"
+    assert get_plan(0, 1, 65536, _capi.F64, 11, 2, 0).path[0] == "coop"
     assert get_plan(0, 3515, 8192, _capi.F32_MIXED, 7, 2, 0).path[0] == "sweep"
     assert get_plan(0, 1, 1 << 22, _capi.F32, 11, 2, 0).path[0] == "strided"
     assert get_plan(0, 2, 1 << 22, _capi.F32, 11, 2, 0).path[0] == "strided"
-    assert get_plan(0, 2, 1 << 16, _capi.F32, 11, 2, 0).path[0] == "lookback"
+    assert get_plan(0, 2, 1 << 16, _capi.F32, 11, 2, 0).path[0] == "coop"
+    assert get_plan(0, 16, 1 << 17, _capi.F64, 11, 2, 0).path[0] == "coop"
     pyitd_b200.clear_plan_cache()
 
 

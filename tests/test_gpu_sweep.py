@@ -35,7 +35,7 @@ def test_sweep_is_the_default_for_big_batches(monkeypatch):
     assert get_plan(0, 3515, 8192, _capi.F32_MIXED, 7, 2, 0).path[0] == "sweep"
     assert get_plan(0, 200, 4098, _capi.F64, 11, 2, 0).path[0] == "sweep"          # rows need no alignment
     assert get_plan(0, 64, 65536, _capi.F64, 11, 2, 0).path[0] == "resident"
-    assert get_plan(0, 1, 65536, _capi.F64, 11, 2, 0).path[0] == "lookback"
+    assert get_plan(0, 1, 65536, _capi.F64, 11, 2, 0).path[0] == "coop"
 
 
 @pytest.mark.parametrize("n", [3, 4, 5, 31, 33, 127, 128, 129, 130, 255, 257, 1023, 1024, 1025, 1026, 1027, 2049, 4100,
