@@ -56,7 +56,9 @@ __global__ void __launch_bounds__(256) wpe3_kernel(const InT *__restrict__ rows,
         return;
     }
     const InT *x = rows + r * n;
-    double wc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    __shared__ double s_acc[6][256];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s_acc[k][threadIdx.x] = 0.0;
     unsigned seen = 0;                                     // bit k: pattern k occurred
     constexpr int UN = 4;                                  // windows in flight per thread (12 loads)
     const long long nwin = n - 2;
@@ -73,27 +75,39 @@ __global__ void __launch_bounds__(256) wpe3_kernel(const InT *__restrict__ rows,
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
             if (i0 + (long long)u * blockDim.x >= nwin) break;
-            // ascending hash order of MEITD.py:108: (2,1,0) (1,2,0) (2,0,1) (0,2,1) (1,0,2) (0,1,2)
-            const int slot = (a[u] <= b[u]) ? ((b[u] <= c[u]) ? 5 : ((a[u] <= c[u]) ? 3 : 2))
-                                            : ((a[u] <= c[u]) ? 4 : ((b[u] <= c[u]) ? 1 : 0));
-            const double mean = div3(__dadd_rn(__dadd_rn(a[u], b[u]), c[u]));
+            // ascending hash order of MEITD.py:108: (2,1,0) (1,2,0) (2,0,1) (0,2,1) (1,0,2) (0,1,2):
+            //   a <= b ? (b <= c ? 5 : (a <= c ? 3 : 2)) : (a <= c ? 4 : (b <= c ? 1 : 0))
+            // without branches (a six-way divergent branch tree per window is what the compiler made of the ternaries):
+            // three compare bits index a packed table
+            const unsigned idx = ((a[u] <= b[u]) ? 4u : 0u) | ((b[u] <= c[u]) ? 2u : 0u) | ((a[u] <= c[u]) ? 1u : 0u);
+            const int slot = (int)((0x55324140u >> (4u * idx)) & 7u);
+            // population variance of the window (MEITD.py:112-113).  The result is compared at 1e-9 absolute, not bit for
+            // bit (the reference's own summation order inside numpy.var is not specified), so the three squares are
+            // accumulated with fused multiply-adds and the two divisions by 3 are multiplications: 11 fp64 operations per
+            // window instead of 22 -- the kernel was bound by the fp64 pipe and the issue slots, not by HBM.
+            const double third = 1.0 / 3.0;
+            const double mean = __dmul_rn(__dadd_rn(__dadd_rn(a[u], b[u]), c[u]), third);
             const double d0 = __dsub_rn(a[u], mean), d1 = __dsub_rn(b[u], mean), d2 = __dsub_rn(c[u], mean);
-            const double w = div3(__dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2)));
+            const double w = __dmul_rn(__fma_rn(d2, d2, __fma_rn(d1, d1, __dmul_rn(d0, d0))), third);
             seen |= 1u << slot;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) wc[k] = __dadd_rn(wc[k], (slot == k) ? w : 0.0);
+            // the thread's six weighted counts live in shared memory, indexed by the pattern: one load, one add, one store
+            // per window instead of six selects and six additions
+            double *ap = &s_acc[slot][threadIdx.x];
+            *ap = __dadd_rn(*ap, w);
         }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the 256 per-thread sums of a pattern are added as a plain fp64 tree (a double-double tree here cost every thread 1500
+    // fp64 instructions per row, a fifth of the kernel, to protect sums whose 256 terms each were accumulated in plain fp64)
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        dd v = {wc[k], 0.0};
+        double v = s_acc[k][threadIdx.x];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = dd_add(v, dd_shfl_xor(v, o));
+        for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
         const int c = __any_sync(0xffffffffu, (seen >> k) & 1u);
         if (lane == 0) {
-            s_hi[warp][k] = v.hi;
-            s_lo[warp][k] = v.lo;
+            s_hi[warp][k] = v;
+            s_lo[warp][k] = 0.0;
             s_cnt[warp][k] = c;
         }
     }
