@@ -339,6 +339,62 @@ def extra_config(torch, dist, which: int, args, rank, world, local_rank, dev, pe
     del chunks, plans, rot, ints
     return out
 
+def config1_leg(torch, dev):
+    """BASELINE.json configs[0]: ONE 65 536-sample chirp+noise signal, the reference's own use (ITD.py:500-503).  Device time
+    of one decomposition (CUDA events around single calls, median), the wall time of the drop-in ITD().itd(x) call with host
+    arrays in and out, the oracle's C port on one host core beside it, and bit-exact parity of the rows."""
+    import numpy as np
+    import pyitd_b200
+    from oracle import itd_oracle as o
+    from pyitd_b200 import _capi, synth
+    from pyitd_b200.itd import get_plan
+    x = synth.config1_chirp()
+    N, mi = int(x.shape[0]), 20
+    plan = get_plan(dev.index, 1, N, _capi.F64, mi, 2, 0)
+    xg = torch.from_numpy(x).to(dev).view(1, N)
+    rot = torch.empty((1, plan.rows, N), dtype=torch.float64, device=dev)
+    ints = [torch.zeros(plan.rows if i == 1 else 1, dtype=torch.int32, device=dev) for i in range(5)]
+    st = torch.cuda.current_stream(dev)
+
+    def step():
+        plan.decompose_device(xg.data_ptr(), rot.data_ptr(), None, ints[0].data_ptr(), ints[1].data_ptr(),
+                              ints[2].data_ptr(), ints[3].data_ptr(), ints[4].data_ptr(), st.cuda_stream)
+
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize(dev)
+    us = []
+    for _ in range(100):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        step()
+        e1.record(st)
+        torch.cuda.synchronize(dev)
+        us.append(e0.elapsed_time(e1) * 1e3)
+    us.sort()
+    launches, path = plan.launches, plan.path[0]
+    itd = pyitd_b200.ITD()
+    itd.itd(x, max_iteration=mi)
+    wall = []
+    for _ in range(20):
+        t0 = time.perf_counter()
+        rows = itd.itd(x, max_iteration=mi)
+        wall.append(time.perf_counter() - t0)
+    wall.sort()
+    t0 = time.perf_counter()
+    want = o.c_decompose(x, mi)
+    cpu_s = time.perf_counter() - t0
+    return {"workload": "configs[0]: ONE 65536-sample chirp+noise signal, fp64, knot-count stop (max_iteration=20)",
+            "kernel_path": path, "launches_per_call": launches, "rows": int(rows.shape[0]),
+            "device_us_median": us[len(us) // 2], "device_us_min": us[0],
+            "value": N / (us[len(us) // 2] * 1e-6), "unit": UNIT,
+            "dropin_call_ms_median": wall[len(wall) // 2] * 1e3,
+            "dropin_api": "pyitd_b200.ITD().itd(numpy x): host array in, host rows out (H2D + one launch + D2H inside)",
+            "cpu_port_one_core_ms": cpu_s * 1e3,
+            "parity": {"bit_exact": bool(rows.tobytes() == want.rotations.tobytes()),
+                       "checked": "every row of the drop-in call vs oracle/itd_oracle.c (ITD.py:351-433)"}}
+
+
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
@@ -614,6 +670,11 @@ def main():
             extra["config5"] = {"error": repr(ex)}
         if world == 1:
             del x
+            try:
+                pyitd_b200.clear_plan_cache()
+                extra["config1"] = config1_leg(torch, dev)
+            except Exception as ex:
+                extra["config1"] = {"error": repr(ex)}
             for which, name in ((4, "config4"), (3, "config3")):
                 try:
                     pyitd_b200.clear_plan_cache()

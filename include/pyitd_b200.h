@@ -77,14 +77,15 @@ PYITD_API void pyitd_plan_destroy(pyitd_plan *plan);
 PYITD_API int     pyitd_plan_rows(const pyitd_plan *plan);             /* max_iteration + 2 */
 PYITD_API int64_t pyitd_plan_workspace_bytes(const pyitd_plan *plan);
 PYITD_API int     pyitd_plan_launches(const pyitd_plan *plan);         /* kernel launches of the last call */
-/* Sweep path, last call (synchronises with the device): how many PAIRS of extractions ran as one fused item (the baseline
- * between them never stored: two passes over X_e, 40 bytes per sample instead of 48 for ITD.py:79-121 twice), and how many
- * counting passes were not followed by a fused pass (the extraction turned out to be the last, or its baseline had too few
- * or too many knots).  PYITD_SWEEP_FUSE=0 at plan creation turns fused pairs off. */
 /* Optional code paths of this build: "sweep_fused_pairs" (always), "sweep_fused_scan" (the scan-free extraction 0 experiment,
  * only with -DPYITD_SWEEP_WITH_FUSED_SCAN).  1 if compiled in, else 0. */
 PYITD_API int     pyitd_has_feature(const char *name);
-PYITD_API int     pyitd_plan_sweep_stats(pyitd_plan *plan, int64_t *fused_pairs, int64_t *unfused_counts);
+/* Sweep path, last call (synchronises with the device): how many PAIRS of extractions ran as one fused item (the baseline
+ * between them never stored: one pass over X_e, 32 bytes per sample instead of 48 for ITD.py:79-121 twice; the knots of
+ * that baseline are predicted from the knot table and the pass checks the prediction on every sample), how many pairs were
+ * not tried after the prediction (too few or too many knots), and how many fused passes failed their check (the extraction
+ * was then redone on its own; that signal tries no further pairs).  PYITD_SWEEP_FUSE=0 at plan creation turns pairs off. */
+PYITD_API int     pyitd_plan_sweep_stats(pyitd_plan *plan, int64_t *fused_pairs, int64_t *pairs_skipped, int64_t *pairs_failed);
 /* Which kernel family pyitd_decompose_* uses for this shape: PYITD_PATH_RESIDENT (signal kept on chip by a
  * thread-block cluster, one launch per batch), PYITD_PATH_STREAM (one CTA per signal, carry in HBM) or
  * PYITD_PATH_LOOKBACK (one CTA per tile with a look-back chain, carry in HBM: a handful of signals) or

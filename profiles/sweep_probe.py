@@ -60,7 +60,7 @@ def main():
            "rows_mean": float(ints[0].double().mean()), "status_max": int(ints[4].max()),
            "env": {k: v for k, v in os.environ.items() if k.startswith("PYITD_")}}
     if plan.path[0] == "sweep" and hasattr(plan._L, "pyitd_plan_sweep_stats"):
-        out["fused_pairs"], out["unfused_counts"] = plan.sweep_stats()
+        out["fused_pairs"], out["pairs_skipped"], out["pairs_failed"] = plan.sweep_stats()
     if args.per_stage:
         plan.enable_timing(True)
         acc = None

@@ -75,7 +75,7 @@ def lib() -> ctypes.CDLL:
         L.pyitd_has_feature.argtypes = [ctypes.c_char_p]
     if hasattr(L, "pyitd_plan_sweep_stats"):           # (absent from older builds used in A/B measurements)
         L.pyitd_plan_sweep_stats.restype = ci
-        L.pyitd_plan_sweep_stats.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+        L.pyitd_plan_sweep_stats.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)]
     L.pyitd_plan_path.restype = ci
     L.pyitd_plan_path.argtypes = [vp, ctypes.POINTER(ci)]
     L.pyitd_plan_set_groups.restype = ci
@@ -160,11 +160,13 @@ class Plan:
     def launches(self) -> int:
         return int(self._L.pyitd_plan_launches(self.handle))
 
-    def sweep_stats(self) -> tuple[int, int]:
-        """(pairs of extractions fused into one item, counting passes without a fused pass) of the last call."""
-        a, b = ctypes.c_int64(0), ctypes.c_int64(0)
-        check(self._L.pyitd_plan_sweep_stats(self.handle, ctypes.byref(a), ctypes.byref(b)), "pyitd_plan_sweep_stats")
-        return int(a.value), int(b.value)
+    def sweep_stats(self) -> tuple[int, int, int]:
+        """(pairs of extractions fused into one item, pairs not tried after the knot prediction, fused passes whose check of
+        the prediction failed) of the last call."""
+        a, b, c = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+        check(self._L.pyitd_plan_sweep_stats(self.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)),
+              "pyitd_plan_sweep_stats")
+        return int(a.value), int(b.value), int(c.value)
 
     @property
     def path(self) -> tuple[str, int]:

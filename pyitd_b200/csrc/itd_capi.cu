@@ -80,8 +80,7 @@ struct pyitd_plan {
     int *coop_bar = nullptr;
     void *coop_sum = nullptr;
     // fused pairs of extractions (itd_sweep.cuh): per-CTA scratch for the knots of the baseline between the two
-    int sw_mid_ctas = 0, *sw_mid_tau = nullptr;
-    void *sw_mid_xk = nullptr;
+    int sw_mid_ctas = 0;
     unsigned *sw_mid_mask = nullptr;
     unsigned long long *sw_stage_ns = nullptr;
     int strided_cap = 0;      // test hook: upper bound on the persistent grid (PYITD_STRIDED_CTAS)
@@ -630,8 +629,8 @@ static int ensure_workspace(pyitd_plan *pl, cudaStream_t st) {
     const int ls_div = getenv("PYITD_LS_DIV") ? (atoi(getenv("PYITD_LS_DIV")) > 1 ? atoi(getenv("PYITD_LS_DIV")) : 16) : 16;   // experiment hook (n/16 measured best: profiles/r1/s5/ls_probe2.log)
     pl->lscap = (ls_on && (pl->stream || pl->strided)) ? (int)((pl->n / ls_div) & ~1ll) : 0;   // even: float rows stay 16-byte aligned
     const size_t b_ls = pl->lscap ? align_up((size_t)pl->S * (size_t)(pl->lscap + 4) * 2 * pl->carry_elem) : 0;
-    // sweep path: ticket slots, done[] + sel[] (one memset clears both), region counts, stage clocks, and the per-CTA scratch of
-    // the fused pairs (PYITD_SWEEP_FUSE=0 turns them off): 4 CTAs per SM is the kernel's launch bound
+    // sweep path: ticket slots, done[], region counts, stage clocks, and the per-CTA flag-word scratch of the fused pairs
+    // (PYITD_SWEEP_FUSE=0 turns them off): 4 CTAs per SM is the kernel's launch bound
     int mid_ctas = 0;
     if (pl->sweep && !(getenv("PYITD_SWEEP_FUSE") && atoi(getenv("PYITD_SWEEP_FUSE")) == 0)) {
         int sms = 0;
@@ -639,9 +638,7 @@ static int ensure_workspace(pyitd_plan *pl, cudaStream_t st) {
         mid_ctas = 4 * sms;
         if ((long long)mid_ctas > pl->S) mid_ctas = (int)pl->S;
     }
-    const size_t mid_list = (size_t)kSweepWarps * (size_t)pl->sw_rs;
-    const size_t b_mid = align_up((size_t)mid_ctas * mid_list * sizeof(int)) + align_up((size_t)mid_ctas * mid_list * pl->carry_elem) +
-                         align_up((size_t)mid_ctas * (size_t)mstride * sizeof(unsigned));
+    const size_t b_mid = align_up((size_t)mid_ctas * (size_t)mstride * sizeof(unsigned));
     const size_t b_sweep = pl->sweep ? align_up((size_t)(pl->rows + 4) * sizeof(int)) + align_up((size_t)pl->S * 2 * sizeof(int)) +
                                            2 * align_up((size_t)pl->S * kSweepWarps * sizeof(int)) +
                                            align_up((size_t)(pl->rows + 2) * sizeof(unsigned long long)) + b_mid
@@ -691,11 +688,7 @@ static int ensure_workspace(pyitd_plan *pl, cudaStream_t st) {
         for (int i = 0; i < 2; ++i) pl->sw_rcount[i] = (int *)take(align_up((size_t)pl->S * kSweepWarps * sizeof(int)));
         pl->sw_stage_ns = (unsigned long long *)take(align_up((size_t)(pl->rows + 2) * sizeof(unsigned long long)));
         pl->sw_mid_ctas = mid_ctas;
-        if (mid_ctas) {
-            pl->sw_mid_tau = (int *)take(align_up((size_t)mid_ctas * mid_list * sizeof(int)));
-            pl->sw_mid_xk = take(align_up((size_t)mid_ctas * mid_list * pl->carry_elem));
-            pl->sw_mid_mask = (unsigned *)take(align_up((size_t)mid_ctas * (size_t)mstride * sizeof(unsigned)));
-        }
+        if (mid_ctas) pl->sw_mid_mask = (unsigned *)take(b_mid);
     }
     // the mask rows are padded to 4 words: the padding (and everything else) starts out as "no knot"
     // on the CALLER's stream: a cudaStreamNonBlocking stream is not ordered after the legacy default stream, so a
@@ -1126,9 +1119,7 @@ static int run_sweep(pyitd_plan *pl, const void *x, void *rotations, void *basel
     sp.kstride = pl->table[0].kstride;
     sp.mstride = pl->table[0].mstride;
     sp.done = pl->sw_done;
-    sp.stats = pl->sw_ticket + pl->rows + 2;               // (zeroed with the ticket slots)
-    sp.mid_tau = pl->sw_mid_tau;
-    sp.mid_xk = pl->sw_mid_xk;
+    sp.stats = pl->sw_ticket + pl->rows + 1;               // three counters behind the ticket slots (zeroed with them)
     sp.mid_mask = pl->sw_mid_mask;
     sp.mid_ctas = pl->sw_mid_ctas;
     // PYITD_SWEEP_FUSE=0: every extraction is an item of its own (the round-2 v6 behaviour); thresholds: itd_sweep.cuh
@@ -1138,6 +1129,7 @@ static int run_sweep(pyitd_plan *pl, const void *x, void *rotations, void *basel
     sp.fuse_min_b = getenv("PYITD_SWEEP_FUSE_MIN_B") ? atoi(getenv("PYITD_SWEEP_FUSE_MIN_B")) : kSweepFuseMinB;
     if (sp.fuse_min_a <= kSweepProbeKnots) sp.fuse_min_a = kSweepProbeKnots + 1;
     if (sp.fuse_min_b < 1) sp.fuse_min_b = 1;
+    if (sp.fuse_max_a > kSweepFuseMaxLimit) sp.fuse_max_a = kSweepFuseMaxLimit;
     sp.stop_e = pl->stop_e;
     sp.stop_kind = sk;
     sp.n_rows = n_rows;
@@ -1160,7 +1152,6 @@ static int run_sweep(pyitd_plan *pl, const void *x, void *rotations, void *basel
     sp.pf_sparse = getenv("PYITD_SWEEP_PF_SPARSE") ? atoi(getenv("PYITD_SWEEP_PF_SPARSE")) : 3;
     sp.pf_scan = getenv("PYITD_SWEEP_PF_SCAN") ? atoi(getenv("PYITD_SWEEP_PF_SCAN")) : 4;
     sp.pf_dense = getenv("PYITD_SWEEP_PF_DENSE") ? atoi(getenv("PYITD_SWEEP_PF_DENSE")) : 2;
-    sp.pf_count = getenv("PYITD_SWEEP_PF_COUNT") ? atoi(getenv("PYITD_SWEEP_PF_COUNT")) : 3;
     sp.pf_fused = getenv("PYITD_SWEEP_PF_FUSED") ? atoi(getenv("PYITD_SWEEP_PF_FUSED")) : 2;
     // short signals: signal-major order keeps each CTA's carry / flags / knot lists in L2 between its stages (all
     // resident CTAs' carries must fit comfortably: 592 CTAs x n x carry bytes <= 48 MB, i.e. n <= ~10 000 fp64 samples)
@@ -1218,14 +1209,15 @@ extern "C" int pyitd_has_feature(const char *name) {
     return 0;
 }
 
-extern "C" int pyitd_plan_sweep_stats(pyitd_plan *pl, int64_t *fused_pairs, int64_t *unfused_counts) {
-    if (!pl || !fused_pairs || !unfused_counts) return fail(PYITD_E_INVALID, "null argument");
+extern "C" int pyitd_plan_sweep_stats(pyitd_plan *pl, int64_t *fused_pairs, int64_t *pairs_skipped, int64_t *pairs_failed) {
+    if (!pl || !fused_pairs || !pairs_skipped || !pairs_failed) return fail(PYITD_E_INVALID, "null argument");
     if (!pl->sweep || !pl->ws) return fail(PYITD_E_INVALID, "the plan has not run the sweep kernel");
     DeviceGuard guard(pl->device);
-    int v[2] = {0, 0};
-    CU(cudaMemcpy(v, pl->sw_ticket + pl->rows + 2, sizeof(v), cudaMemcpyDeviceToHost));      // waits for the device
+    int v[3] = {0, 0, 0};
+    CU(cudaMemcpy(v, pl->sw_ticket + pl->rows + 1, sizeof(v), cudaMemcpyDeviceToHost));      // waits for the device
     *fused_pairs = v[0];
-    *unfused_counts = v[1];
+    *pairs_skipped = v[1];
+    *pairs_failed = v[2];
     return 0;
 }
 

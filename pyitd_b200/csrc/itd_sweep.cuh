@@ -49,14 +49,16 @@ constexpr int kSweepCap = PYITD_SWEEP_CAP;
 constexpr bool kSweepDynSmem = (kSweepCap > 2000);
 constexpr int kSweepPre = 2, kSweepPost = 3;          // halo slots of a region list
 constexpr int kSweepScratch = kSweepCap / kSweepWarps;      // warp-private table entries of a many-knot item (>= span knots + 5)
-// fused pairs: extraction e with kSweepFuseMinA <= K and K + 2 <= kSweepFuseMaxA first COUNTS the knots of its baseline;
-// with at least kSweepFuseMinB of them (and both tables fitting the block's arrays) extractions e and e + 1 run as one pass
+// fused pairs: for extraction e with kSweepFuseMinA <= K and K + 2 <= kSweepFuseMaxA the knots of its baseline are PREDICTED
+// from the table (see sweep_kernel); with at least kSweepFuseMinB of them (and both tables fitting the block's arrays)
+// extractions e and e + 1 run as one pass that also checks the prediction
 constexpr int kSweepFuseMinA = 12, kSweepFuseMaxA = 1640, kSweepFuseMinB = 4;
+constexpr int kSweepFuseMaxLimit = 1780;              // the prediction step handles at most this many knots
 constexpr int kSweepProbeKnots = 3;                   // extractions with at most this many knots are probed first
 static_assert(kSweepScratch >= kSweepSpan + 5, "a span's knots + 5 must fit a warp table");
 enum { kPtrIn = 0, kPtrRot, kPtrBas, kPtrCarry, kPtrGmask, kPtrNmask, kPtrCtau, kPtrCxk, kPtrNtau, kPtrNxk,
        kPtrRot2, kPtrBas2, kPtrGmask2, kSweepPtrs };
-constexpr int kSweepDoneAll = 0x3fffffff;             // done[] value of a signal that has stopped
+constexpr int kSweepDoneAll = 0x0fffffff;             // done[] value (low 28 bits) of a signal that has stopped
 
 struct SweepTable {
     int *tau;            // [S, 8 * rs]  region r at r * rs: kSweepPre halo slots, the region's knots in order, kSweepPost halo slots
@@ -72,17 +74,17 @@ struct SweepParams {
     // carry[sel ^ 1]; it writes the last baseline it computes to carry[sel] and that baseline's knots to tab[sel ^ 1].
     void *carry[2];      // [S, N] carry type
     SweepTable tab[2];
-    // fused pair (e, e + 1): the knots of B_e live only between the two passes of one item, in the CTA's own scratch
-    int *mid_tau;        // [mid_ctas, 8 * rs]
-    void *mid_xk;        // [mid_ctas, 8 * rs] carry type
+    // fused pair (e, e + 1): the flag words of B_e's knots, in the CTA's own scratch
     unsigned *mid_mask;  // [mid_ctas, mstride]
     int mid_ctas;        // CTAs the scratch was sized for (0: no fused pairs)
-    int *stats;          // [2] pairs of extractions fused; counting passes that did not end in a fused pass
+    int *stats;          // [3] pairs of extractions fused; pairs not tried after the prediction (too few / too many knots);
+                         //     fused passes whose check failed (the extraction was redone on its own)
     void *rot, *bas;     // [S, rows, N] output type; bas may be null
     long long out_sig_stride;
     long long kstride, mstride;
     int *ticket;         // [1]  zeroed before the launch
-    int *done;           // [S]  stages completed: 1 after the scan, e + 2 after extraction e; bit 30: the table selector
+    int *done;           // [S]  stages completed: 1 after the scan, e + 2 after extraction e; bit 30: the table selector;
+                         //      bit 28: a fused pair of this signal failed its check once -- no further pairs are tried
     int *stop_e, *stop_kind, *n_rows, *knot_counts, *status, *input_knots;
     unsigned long long *stage_ns;   // optional [rows + 1]: CTA-nanoseconds spent per stage (index stage + 1)
     int S, n;
@@ -92,7 +94,7 @@ struct SweepParams {
     unsigned opts;
     int pf_scan;                   // ... of the input scan inside extraction 0
     int pf_sparse, pf_dense;       // L2 prefetch distance of the sample stream in spans (0: none), few / many knots
-    int pf_count, pf_fused;        // ... of the two passes of a fused pair (the counting pass writes next to nothing)
+    int pf_fused;                  // ... of the pass of a fused pair
     // item order.  0: stage-major tickets (every signal's stage e before any signal's stage e + 1; an item waits for its
     // signal's previous stage through done[]).  1: a ticket is a SIGNAL and the CTA runs all of its stages back to back:
     // the carry, flag words and knot lists it reads were written by the same CTA a few microseconds earlier and are
@@ -111,7 +113,8 @@ struct SweepSmem {
     int prefix[kSweepWarps + 1];               // knots before each region (prefix[8] = K)
     int prefix2[kSweepWarps + 1];              // fused pair: the same for the knots of B_e
     CarryT endl2[2], endx2[2];                 // ... and its end values
-    CarryT bend[4];                            // B_e at samples 0, 1, n-2, n-1 (written by the counting pass)
+    CarryT xe[4];                              // X_e at samples 0, 1, n-2, n-1
+    int pred_bad;                              // fused pair: an extremum of B_e away from the predicted knots was seen
     int cnt[kSweepWarps];                      // next level's knots per region
     CarryT endl[2], endx[2];                   // L_0, L_{K+1} (ITD.py:101-102); X_0 = in[0], X_{K+1} = in[n-1]
     // the item's base pointers (per signal / per row), computed once per item by one thread: the span loop adds a
@@ -121,7 +124,7 @@ struct SweepSmem {
     int knots_in[kSweepWarps];                 // ... and the input knots each warp found in its own spans
     int ticket, zero_dx, dn;
     // the item's scalars, parked here while the warps stream (reloaded afterwards: no register is held across the span loops)
-    int it_e, it_sig, it_sel, it_de, it_dsig, it_flags, it_k2;
+    int it_e, it_sig, it_sel, it_de, it_dsig, it_flags, it_k2, it_nofuse;
     unsigned long long t_start;
 };
 
@@ -165,17 +168,16 @@ __device__ __forceinline__ T ld_cg(const T *p) {
 // ITD.py:44-59 on x and -x) while it builds the record table of a chunk, straight into shared memory -- the input's
 // knot lists (0.56 knots per sample on the benchmark: 12 B written and 12 B read per knot) never exist, and the
 // stage that read the input just to find them is gone.
-// kCount = extraction e run for its knots only (flag words, lists and counts of B_e are written; R_e and B_e are not): the
-// first pass of a fused pair.  kRecomp = B_e recomputed into row e + 1 (the trend row when a fused pair's second
-// extraction turns out to be the discarded one).
-enum { kLevel = 0, kScan = 1, kProbe = 2, kFirst = 3, kCount = 4, kRecomp = 5 };
+// kRecomp = B_e recomputed into row e + 1 (the trend row when a fused pair's second extraction turns out to be the discarded
+// one).
+enum { kLevel = 0, kScan = 1, kProbe = 2, kFirst = 3, kRecomp = 5 };
 template <typename XT, typename CarryT, typename OutT, int KIND, bool BAS>
 __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<CarryT> &sm, const bool dense,
                                              const bool last, const int K, const int warp, const int lane,
                                              int &region_knots, int &input_knots, bool &zero_dx, bool &bad) {
     using A = Arith<CarryT>;
     constexpr int ITEMS = kSweepItems, SPAN = kSweepSpan;
-    constexpr bool SCAN = (KIND == kScan), FIRST = (KIND == kFirst), COUNT = (KIND == kCount), RECOMP = (KIND == kRecomp);
+    constexpr bool SCAN = (KIND == kScan), FIRST = (KIND == kFirst), RECOMP = (KIND == kRecomp);
     constexpr bool PROBE = (KIND == kProbe) || RECOMP;               // no flag words, lists or carry are written
     const int n = p.n;
     const int sp0 = warp * p.spw;
@@ -458,7 +460,7 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
         if (have_right) xr = ld_cg(in_p() + tend);
         if (!SCAN && (!EDGE || sp + 1 < p.spans)) mn = ld_cg(reinterpret_cast<const uint4 *>(gmask_p() + (sp + 1) * ITEMS));
         {
-            const int pf = COUNT ? p.pf_count : is_dense ? p.pf_dense : p.pf_sparse;
+            const int pf = is_dense ? p.pf_dense : p.pf_sparse;
             if (pf > 0 && sp + pf < sp1 && lane < SPAN * (int)sizeof(XT) / 128)
                 prefetch_l2(in_p() + t0 + pf * SPAN + lane * (128 / (int)sizeof(XT)));
         }
@@ -496,11 +498,6 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
                 const CarryT xv = (CarryT)xc[r];
                 b[r] = A::add(sm.L[j], A::mul(sm.S[j], A::sub(xv, sm.X[j])));     // ITD.py:115-117
                 if (EDGE && t0 + r * 32 + lane >= n - 1) b[r] = (CarryT)0;        // ITD.py:112 (and the padding lanes)
-                if (COUNT && EDGE) {                                              // the end values of the next extraction's input
-                    const int t = t0 + r * 32 + lane;
-                    if (t <= 1) sm.bend[t] = b[r];
-                    if (t == n - 2 || t == n - 1) sm.bend[t - (n - 4)] = b[r];
-                }
             }
             OutT *rot = rot_p() + t0 + lane;
             if (PROBE) {
@@ -508,8 +505,6 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
 #pragma unroll
                 for (int r = 0; r < ITEMS; ++r)
                     if (!EDGE || t0 + r * 32 + lane < n) __stcs(rot + r * 32, RECOMP ? (OutT)b[r] : (OutT)xc[r]);
-            } else if (COUNT) {
-                // nothing is stored: only the knots of B_e are wanted
             } else {
                 CarryT *carry = carry_p() + t0 + lane;
                 OutT *bas = BAS ? bas_p() + t0 + lane : nullptr;
@@ -613,15 +608,16 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
 
 // ---------------------------------------------------------------------------------------------
 // one region of one signal, TWO extractions at once (few knots in both: records from the block's two tables).
-// Reads X_e once; writes R_e, R_{e+1} and B_{e+1}; B_e exists only in registers: 40 bytes per sample (8 for the
-// counting pass that found B_e's knots + 32 here) instead of 48 for two separate extractions.
+// Reads X_e once; writes R_e, R_{e+1} and B_{e+1}; B_e exists only in registers: 32 bytes per sample instead of 48 for two
+// separate extractions.  The knots of B_e were PREDICTED (sweep_kernel: the extrema stencil at the knots of X_e); this pass
+// runs the stencil on every sample of B_e and reports any flag word that differs from the prediction (bad_pred).
 //   B_e[t]     = L_k + s_k (X_e[t] - X_k)           table A at index prefix[warp]  + knots of X_e at or before t
 //   B_{e+1}[t] = L'_k + s'_k (B_e[t] - X'_k)        table B at index offB + prefix2[warp] + knots of B_e at or before t
 // (ITD.py:115-119 twice); the extrema of B_{e+1} are the knots of extraction e + 2.
 // ---------------------------------------------------------------------------------------------
 template <typename CarryT, typename OutT, bool BAS>
 __device__ __forceinline__ void sweep_region_fused(const SweepParams &p, SweepSmem<CarryT> &sm, const int offB,
-                                                   const int warp, const int lane, int &region_knots) {
+                                                   const int warp, const int lane, int &region_knots, bool &bad_pred) {
     using A = Arith<CarryT>;
     constexpr int ITEMS = kSweepItems, SPAN = kSweepSpan;
     const int n = p.n;
@@ -638,7 +634,7 @@ __device__ __forceinline__ void sweep_region_fused(const SweepParams &p, SweepSm
     auto recA = [&](const int j, const CarryT v) { return A::add(sm.L[j], A::mul(sm.S[j], A::sub(v, sm.X[j]))); };
 
     int posA = 0, posB = 0, npos = 0;
-    CarryT bleft = (CarryT)0;                                        // B_{e+1} left of the span
+    CarryT bleft = (CarryT)0, bleftA = (CarryT)0;                    // B_{e+1} and B_e left of the span
     CarryT xc[ITEMS];
 #pragma unroll
     for (int r = 0; r < ITEMS; ++r) {
@@ -690,7 +686,10 @@ __device__ __forceinline__ void sweep_region_fused(const SweepParams &p, SweepSm
             }
         }
         // left neighbour of the region's first span (both levels), then the next span's samples
-        if (sp == sp0 && sp0 > 0) bleft = recA(ibB, recA(ibA, ld_cg(in_p() + t0 - 1)));
+        if (sp == sp0 && sp0 > 0) {
+            bleftA = recA(ibA, ld_cg(in_p() + t0 - 1));
+            bleft = recA(ibB, bleftA);
+        }
         {
             const CarryT *nx = in_p() + tend + lane;
 #pragma unroll
@@ -718,9 +717,19 @@ __device__ __forceinline__ void sweep_region_fused(const SweepParams &p, SweepSm
                 }
             }
         }
-        CarryT bright = (CarryT)0;
-        if (have_right && (!EDGE || tend < n - 1))                               // both baselines end with 0 (ITD.py:112)
-            bright = recA(ibB + cnt2 + fright2, recA(ibA + cnt + fright, xr));
+        CarryT bright = (CarryT)0, brightA = (CarryT)0;
+        if (have_right && (!EDGE || tend < n - 1)) {                             // both baselines end with 0 (ITD.py:112)
+            brightA = recA(ibA + cnt + fright, xr);
+            bright = recA(ibB + cnt2 + fright2, brightA);
+        }
+        // ---- the check: the extrema of B_e are exactly the predicted knots
+        {
+            unsigned fa[ITEMS];
+            span_extrema<EDGE, ITEMS, CarryT>(b, bleftA, brightA, lane, t0, n, fa);
+#pragma unroll
+            for (int r = 0; r < ITEMS; ++r) bad_pred |= (fa[r] != mw2[r]);
+            bleftA = shfl_idx(b[ITEMS - 1], 31);
+        }
 
         // ---- extrema of B_{e+1}: the flag words and knots of extraction e + 2
         unsigned fw[ITEMS];
@@ -812,7 +821,7 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
     const int n = p.n, S = p.S;
     const bool depth = p.depth_first != 0;
     const long long n_items = depth ? (long long)S : (long long)(p.stage_last - p.stage_first + 1) * S;
-    int d_sig = -1, d_e = 0, d_sel = 0;                        // depth-first cursor: the signal this CTA is working through
+    int d_sig = -1, d_e = 0, d_sel = 0, d_nofuse = 0;          // depth-first cursor: the signal this CTA is working through
     // after an item: the next stage of the same signal, or (signal finished) a new ticket
     auto advance = [&](const int e, const bool stopped) {       // e: the last extraction this item completed
         if (e >= p.stage_last || (stopped && !(p.opts & kOptZeroTail))) d_sig = -1;
@@ -821,33 +830,17 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
 
     // ---- the block's knot table {X, L, S}[off .. off + Kc + 1], one thread per knot (few knots) -----------------------
     // lists: the signal's region lists; pre: knots before each region; el / ex: L and X at the two end knots
-    auto build_table = [&](const int off, const int Kc, const int *ctau, const CarryT *cxk, const int *pre,
-                           const CarryT *el, const CarryT *ex) {
-        auto slot_of = [&](const int g) -> long long {              // list slot of the interior knot with global rank g
-            int r = 0;
+    // list slot of the interior knot of the item's input with global rank g (1 <= g <= K)
+    auto slot_of = [&](const int g) -> long long {
+        int r = 0;
 #pragma unroll
-            for (int q = 1; q < kSweepWarps; ++q) r += (pre[q] < g) ? 1 : 0;
-            return (long long)r * p.rs + kSweepPre + (g - 1 - pre[r]);
-        };
-        int *taus = reinterpret_cast<int *>(sm.S + off);              // tau lives in S's storage until S is computed
-        for (int k = tid; k <= Kc + 1; k += blockDim.x) {
-            int tv;
-            CarryT xv;
-            if (k == 0) {
-                tv = 0;
-                xv = ex[0];
-            } else if (k == Kc + 1) {
-                tv = n - 1;
-                xv = ex[1];
-            } else {
-                const long long sl = slot_of(k);
-                tv = ld_cg(ctau + sl);
-                xv = ld_cg(cxk + sl);
-            }
-            taus[k] = tv;
-            sm.X[off + k] = xv;
-        }
-        __syncthreads();
+        for (int q = 1; q < kSweepWarps; ++q) r += (sm.prefix[q] < g) ? 1 : 0;
+        return (long long)r * p.rs + kSweepPre + (g - 1 - sm.prefix[r]);
+    };
+    // second half of a table build: L (ITD.py:106-110) and the slopes (ITD.py:116) of entries off .. off + Kc + 1, whose tau
+    // words (in S's storage) and X are in place
+    auto table_compute = [&](const int off, const int Kc, const CarryT *el) {
+        int *taus = reinterpret_cast<int *>(sm.S + off);
         for (int k = tid; k <= Kc + 1; k += blockDim.x) {
             CarryT Lv;
             if (k == 0) {
@@ -875,6 +868,138 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
         }
         if (zdx) sm.zero_dx = 1;
         __syncthreads();
+    };
+    auto build_table = [&](const int Kc, const int *ctau, const CarryT *cxk, const CarryT *el, const CarryT *ex) {
+        int *taus = reinterpret_cast<int *>(sm.S);                    // tau lives in S's storage until S is computed
+        for (int k = tid; k <= Kc + 1; k += blockDim.x) {
+            int tv;
+            CarryT xv;
+            if (k == 0) {
+                tv = 0;
+                xv = ex[0];
+            } else if (k == Kc + 1) {
+                tv = n - 1;
+                xv = ex[1];
+            } else {
+                const long long sl = slot_of(k);
+                tv = ld_cg(ctau + sl);
+                xv = ld_cg(cxk + sl);
+            }
+            taus[k] = tv;
+            sm.X[k] = xv;
+        }
+        __syncthreads();
+        table_compute(0, Kc, el);
+    };
+
+    // ---- fused pair, step 1: the knots of B_e WITHOUT a pass over the signal ----------------------------------------
+    // Between two knots of X_e the baseline B_e = L_k + s_k (X_e - X_k) is a monotone function of a monotone stretch of
+    // X_e (rounding is monotone), so an extremum of B_e away from the knots of X_e needs two equal neighbouring values of
+    // B_e (a flat step) or a sample next to a knot that rounding pushed past it: rare on real data.  So: run the 3-point
+    // stencil (ITD.py:44-59) on B_e AT the knots of X_e only -- one thread per knot, B_e at tau_k - 1, tau_k, tau_k + 1 from
+    // the table and two gathered samples -- and take the flagged knots as the knots of B_e: their compacted list becomes
+    // the second table (at K + 2 in the block's arrays), their flag bits go to the CTA's scratch words.  The fused pass
+    // then runs the stencil on EVERY sample of B_e (which it has in registers anyway) and compares: if any flag word
+    // differs, the item falls back to a plain extraction e and the signal stops trying pairs.  A wrong prediction costs
+    // time, never a wrong bit.
+    // Returns the predicted knot count of B_e, or -1 if a fused pass is not possible / not worth it.
+    auto predict_pair = [&](const int K, const int *ctau, const CarryT *x_in) -> int {
+        unsigned *mm = p.mid_mask + (long long)blockIdx.x * p.mstride;
+        for (int w = tid; w < (int)p.mstride; w += blockDim.x) __stcg(mm + w, 0u);
+        const int offB = K + 2;
+        int *tausB = reinterpret_cast<int *>(sm.S + offB);
+        auto recA = [&](const int j, const CarryT v) { return A::add(sm.L[j], A::mul(sm.S[j], A::sub(v, sm.X[j]))); };
+        __syncthreads();                                               // the scratch words are zero before any bit is set
+        // candidates: the knots 1 .. K of X_e, and sample n-2 (B_e[n-1] is forced to 0, ITD.py:112, so n-2 can be an extremum
+        // of B_e without being one of X_e -- it is one in every tenth extraction of the benchmark).  Warp w takes the w-th
+        // run of candidates, 32 at a time; nothing is synchronised until every load of every step has been issued.
+        constexpr int PSTEPS = 7;                                      // 8 warps x 7 x 32 >= kSweepFuseMaxLimit + 1
+        const int kw = (K + 1 + kSweepWarps - 1) / kSweepWarps;
+        const int kbeg = 1 + warp * kw;
+        int tks[PSTEPS];
+        CarryT bhs[PSTEPS];
+        unsigned bals[PSTEPS];
+        int wtot = 0;
+#pragma unroll
+        for (int st = 0; st < PSTEPS; ++st) {
+            const int q = st * 32 + lane, k = kbeg + q;
+            bool f = false;
+            int tk = 0;
+            CarryT bh = (CarryT)0;
+            if (q < kw && k <= K) {
+                tk = ld_cg(ctau + slot_of(k));
+                const int tn = (k + 1 <= K) ? ld_cg(ctau + slot_of(k + 1)) : n - 1;
+                const CarryT xp = ld_cg(x_in + tk - 1), xn = ld_cg(x_in + tk + 1);
+                const CarryT bp = recA(k - 1, xp);                     // sample tau_k - 1 lies in segment k - 1
+                bh = recA(k, sm.X[k]);
+                const CarryT bn = (tk + 1 >= n - 1) ? (CarryT)0 : recA((tk + 1 == tn) ? k + 1 : k, xn);      // ITD.py:112
+                f = is_knot(bp, bh, bn);
+            } else if (q < kw && k == K + 1) {
+                const int tK = ld_cg(ctau + slot_of(K));              // (K >= 1)
+                if (tK != n - 2) {
+                    tk = n - 2;
+                    const CarryT bp = recA(K, ld_cg(x_in + n - 3));
+                    bh = recA(K, sm.xe[2]);
+                    f = is_knot(bp, bh, (CarryT)0);
+                }
+            }
+            bals[st] = __ballot_sync(0xffffffffu, f);
+            tks[st] = tk;
+            bhs[st] = bh;
+            wtot += __popc(bals[st]);
+        }
+        if (lane == 0) sm.cnt[warp] = wtot;
+        __syncthreads();
+        int base = 0, K2 = 0;
+#pragma unroll
+        for (int w = 0; w < kSweepWarps; ++w) {
+            const int cw = sm.cnt[w];
+            K2 += cw;
+            base += (w < warp) ? cw : 0;
+        }
+#pragma unroll
+        for (int st = 0; st < PSTEPS; ++st) {
+            if ((bals[st] >> lane) & 1u) {
+                const int rank = base + __popc(bals[st] & ((1u << lane) - 1u));
+                if (offB + rank + 2 < SweepSmem<CarryT>::kCap) {
+                    tausB[1 + rank] = tks[st];
+                    sm.X[offB + 1 + rank] = bhs[st];
+                }
+                atomicOr(mm + (tks[st] >> 5), 1u << (tks[st] & 31));
+            }
+            base += __popc(bals[st]);
+        }
+        const bool go = (K2 >= p.fuse_min_b) && (K2 >= p.min_extrema) && (K + K2 + 4 <= SweepSmem<CarryT>::kCap);
+        if (!go) {
+            __syncthreads();                                           // (sm.cnt / sm.knots_in are reused by the caller)
+            return -1;
+        }
+        if (tid == 0) {
+            // the end knots of B_e and ITD.py:100-102 on it: B_e at samples 0, 1, n-2 (n-1 holds 0, ITD.py:112)
+            const int t1 = ld_cg(ctau + slot_of(1));                  // (K >= 1)
+            const CarryT b0 = recA(0, sm.xe[0]), b1 = recA((t1 == 1) ? 1 : 0, sm.xe[1]);
+            const CarryT bz = recA(K, sm.xe[2]);
+            tausB[0] = 0;
+            sm.X[offB] = b0;
+            tausB[K2 + 1] = n - 1;
+            sm.X[offB + K2 + 1] = (CarryT)0;
+            sm.endl2[0] = mean2<CarryT>(b0, b1);
+            sm.endl2[1] = mean2<CarryT>(bz, (CarryT)0);
+        }
+        __syncthreads();
+        if (tid <= kSweepWarps) {                                      // knots of B_e before each region
+            const int tstart = (tid == kSweepWarps) ? n : tid * p.spw * kSweepSpan;
+            int lo = 1, hi = K2 + 1;                                   // first entry in [1, K2] with tau >= tstart
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (tausB[mid] < tstart) lo = mid + 1;
+                else hi = mid;
+            }
+            sm.prefix2[tid] = lo - 1;
+        }
+        __syncthreads();
+        table_compute(offB, K2, sm.endl2);
+        return K2;
     };
 
     for (;;) {
@@ -911,8 +1036,10 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
             // extraction e was the second of a fused pair (e - 1, e), or the signal has stopped
             already = ((sm.dn & kSweepDoneAll) >= e + 2);
             d_sel = (sm.dn >> 30) & 1;
+            d_nofuse = (sm.dn >> 28) & 1;
         } else if (e <= 0) {
             d_sel = (e < 0) ? 1 : 0;                           // the scan writes tab[0]
+            d_nofuse = 0;
         }
         const int se = (e >= 0) ? ld_cg(p.stop_e + sig) : kStopOpen;
         if (e > se) {
@@ -942,6 +1069,7 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
             sm.it_e = e;
             sm.it_sig = sig;
             sm.it_sel = d_sel;
+            sm.it_nofuse = d_nofuse;
             sm.it_de = d_e;
             sm.it_dsig = d_sig;
             const long long koff = (long long)sig * p.kstride, moff = (long long)sig * p.mstride;
@@ -990,6 +1118,7 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
                 sm.endl[1] = mean2<CarryT>(z0, z1);
                 sm.endx[0] = a0;
                 sm.endx[1] = z1;
+                sm.xe[0] = a0, sm.xe[1] = a1, sm.xe[2] = z0, sm.xe[3] = z1;
             }
             __syncthreads();
             K = sm.prefix[kSweepWarps];
@@ -997,20 +1126,13 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
 #ifdef PYITD_SWEEP_NO_FUSE_CODE
             can_fuse = false;
 #else
-            can_fuse = p.fuse && !dense && e >= 1 && K >= p.fuse_min_a && K + 2 <= p.fuse_max_a && e + 1 < p.emax &&
-                       e + 1 <= p.stage_last && (int)blockIdx.x < p.mid_ctas;
+            can_fuse = p.fuse && !d_nofuse && !dense && e >= 1 && K >= p.fuse_min_a && K + 2 <= p.fuse_max_a &&
+                       e + 1 < p.emax && e + 1 <= p.stage_last && (int)blockIdx.x < p.mid_ctas;
 #endif
             const int *ctau = cur.tau + koff;
             const CarryT *cxk = reinterpret_cast<const CarryT *>(cur.xk) + koff;
             if (dense) {
                 // ---- halo slots of every region list: the two knots before and the three after the region ----
-                // list slot of the interior knot with global rank g (1 <= g <= K)
-                auto slot_of = [&](const int g) -> long long {
-                    int r = 0;
-#pragma unroll
-                    for (int q = 1; q < kSweepWarps; ++q) r += (sm.prefix[q] < g) ? 1 : 0;
-                    return (long long)r * p.rs + kSweepPre + (g - 1 - sm.prefix[r]);
-                };
                 if (!first_fused && tid < kSweepWarps * (kSweepPre + kSweepPost)) {
                     const int r = tid / (kSweepPre + kSweepPost), h = tid % (kSweepPre + kSweepPost);
                     const int c = sm.prefix[r + 1] - sm.prefix[r];
@@ -1035,7 +1157,7 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
                 }
                 __syncthreads();
             } else {
-                build_table(0, K, ctau, cxk, sm.prefix, sm.endl, sm.endx);
+                build_table(K, ctau, cxk, sm.endl, sm.endx);
             }
         }
 
@@ -1056,73 +1178,56 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
             probed_stop = (kp < p.min_extrema);
             __syncthreads();
         }
-        // ---- a fused pair: extractions e and e + 1 in two passes over X_e; B_e is never stored -------------------------
-        // pass 1 (kCount) evaluates B_e for its extrema only and leaves their lists and flag words in the CTA's scratch
-        // (8 bytes read per sample); pass 2 reads X_e again and writes R_e, R_{e+1}, B_{e+1} (32 bytes per sample): 40 bytes
-        // for two extractions instead of 48.  ITD.py:79-121 twice; the stop test of extraction e (ITD.py:404) is the
-        // count of pass 1.
+        // ---- a fused pair: extractions e and e + 1 in ONE pass over X_e; B_e is never stored ---------------------------
+        // The knots of B_e are predicted from the table (predict_pair); the pass reads X_e and writes R_e, R_{e+1}, B_{e+1}
+        // (32 bytes per sample instead of 48 for ITD.py:79-121 twice) and checks the prediction on every sample.  The stop
+        // test of extraction e (ITD.py:404) is the predicted count: a pair is only tried when it says "go on".
         int fused = 0, K2 = 0;
-        bool counted_stop = false;
+        bool pair_failed = false;
         if (can_fuse) {
-            if (tid == 64) {
-                sm.ptr[kPtrNmask] = p.mid_mask + (long long)blockIdx.x * p.mstride;
-                sm.ptr[kPtrNtau] = p.mid_tau + (long long)blockIdx.x * kSweepWarps * p.rs;
-                sm.ptr[kPtrNxk] = reinterpret_cast<CarryT *>(p.mid_xk) + (long long)blockIdx.x * kSweepWarps * p.rs;
-            }
-            __syncthreads();
-            int unused = 0;
-            sweep_region<CarryT, CarryT, OutT, kCount, BAS>(p, sm, false, false, K, warp, lane, region_knots, unused, zero_dx, bad);
-            if (lane == 0) sm.cnt[warp] = region_knots;
-            __syncthreads();
-            e = sm.it_e, sig = sm.it_sig, d_sel = sm.it_sel, d_e = sm.it_de, d_sig = sm.it_dsig, K = sm.prefix[kSweepWarps];
-#pragma unroll
-            for (int r = 0; r < kSweepWarps; ++r) K2 += sm.cnt[r];
-            if (K2 < p.min_extrema) {
-                counted_stop = true;                                   // extraction e is the discarded last one (ITD.py:404-411)
+            const CarryT *x_in = reinterpret_cast<const CarryT *>(p.carry[d_sel ^ 1]) + (long long)sig * n;
+            K2 = predict_pair(K, p.tab[d_sel].tau + (long long)sig * p.kstride, x_in);
+            if (K2 < 0) {
                 if (tid == 0) atomicAdd(p.stats + 1, 1);
+                K2 = 0;
             } else {
-                const bool go = (K2 >= p.fuse_min_b) && (K + K2 + 4 <= SweepSmem<CarryT>::kCap);
-                if (tid == 0) {
-                    int run = 0;
-                    for (int r = 0; r < kSweepWarps; ++r) {
-                        sm.prefix2[r] = run;
-                        run += sm.cnt[r];
-                    }
-                    sm.prefix2[kSweepWarps] = run;
-                    sm.endl2[0] = mean2<CarryT>(sm.bend[0], sm.bend[1]);       // ITD.py:100-102 on B_e
-                    sm.endl2[1] = mean2<CarryT>(sm.bend[2], sm.bend[3]);
-                    sm.endx2[0] = sm.bend[0];
-                    sm.endx2[1] = sm.bend[3];
-                }
                 if (tid == 64) {
                     const long long row2 = (long long)sig * p.out_sig_stride + (long long)(e + 1) * n;
-                    const long long koff = (long long)sig * p.kstride, moff = (long long)sig * p.mstride;
-                    const SweepTable &nxt = p.tab[d_sel ^ 1];
                     sm.ptr[kPtrRot2] = reinterpret_cast<OutT *>(p.rot) + row2;
                     sm.ptr[kPtrBas2] = BAS ? reinterpret_cast<OutT *>(p.bas) + row2 : nullptr;
                     sm.ptr[kPtrGmask2] = p.mid_mask + (long long)blockIdx.x * p.mstride;
-                    sm.ptr[kPtrNmask] = nxt.mask + moff;
-                    sm.ptr[kPtrNtau] = nxt.tau + koff;
-                    sm.ptr[kPtrNxk] = reinterpret_cast<CarryT *>(nxt.xk) + koff;
+                    sm.pred_bad = 0;
                 }
                 __syncthreads();
-                if (tid == 0) atomicAdd(p.stats + (go ? 0 : 1), 1);
-                if (go) {
-                    build_table(K + 2, K2, p.mid_tau + (long long)blockIdx.x * kSweepWarps * p.rs,
-                                reinterpret_cast<const CarryT *>(p.mid_xk) + (long long)blockIdx.x * kSweepWarps * p.rs, sm.prefix2,
-                                sm.endl2, sm.endx2);
-                    sweep_region_fused<CarryT, OutT, BAS>(p, sm, K + 2, warp, lane, region_knots);
+                bool bad_pred = false;
+                sweep_region_fused<CarryT, OutT, BAS>(p, sm, K + 2, warp, lane, region_knots, bad_pred);
+                if (__any_sync(0xffffffffu, bad_pred) && lane == 0) sm.pred_bad = 1;
+                if (lane == 0) sm.cnt[warp] = region_knots;
+                __syncthreads();
+                e = sm.it_e, sig = sm.it_sig, d_sel = sm.it_sel, d_e = sm.it_de, d_sig = sm.it_dsig, K = sm.prefix[kSweepWarps];
+                d_nofuse = sm.it_nofuse;
+                pair_failed = (sm.pred_bad != 0);
+                if (tid == 0) atomicAdd(p.stats + (pair_failed ? 2 : 0), 1);
+                if (pair_failed) {
+                    // B_e has an extremum the prediction did not see (a flat step, a tie next to a knot): everything the pass
+                    // wrote is overwritten by the plain extraction e below (row e, the carry, the next knot lists) or by
+                    // whatever later fills row e + 1; this signal does not try pairs again
+                    d_nofuse = 1;
+                    K2 = 0;
+                    __syncthreads();                                   // (sm.cnt is written again below)
+                } else {
                     fused = 1;
                 }
             }
         }
         if (tid == 0) {
-            sm.it_flags = fused | (counted_stop ? 2 : 0) | (probed_stop ? 4 : 0);
+            sm.it_flags = fused | (probed_stop ? 4 : 0);
             sm.it_k2 = K2;
+            sm.it_nofuse = d_nofuse;
         }
         int knots_in = 0;
-        if (probed_stop || counted_stop || fused) {
-            // probed_stop: row e already holds the trend row; the region counts of the probe / count are the ones to report
+        if (probed_stop || fused) {
+            // probed_stop: row e already holds the trend row; the region counts of the probe are the ones to report
         } else if (e < 0) {
             sweep_region<InT, CarryT, OutT, kScan, BAS>(p, sm, false, false, 0, warp, lane, region_knots, knots_in, zero_dx, bad);
         } else if (e == 0 && kFusedScan(p)) {
@@ -1133,14 +1238,14 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
         } else {
             sweep_region<InT, CarryT, OutT, kLevel, BAS>(p, sm, dense, last0, K, warp, lane, region_knots, knots_in, zero_dx, bad);
         }
-        if (!counted_stop && lane == 0) sm.cnt[warp] = region_knots;
+        if (lane == 0) sm.cnt[warp] = region_knots;
         if (__any_sync(0xffffffffu, zero_dx) && lane == 0) sm.zero_dx = 1;
         if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.status + sig, kStNonFinite);
         __syncthreads();
 
         // ---- end of the item: region counts, stop rule, trend row ---------------------------------
         e = sm.it_e, sig = sm.it_sig, d_sel = sm.it_sel, d_e = sm.it_de, d_sig = sm.it_dsig, K = sm.prefix[kSweepWarps];
-        fused = sm.it_flags & 1, counted_stop = (sm.it_flags & 2) != 0, probed_stop = (sm.it_flags & 4) != 0, K2 = sm.it_k2;
+        fused = sm.it_flags & 1, probed_stop = (sm.it_flags & 4) != 0, K2 = sm.it_k2, d_nofuse = sm.it_nofuse;
         const bool last = (e == p.emax);
         const int ee = e + fused;                                      // the last extraction this item completed
         int Kn = 0;
@@ -1168,7 +1273,7 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
                 }
             }
             if (stop_knots && !probed_stop && !fused) {
-                // the discarded extraction wrote R_e into row e (nothing after a counting pass); the reference returns
+                // the discarded extraction wrote R_e into row e; the reference returns
                 // baselines[e-1] there, i.e. the INPUT of this extraction (zeros when e == 0)  (ITD.py:410-411)
                 OutT *rot = reinterpret_cast<OutT *>(p.rot) + (long long)sig * p.out_sig_stride + (long long)e * n;
                 const CarryT *x_in = reinterpret_cast<const CarryT *>(p.carry[d_sel ^ 1]) + (long long)sig * n;
@@ -1193,7 +1298,8 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
         if (tid == 0) {
             __threadfence();
             // a stopped signal lets every later stage of it through at once (they only zero-fill on request)
-            st_release(p.done + sig, ((e >= 0 && (stop_knots || last)) ? kSweepDoneAll : ee + 2) | ((d_sel ^ 1) << 30));
+            st_release(p.done + sig,
+                       ((e >= 0 && (stop_knots || last)) ? kSweepDoneAll : ee + 2) | ((d_sel ^ 1) << 30) | (d_nofuse << 28));
             if (p.stage_ns) atomicAdd(p.stage_ns + (e + 1), global_ns() - sm.t_start);
         }
         d_sel ^= 1;
