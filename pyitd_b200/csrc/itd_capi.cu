@@ -1160,6 +1160,9 @@ static int run_sweep(pyitd_plan *pl, const void *x, void *rotations, void *basel
     // signal-major order keeps the carry in L2 between a signal's extractions: a fused pair saves no DRAM traffic there and its
     // counting pass only adds instructions (config 4: 1.12 -> 1.51 ms with pairs).  PYITD_SWEEP_FUSE=2 forces them on.
     if (sp.depth_first && !(getenv("PYITD_SWEEP_FUSE") && atoi(getenv("PYITD_SWEEP_FUSE")) == 2)) sp.fuse = 0;
+    // the prediction alone also picks probe / plain extraction for the items that are not fused (not for short signals either:
+    // config 4 1.19 -> 1.40 ms with it, the per-item work there is a few microseconds)
+    sp.predict = sp.fuse;
     // PYITD_SWEEP_FUSED_SCAN=1: no scan stage -- extraction 0 finds the knots of the raw input inside its chunk builds and the
     // input's knot lists never exist (-5.7 GB of DRAM traffic per 4096 x 65536 step).  Bit-identical, but level 0 is
     // issue-bound and the extra stencil work costs more than the scan stage it replaces (3.18 ms vs 0.75 + 2.07 ms,

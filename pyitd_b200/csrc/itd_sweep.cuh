@@ -101,6 +101,7 @@ struct SweepParams {
     // still in L2 -- for short signals (framed audio), where all resident CTAs' working sets fit there.
     int depth_first;
     int fuse;                      // 1: pairs of few-knot extractions run as one item that never stores the baseline between them
+    int predict;                   // 1: the knot count of a few-knot extraction's baseline is predicted from its table
     int fuse_min_a, fuse_max_a, fuse_min_b;   // thresholds (kSweepFuse*; experiment hooks)
     int fused_scan;                // 1: no scan stage (stage_first >= 0): extraction 0 finds the input's knots itself (kFirst)
 };
@@ -902,8 +903,11 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
     // then runs the stencil on EVERY sample of B_e (which it has in registers anyway) and compares: if any flag word
     // differs, the item falls back to a plain extraction e and the signal stops trying pairs.  A wrong prediction costs
     // time, never a wrong bit.
-    // Returns the predicted knot count of B_e, or -1 if a fused pass is not possible / not worth it.
-    auto predict_pair = [&](const int K, const int *ctau, const CarryT *x_in) -> int {
+    // Returns the predicted knot count of B_e (a LOWER bound of the true count: every predicted knot is one); go = the
+    // second table is in place and a fused pass is possible and worth it (only asked for with want_pair).
+    // The count also steers extractions that are not fused: a predicted count below min_extrema means that this
+    // extraction is almost certainly the discarded last one (ITD.py:404-411), which is then probed first.
+    auto predict_pair = [&](const int K, const int *ctau, const CarryT *x_in, const bool want_pair, bool &go) -> int {
         unsigned *mm = p.mid_mask + (long long)blockIdx.x * p.mstride;
         for (int w = tid; w < (int)p.mstride; w += blockDim.x) __stcg(mm + w, 0u);
         const int offB = K + 2;
@@ -969,10 +973,10 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
             }
             base += __popc(bals[st]);
         }
-        const bool go = (K2 >= p.fuse_min_b) && (K2 >= p.min_extrema) && (K + K2 + 4 <= SweepSmem<CarryT>::kCap);
+        go = want_pair && (K2 >= p.fuse_min_b) && (K2 >= p.min_extrema) && (K + K2 + 4 <= SweepSmem<CarryT>::kCap);
         if (!go) {
-            __syncthreads();                                           // (sm.cnt / sm.knots_in are reused by the caller)
-            return -1;
+            __syncthreads();                                           // (sm.cnt is reused by the caller)
+            return K2;
         }
         if (tid == 0) {
             // the end knots of B_e and ITD.py:100-102 on it: B_e at samples 0, 1, n-2 (n-1 holds 0, ITD.py:112)
@@ -1165,9 +1169,20 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
         int region_knots = 0;
         bool zero_dx = false, bad = false;
         const bool last0 = (e == p.emax);
-        // an extraction with at most kSweepProbeKnots knots is probably the discarded last one: probe it first
+        // ---- the knots of B_e, predicted (few knots, e >= 1): decides between probe, fused pair and plain extraction
+        int K2 = 0;
+        bool go = false, predicted = false;
+        if (p.predict && !d_nofuse && !dense && e >= 1 && !last0 && K >= 1 && K <= kSweepFuseMaxLimit &&
+            (int)blockIdx.x < p.mid_ctas) {
+            const CarryT *x_in = reinterpret_cast<const CarryT *>(p.carry[d_sel ^ 1]) + (long long)sig * n;
+            K2 = predict_pair(K, p.tab[d_sel].tau + (long long)sig * p.kstride, x_in, can_fuse, go);
+            predicted = true;
+            if (can_fuse && !go && tid == 0) atomicAdd(p.stats + 1, 1);
+        }
+        // an extraction whose baseline is predicted to have fewer than min_extrema extrema (without a prediction: one with at
+        // most kSweepProbeKnots knots) is probably the discarded last one: probe it first
         bool probed_stop = false;
-        if (e >= 1 && !last0 && !can_fuse && K <= kSweepProbeKnots) {
+        if (e >= 1 && !last0 && !go && (predicted ? (K2 < p.min_extrema) : (K <= kSweepProbeKnots))) {
             int unused = 0;
             sweep_region<CarryT, CarryT, OutT, kProbe, BAS>(p, sm, false, false, K, warp, lane, region_knots, unused, zero_dx, bad);
             if (lane == 0) sm.cnt[warp] = region_knots;
@@ -1182,15 +1197,10 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
         // The knots of B_e are predicted from the table (predict_pair); the pass reads X_e and writes R_e, R_{e+1}, B_{e+1}
         // (32 bytes per sample instead of 48 for ITD.py:79-121 twice) and checks the prediction on every sample.  The stop
         // test of extraction e (ITD.py:404) is the predicted count: a pair is only tried when it says "go on".
-        int fused = 0, K2 = 0;
+        int fused = 0;
         bool pair_failed = false;
-        if (can_fuse) {
-            const CarryT *x_in = reinterpret_cast<const CarryT *>(p.carry[d_sel ^ 1]) + (long long)sig * n;
-            K2 = predict_pair(K, p.tab[d_sel].tau + (long long)sig * p.kstride, x_in);
-            if (K2 < 0) {
-                if (tid == 0) atomicAdd(p.stats + 1, 1);
-                K2 = 0;
-            } else {
+        if (go) {
+            {
                 if (tid == 64) {
                     const long long row2 = (long long)sig * p.out_sig_stride + (long long)(e + 1) * n;
                     sm.ptr[kPtrRot2] = reinterpret_cast<OutT *>(p.rot) + row2;
