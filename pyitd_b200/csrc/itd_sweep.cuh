@@ -1233,7 +1233,7 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
         if (tid == 0) {
             sm.it_flags = fused | (probed_stop ? 4 : 0);
             sm.it_k2 = K2;
-            sm.it_nofuse = d_nofuse;
+            if (pair_failed) sm.it_nofuse = 1;                         // (behind the barrier of the failed path: nobody reads it now)
         }
         int knots_in = 0;
         if (probed_stop || fused) {
