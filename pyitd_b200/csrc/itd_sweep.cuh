@@ -40,6 +40,13 @@ namespace pyitd {
 constexpr int kSweepWarps = 8;
 constexpr int kSweepItems = 4;
 constexpr int kSweepSpan = 32 * kSweepItems;          // samples per warp iteration
+// The knot lists hold (tau_k, X_k).  -DPYITD_SWEEP_TAU_ONLY keeps tau only and gathers X_k = X_e[tau_k] from the input when a
+// table is built (-16 B of traffic per knot: the scan stage 0.73 -> 0.57 ms); measured and NOT adopted: the dependent
+// loads (tau, then the sample) make every chunk build of a many-knot level and every table build wait twice
+// (e = 0 .. 3: 2.10 / 1.47 / 1.26 / 1.52 -> 2.21 / 1.64 / 1.56 / 1.65 ms; the step 12.75 -> 13.4 ms), profiles/r2/README.md.
+#ifndef PYITD_SWEEP_TAU_ONLY
+#define PYITD_SWEEP_XK_LISTS 1
+#endif
 #ifndef PYITD_SWEEP_CAP
 #define PYITD_SWEEP_CAP 2240
 #endif
@@ -235,10 +242,13 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
         const int m = __popc(__ballot_sync(0xffffffffu, lane < nsp && pre + 5 <= kSweepScratch));
         const int tot = __shfl_sync(0xffffffffu, pre, m - 1);
         const int *ctau = reinterpret_cast<const int *>(sm.ptr[kPtrCtau]) + roff + pos;
+#ifdef PYITD_SWEEP_XK_LISTS
         const CarryT *cxk = reinterpret_cast<const CarryT *>(sm.ptr[kPtrCxk]) + roff + pos;
+#endif
         int *tw = reinterpret_cast<int *>(sm.S + wsc);               // tau words live in S's storage until S is computed
         const int g0 = gbase0 + pos - 1;
         __syncwarp();                                                // the previous chunk's lookups are done
+#ifdef PYITD_SWEEP_XK_LISTS
         for (int i = lane; i < tot + 5; i += 32) {
             tw[i] = ld_cg(ctau + i);
             sm.X[wsc + i] = ld_cg(cxk + i);
@@ -247,6 +257,17 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
             if (lane < 4) prefetch_l2(ctau + tot + 5 + kSweepScratch / 2 + lane * 32);
             else prefetch_l2(cxk + tot + 5 + kSweepScratch / 2 + (lane - 4) * 16);
         }
+#else
+        // the lists hold tau only: X_k = X_e[tau_k] is gathered from the input (32 consecutive knots of a many-knot level sit
+        // in a handful of 128-byte lines, which the span loop is about to read anyway)
+        for (int i = lane; i < tot + 5; i += 32) {
+            const int tv = ld_cg(ctau + i);
+            tw[i] = tv;
+            sm.X[wsc + i] = (CarryT)ld_cg(in_p() + tv);
+        }
+        if (lane < 4 && pos + tot + 5 + 3 * kSweepScratch < p.rs)      // the next chunk's entries towards L2
+            prefetch_l2(ctau + tot + 5 + kSweepScratch / 2 + lane * 32);
+#endif
         __syncwarp();
         // the end knots 0 and K+1 (and the unused ranks beyond them) are rare: one warp-uniform test per chunk
         const bool clip = (g0 + 1 <= 0) || (g0 + tot + 3 >= K + 1);
@@ -568,7 +589,9 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
         }
         if (!PROBE && newc) {
             int *ntau = reinterpret_cast<int *>(sm.ptr[kPtrNtau]) + roff + kSweepPre + npos;
+#ifdef PYITD_SWEEP_XK_LISTS
             CarryT *nxk = reinterpret_cast<CarryT *>(sm.ptr[kPtrNxk]) + roff + kSweepPre + npos;
+#endif
             const unsigned lt_mask = le_mask >> 1;
             int pre = 0;
 #pragma unroll
@@ -576,7 +599,9 @@ __device__ __forceinline__ void sweep_region(const SweepParams &p, SweepSmem<Car
                 if ((fw[r] >> lane) & 1u) {
                     const int rank = pre + __popc(fw[r] & lt_mask);
                     __stwb(ntau + rank, t0 + r * 32 + lane);
+#ifdef PYITD_SWEEP_XK_LISTS
                     __stwb(nxk + rank, b[r]);
+#endif
                 }
                 pre += __popc(fw[r]);
             }
@@ -743,7 +768,9 @@ __device__ __forceinline__ void sweep_region_fused(const SweepParams &p, SweepSm
         }
         if (newc) {
             int *ntau = reinterpret_cast<int *>(sm.ptr[kPtrNtau]) + roff + kSweepPre + npos;
+#ifdef PYITD_SWEEP_XK_LISTS
             CarryT *nxk = reinterpret_cast<CarryT *>(sm.ptr[kPtrNxk]) + roff + kSweepPre + npos;
+#endif
             const unsigned lt_mask = le_mask >> 1;
             int pre = 0;
 #pragma unroll
@@ -751,7 +778,9 @@ __device__ __forceinline__ void sweep_region_fused(const SweepParams &p, SweepSm
                 if ((fw[r] >> lane) & 1u) {
                     const int rank = pre + __popc(fw[r] & lt_mask);
                     __stwb(ntau + rank, t0 + r * 32 + lane);
+#ifdef PYITD_SWEEP_XK_LISTS
                     __stwb(nxk + rank, b2[r]);
+#endif
                 }
                 pre += __popc(fw[r]);
             }
@@ -870,7 +899,8 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
         if (zdx) sm.zero_dx = 1;
         __syncthreads();
     };
-    auto build_table = [&](const int Kc, const int *ctau, const CarryT *cxk, const CarryT *el, const CarryT *ex) {
+    // (x_at: the item's input at a sample -- the lists hold tau only, X_k is gathered)
+    auto build_table = [&](const int Kc, const int *ctau, const CarryT *cxk, const CarryT *el, const CarryT *ex, auto x_at) {
         int *taus = reinterpret_cast<int *>(sm.S);                    // tau lives in S's storage until S is computed
         for (int k = tid; k <= Kc + 1; k += blockDim.x) {
             int tv;
@@ -884,7 +914,11 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
             } else {
                 const long long sl = slot_of(k);
                 tv = ld_cg(ctau + sl);
+#ifdef PYITD_SWEEP_XK_LISTS
                 xv = ld_cg(cxk + sl);
+#else
+                xv = x_at(tv);
+#endif
             }
             taus[k] = tv;
             sm.X[k] = xv;
@@ -1153,15 +1187,27 @@ __global__ void __launch_bounds__(kSweepWarps * 32, 4) sweep_kernel(const SweepP
                     } else if (g >= 1 && g <= K) {
                         const long long sl = slot_of(g);
                         tv = ld_cg(ctau + sl);
+#ifdef PYITD_SWEEP_XK_LISTS
                         xv = ld_cg(cxk + sl);
+#endif
                     }
                     const long long dst = (long long)r * p.rs + kSweepPre + j;
                     const_cast<int *>(ctau)[dst] = tv;
+#ifdef PYITD_SWEEP_XK_LISTS
                     const_cast<CarryT *>(cxk)[dst] = xv;
+#else
+                    (void)xv;
+#endif
                 }
                 __syncthreads();
             } else {
-                build_table(K, ctau, cxk, sm.endl, sm.endx);
+                if (e == 0) {
+                    const InT *xi = reinterpret_cast<const InT *>(p.x) + (long long)sig * n;
+                    build_table(K, ctau, cxk, sm.endl, sm.endx, [&](const int t) { return (CarryT)xi[t]; });
+                } else {
+                    const CarryT *xi = reinterpret_cast<const CarryT *>(p.carry[d_sel ^ 1]) + (long long)sig * n;
+                    build_table(K, ctau, cxk, sm.endl, sm.endx, [&](const int t) { return ld_cg(xi + t); });
+                }
             }
         }
 
