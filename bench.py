@@ -459,6 +459,7 @@ def main():
     barrier()
     assert int(status.abs().max()) == 0, "synthetic workload hit an error status"
     launches_per_step = plan.launches
+    pair_stats = plan.sweep_stats() if plan.path[0] == "sweep" else None
 
     # ---- timed region: exactly K steps, CUDA events on the launching stream ----------------------
     sampler = ClockSampler(local_rank)
@@ -588,6 +589,13 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": ms_per_step, "level_launches": 1,
                 "achieved_definition": "algorithmic bytes of all extractions of the step (24 B per sample-level) / CUDA-event "
                                        "duration of the one sweep_kernel launch that runs the knot scan and every level"})
+            if pair_stats is not None:
+                # fused pairs of extractions never store the baseline between them: such a pair MOVES 32 B per sample for 48
+                # algorithmic bytes, so `achieved` can exceed the DRAM throughput of the launch (see `traffic`)
+                roofline["fused_pairs_per_step"] = {
+                    "fused": pair_stats[0], "not_tried_after_prediction": pair_stats[1], "failed_check_redone": pair_stats[2],
+                    "bytes_saved_per_step": pair_stats[0] * N * 16,
+                    "note": "two consecutive few-knot extractions in one pass: 32 B per sample instead of 48 (DESIGN 4)"}
         if span_ms is not None:
             # grouped launch chains: all level launches + the knot scans inside one fork-to-join span
             ach = alg_bytes / (span_ms * 1e-3) / 1e9
