@@ -43,6 +43,14 @@ def test_lengths_around_chunks(n, chunk, monkeypatch):
     assert _plan_path() == "coop"
 
 
+@pytest.mark.parametrize("n", [150001, 262143])
+def test_longest_signals_of_the_path(n):
+    """Just below 2^18 samples (from there on the strided path takes a single signal): 1792-sample chunks on 147 CTAs."""
+    x = synth.eeg_like(2, n, seed=n, device="cpu").numpy()
+    check_against_oracle(x, max_iteration=11)
+    assert _plan_path() == "coop"
+
+
 @pytest.mark.parametrize("S", [1, 2, 5, 16, 40])
 def test_signals_per_group(S, monkeypatch):
     """S = 40 forced onto this path: fewer groups than signals on 65 536-sample signals (128 CTAs each), so a group works

@@ -286,3 +286,33 @@ def test_fused_pairs_equal_single_extractions(thr, depth, monkeypatch):
     assert fused_total > 0
     if thr is not None and thr[0] == "4":
         assert skipped_total > 0 and failed_total > 0
+
+
+@pytest.mark.parametrize("dt", ["f32_mixed", "f32"])
+def test_fused_pairs_fp32_variants(dt, monkeypatch):
+    """The fused pairs in the two float32 variants (fp64 carry around float32 rows; everything in binary32): same bytes as one
+    item per extraction, and as the rounded / binary32 oracle."""
+    monkeypatch.setenv("PYITD_SWEEP_DEPTH", "0")
+    x32 = synth.eeg_like(170, 20000, seed=77, device="cpu").numpy().astype(np.float32)
+    x32[::7] = np.round(x32[::7] * 32) / 32                        # flat steps: failed predictions
+    monkeypatch.setenv("PYITD_SWEEP_FUSE", "0")
+    pyitd_b200.clear_plan_cache()
+    a = pyitd_b200.decompose(gpu(x32), max_iteration=11, dtype=dt, return_baselines=True, zero_tail=True)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("PYITD_SWEEP_FUSE", "2")
+    pyitd_b200.clear_plan_cache()
+    b = pyitd_b200.decompose(gpu(x32), max_iteration=11, dtype=dt, return_baselines=True, zero_tail=True)
+    torch.cuda.synchronize()
+    f, _, bad = _last_plan().sweep_stats()
+    assert f > 0 and bad > 0
+    ok = ((a.status == 0) & (b.status == 0))
+    assert torch.equal(a.status, b.status) and int(ok.sum()) > 100
+    assert torch.equal(a.rotations[ok], b.rotations[ok]) and torch.equal(a.n_rows[ok], b.n_rows[ok])
+    assert torch.equal(a.knot_counts[ok], b.knot_counts[ok])
+    for s_ in [int(i) for i in torch.nonzero(ok).flatten()[:10]]:
+        if dt == "f32":
+            want = o.c_decompose(x32[s_], 11)
+            assert b.rows_of(s_).cpu().numpy().tobytes() == want.rotations.tobytes(), s_
+        else:
+            want = o.c_decompose(x32[s_].astype(np.float64), 11)
+            assert b.rows_of(s_).cpu().numpy().tobytes() == want.rotations.astype(np.float32).tobytes(), s_
