@@ -61,41 +61,44 @@ __global__ void __launch_bounds__(256) wpe3_kernel(const InT *__restrict__ rows,
     for (int k = 0; k < 6; ++k) s_acc[k][threadIdx.x] = 0.0;
     unsigned seen = 0;                                     // bit k: pattern k occurred
     constexpr int UN = 4;                                  // windows in flight per thread (12 loads)
-    const long long nwin = n - 2;
-    for (long long i0 = threadIdx.x; i0 < nwin; i0 += (long long)UN * blockDim.x) {
+    auto window = [&](const double a, const double b, const double c) {
+        // ascending hash order of MEITD.py:108: (2,1,0) (1,2,0) (2,0,1) (0,2,1) (1,0,2) (0,1,2):
+        //   a <= b ? (b <= c ? 5 : (a <= c ? 3 : 2)) : (a <= c ? 4 : (b <= c ? 1 : 0))
+        // without branches (a six-way divergent branch tree per window is what the compiler made of the ternaries):
+        // three compare bits index a packed table
+        const unsigned idx = ((a <= b) ? 4u : 0u) | ((b <= c) ? 2u : 0u) | ((a <= c) ? 1u : 0u);
+        const int slot = (int)((0x55324140u >> (4u * idx)) & 7u);
+        // population variance of the window (MEITD.py:112-113).  The result is compared at 1e-9 absolute, not bit for
+        // bit (the reference's own summation order inside numpy.var is not specified), so the three squares are
+        // accumulated with fused multiply-adds and the two divisions by 3 are multiplications: 11 fp64 operations per
+        // window instead of 22.
+        const double third = 1.0 / 3.0;
+        const double mean = __dmul_rn(__dadd_rn(__dadd_rn(a, b), c), third);
+        const double d0 = __dsub_rn(a, mean), d1 = __dsub_rn(b, mean), d2 = __dsub_rn(c, mean);
+        const double w = __dmul_rn(__fma_rn(d2, d2, __fma_rn(d1, d1, __dmul_rn(d0, d0))), third);
+        seen |= 1u << slot;
+        // the thread's six weighted counts live in shared memory, indexed by the pattern: one load, one add, one store
+        // per window instead of six selects and six additions
+        double *ap = &s_acc[slot][threadIdx.x];
+        *ap = __dadd_rn(*ap, w);
+    };
+    // 32-bit indices (the host entry point rejects rows of 2^31 samples or more); the main loop has no bounds checks, the
+    // tail takes single windows
+    const int nwin = (int)(n - 2), bd = (int)blockDim.x;
+    int i0 = (int)threadIdx.x;
+    for (; i0 + (UN - 1) * bd < nwin; i0 += UN * bd) {
         double a[UN], b[UN], c[UN];
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
-            const long long i = i0 + (long long)u * blockDim.x;
-            const bool in = i < nwin;
-            a[u] = in ? (double)__ldg(x + i) : 0.0;
-            b[u] = in ? (double)__ldg(x + i + 1) : 0.0;
-            c[u] = in ? (double)__ldg(x + i + 2) : 0.0;
+            const InT *q = x + i0 + u * bd;
+            a[u] = (double)__ldg(q);
+            b[u] = (double)__ldg(q + 1);
+            c[u] = (double)__ldg(q + 2);
         }
 #pragma unroll
-        for (int u = 0; u < UN; ++u) {
-            if (i0 + (long long)u * blockDim.x >= nwin) break;
-            // ascending hash order of MEITD.py:108: (2,1,0) (1,2,0) (2,0,1) (0,2,1) (1,0,2) (0,1,2):
-            //   a <= b ? (b <= c ? 5 : (a <= c ? 3 : 2)) : (a <= c ? 4 : (b <= c ? 1 : 0))
-            // without branches (a six-way divergent branch tree per window is what the compiler made of the ternaries):
-            // three compare bits index a packed table
-            const unsigned idx = ((a[u] <= b[u]) ? 4u : 0u) | ((b[u] <= c[u]) ? 2u : 0u) | ((a[u] <= c[u]) ? 1u : 0u);
-            const int slot = (int)((0x55324140u >> (4u * idx)) & 7u);
-            // population variance of the window (MEITD.py:112-113).  The result is compared at 1e-9 absolute, not bit for
-            // bit (the reference's own summation order inside numpy.var is not specified), so the three squares are
-            // accumulated with fused multiply-adds and the two divisions by 3 are multiplications: 11 fp64 operations per
-            // window instead of 22 -- the kernel was bound by the fp64 pipe and the issue slots, not by HBM.
-            const double third = 1.0 / 3.0;
-            const double mean = __dmul_rn(__dadd_rn(__dadd_rn(a[u], b[u]), c[u]), third);
-            const double d0 = __dsub_rn(a[u], mean), d1 = __dsub_rn(b[u], mean), d2 = __dsub_rn(c[u], mean);
-            const double w = __dmul_rn(__fma_rn(d2, d2, __fma_rn(d1, d1, __dmul_rn(d0, d0))), third);
-            seen |= 1u << slot;
-            // the thread's six weighted counts live in shared memory, indexed by the pattern: one load, one add, one store
-            // per window instead of six selects and six additions
-            double *ap = &s_acc[slot][threadIdx.x];
-            *ap = __dadd_rn(*ap, w);
-        }
+        for (int u = 0; u < UN; ++u) window(a[u], b[u], c[u]);
     }
+    for (; i0 < nwin; i0 += bd) window((double)__ldg(x + i0), (double)__ldg(x + i0 + 1), (double)__ldg(x + i0 + 2));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // the 256 per-thread sums of a pattern are added as a plain fp64 tree (a double-double tree here cost every thread 1500
     // fp64 instructions per row, a fifth of the kernel, to protect sums whose 256 terms each were accumulated in plain fp64)

@@ -1549,7 +1549,8 @@ extern "C" int pyitd_wpe_device(const void *rows, int64_t n_rows_total, int64_t 
                                 void *stream) {
     if (!rows || !out) return fail(PYITD_E_INVALID, "null argument");
     if (order != 3) return fail(PYITD_E_INVALID, "only order 3 is implemented (the only order the reference uses)");
-    if (n_rows_total < 1 || n_rows_total > 0x7fffffffll || n_samples < 0) return fail(PYITD_E_INVALID, "bad shape");
+    if (n_rows_total < 1 || n_rows_total > 0x7fffffffll || n_samples < 0 || n_samples > 0x7fffffffll)
+        return fail(PYITD_E_INVALID, "bad shape");
     if (valid_rows && rows_per_signal < 1) return fail(PYITD_E_INVALID, "rows_per_signal must be >= 1 with valid_rows");
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == PYITD_F64)
