@@ -27,6 +27,14 @@
 //         after the region's knots are filled with the neighbouring regions' knots ("halo") by 40 threads at the start
 //         of the item.  The spans of such a chunk then stream exactly like spans of a few-knot level.
 //
+//   * FUSED PAIRS (sweep_region_fused, predict_pair): two consecutive few-knot extractions e, e + 1 run as ONE pass that
+//     reads X_e and writes R_e, R_{e+1}, B_{e+1}; B_e lives in registers only (32 bytes per sample instead of 48).  The
+//     pass needs the knots of B_e up front; they are PREDICTED from the knot table without touching the signal -- between
+//     two knots of X_e the baseline is a monotone function of a monotone stretch, so its extrema sit at knots of X_e (or
+//     at sample n-2, whose right neighbour is forced to 0) unless two neighbouring values are equal -- and the pass CHECKS
+//     the prediction on every sample: if a flag word differs the item redoes extraction e on its own.  The predicted knot
+//     count (a lower bound of the true one) also decides whether an extraction that is not fused is probed first.
+//
 // Same arithmetic, same operation order, -fmad=false: bit-identical to the reference in fp64.
 #pragma once
 
