@@ -136,12 +136,25 @@ struct pyitd_plan {
     bool busy_valid = false;
 };
 
-// order this call after the plan's previous call when that one ran on another stream
+// order this call after the plan's previous call when that one ran on another stream.
+// A stream that is being CAPTURED into a CUDA graph (the decomposition is a fixed sequence of memsets and one or a few
+// launches with no host round trip, so it captures; the workspace must exist: call once before capturing) cannot wait for an
+// event recorded outside the capture, nor may an event recorded inside it be waited for outside: the ordering of a graph
+// against the plan's other calls is the caller's, as for any captured work.
+static bool stream_is_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return cs != cudaStreamCaptureStatusNone;
+}
 static int plan_acquire(pyitd_plan *pl, cudaStream_t st) {
-    if (pl->busy_valid && pl->busy_stream != st) CU(cudaStreamWaitEvent(st, pl->busy, 0));
+    if (pl->busy_valid && pl->busy_stream != st && !stream_is_capturing(st)) CU(cudaStreamWaitEvent(st, pl->busy, 0));
     return 0;
 }
 static int plan_release(pyitd_plan *pl, cudaStream_t st) {
+    if (stream_is_capturing(st)) return 0;
     if (!pl->busy) CU(cudaEventCreateWithFlags(&pl->busy, cudaEventDisableTiming));
     CU(cudaEventRecord(pl->busy, st));
     pl->busy_stream = st;

@@ -316,3 +316,44 @@ def test_fused_pairs_fp32_variants(dt, monkeypatch):
         else:
             want = o.c_decompose(x32[s_].astype(np.float64), 11)
             assert b.rows_of(s_).cpu().numpy().tobytes() == want.rotations.astype(np.float32).tobytes(), s_
+
+
+@pytest.mark.parametrize("shape", [(200, 20000, "sweep"), (1, 65536, "coop"), (3, 30000, "coop")])
+def test_cuda_graph_capture_and_replay(shape, monkeypatch):
+    """A decomposition is a fixed sequence of memsets and launches with no host round trip (the level loop and the stop test
+    run on the device: ONE persistent / cooperative launch), so it can be captured into a CUDA graph once the plan's
+    workspace exists, and replayed; warm-up on another stream than the capturing one on purpose."""
+    monkeypatch.delenv("PYITD_FORCE_PATH")
+    pyitd_b200.clear_plan_cache()
+    from pyitd_b200.itd import get_plan
+    S, N, path = shape
+    x = synth.eeg_like(S, N, seed=3, device="cuda")
+    plan = get_plan(0, S, N, _capi.F64, 11, 2, 0)
+    assert plan.path[0] == path
+    rows = plan.rows
+    rot = torch.zeros((S, rows, N), dtype=torch.float64, device="cuda")
+    ints = [torch.zeros(S * (rows if i == 1 else 1), dtype=torch.int32, device="cuda") for i in range(5)]
+
+    def step(st):
+        plan.decompose_device(x.data_ptr(), rot.data_ptr(), None, ints[0].data_ptr(), ints[1].data_ptr(), ints[2].data_ptr(),
+                              ints[3].data_ptr(), ints[4].data_ptr(), st.cuda_stream)
+
+    step(torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        step(side)
+    for _ in range(3):
+        rot.zero_()
+        for t in ints:
+            t.fill_(-7)
+        g.replay()
+        torch.cuda.synchronize()
+        assert int(ints[4].abs().max()) == 0
+        xs = x.cpu().numpy()
+        for s_ in range(min(S, 4)):
+            want = o.c_decompose(xs[s_], 11)
+            nr = int(ints[0][s_])
+            assert nr == want.rotations.shape[0]
+            assert rot[s_, :nr].cpu().numpy().tobytes() == want.rotations.tobytes()
