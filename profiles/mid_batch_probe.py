@@ -16,6 +16,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--samples", type=int, default=65536)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--signals", default="17,32,64,100,159")
     args = ap.parse_args()
     import torch
 
@@ -25,9 +26,12 @@ def main():
 
     dev = torch.device("cuda", 0)
     N = args.samples
-    for S in (17, 32, 64, 100, 159):
+    for S in [int(v) for v in args.signals.split(",")]:
         x = synth.eeg_like(S, N, seed=1234, device=dev)
         out = {"signals": S, "samples": N}
+        os.environ.pop("PYITD_FORCE_PATH", None)
+        pyitd_b200.clear_plan_cache()
+        out["default"] = get_plan(0, S, N, _capi.F64, 11, 2, 0).path[0]
         for path in ("resident", "coop", "sweep", "lookback"):
             if path == "coop" and S > 64:
                 continue

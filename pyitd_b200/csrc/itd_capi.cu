@@ -557,15 +557,36 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
     const bool stream_ok_rows = (n_samples % 4 == 0);             // 16-byte aligned rows for the TMA bulk copies
     const bool stream_ok = stream_ok_rows && stream_tiles <= kStreamMaxTiles;
     bool stream = stream_ok && n_samples >= 2048 && n_signals >= 160;
-    bool resident = !stream && n_signals > 16 && n_signals < 160 && n_samples >= 4096;
+    // geometry of the cooperative kernel (itd_coop.cuh): chunk = about one CTA per SM for one signal; how many signals the
+    // chip holds at once (its shared memory takes ~9 signals of 65 536 fp64 samples, ~37 of 8192)
+    int coop_sms = 0;
+    cudaDeviceGetAttribute(&coop_sms, cudaDevAttrMultiProcessorCount, device);
+    long long coop_C = (n_samples + coop_sms - 1) / coop_sms;
+    coop_C = ((coop_C + 255) / 256) * 256;
+    if (const char *env = getenv("PYITD_COOP_CHUNK")) {
+        const long long v = atoll(env);
+        if (v >= 256 && v % 256 == 0) coop_C = v;
+    }
+    const long long coop_gsz = (n_samples + coop_C - 1) / coop_C;
+    bool coop_one_round = false;
+    if (coop_C <= kCoopMaxChunk && n_samples >= 3) {
+        const size_t csm = (pl->carry_elem == 8) ? coop_smem_bytes<double>((int)coop_C) : coop_smem_bytes<float>((int)coop_C);
+        long long per_sm = (long long)(227 * 1024) / (long long)(csm + 1024);
+        if (per_sm > 2048 / kCoopThreads) per_sm = 2048 / kCoopThreads;
+        // measured (profiles/r2/mid_batch_probe.jsonl, coop_shapes.jsonl): one round of the cooperative kernel beats the
+        // cluster-resident kernel up to ~24 signals (8192 samples: 61 vs 106 us at 17 signals, 104 vs 107 at 32); a second
+        // round does not (65 536 samples: 292 us for 16 signals in two rounds vs 209 us resident)
+        coop_one_round = n_signals <= per_sm * coop_sms / coop_gsz && n_signals <= 24;
+    }
+    bool resident = !stream && !coop_one_round && n_signals > 8 && n_signals < 160 && n_samples >= 4096;
     if (const char *env = getenv("PYITD_FORCE_PATH")) {
         stream = !strcmp(env, "stream") && stream_ok;
         resident = !strcmp(env, "resident");
     }
-    // one long signal: the streaming pipeline made persistent over its tiles (2.4x the look-back kernel at 2^28)
-    bool strided = !stream && !resident && n_signals <= 16 && stream_ok_rows && n_samples >= (1 << 18);
-    if (const char *env = getenv("PYITD_FORCE_PATH")) strided = !strcmp(env, "strided") && n_signals <= 64 && stream_ok_rows;
     pl->resident = resident && res_configure(pl);
+    // one long signal: the streaming pipeline made persistent over its tiles (2.4x the look-back kernel at 2^28)
+    bool strided = !stream && !pl->resident && n_signals <= 16 && stream_ok_rows && n_samples >= (1 << 18);
+    if (const char *env = getenv("PYITD_FORCE_PATH")) strided = !strcmp(env, "strided") && n_signals <= 64 && stream_ok_rows;
     if (pl->resident) stream = strided = false;
     if (stream || strided) cfg = (stream && kStreamWarps == 4) ? 0 : 1;   // the look-back kernels must agree on the tile of the stream / strided kernels
     pl->strided = strided;
@@ -579,20 +600,13 @@ extern "C" int pyitd_plan_create(pyitd_plan **out, int device, int64_t n_signals
     // up to 16 signals that the look-back kernels would take: one cooperative launch, signal on chip, one group barrier per
     // extraction (PYITD_FORCE_PATH=lookback keeps the launch chain).  Chunk: about one CTA per SM for one signal.
     {
-        int sms = 0;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        long long C = (n_samples + sms - 1) / sms;
-        C = ((C + 255) / 256) * 256;
-        if (const char *env = getenv("PYITD_COOP_CHUNK")) {
-            const long long v = atoll(env);
-            if (v >= 256 && v % 256 == 0) C = v;
-        }
-        bool coop = !stream && !pl->resident && !strided && !sweep && n_signals <= 16 && n_samples >= 3 && C <= kCoopMaxChunk;
+        bool coop = !stream && !pl->resident && !strided && !sweep && (coop_one_round || n_signals <= 16) && n_samples >= 3 &&
+                    coop_C <= kCoopMaxChunk;
         if (const char *env = getenv("PYITD_FORCE_PATH"))
-            coop = !strcmp(env, "coop") && n_signals <= 64 && n_samples >= 3 && C <= kCoopMaxChunk && !pl->resident;
+            coop = !strcmp(env, "coop") && n_signals <= 64 && n_samples >= 3 && coop_C <= kCoopMaxChunk && !pl->resident;
         pl->coop = coop;
-        pl->coop_C = (int)C;
-        pl->coop_gsz = (int)((n_samples + C - 1) / C);
+        pl->coop_C = (int)coop_C;
+        pl->coop_gsz = (int)coop_gsz;
     }
     pl->sw_spans = (int)((n_samples + kSweepSpan - 1) / kSweepSpan);
     pl->sw_spw = (pl->sw_spans + kSweepWarps - 1) / kSweepWarps;

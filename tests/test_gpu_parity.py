@@ -366,7 +366,9 @@ def test_default_path_by_shape():
     assert get_plan(0, 1, 1 << 22, _capi.F32, 11, 2, 0).path[0] == "strided"
     assert get_plan(0, 2, 1 << 22, _capi.F32, 11, 2, 0).path[0] == "strided"
     assert get_plan(0, 2, 1 << 16, _capi.F32, 11, 2, 0).path[0] == "coop"
-    assert get_plan(0, 16, 1 << 17, _capi.F64, 11, 2, 0).path[0] == "coop"
+    assert get_plan(0, 4, 1 << 17, _capi.F64, 11, 2, 0).path[0] == "coop"
+    assert get_plan(0, 20, 8192, _capi.F64, 11, 2, 0).path[0] == "coop"           # the chip holds them all at once
+    assert get_plan(0, 12, 65536, _capi.F64, 11, 2, 0).path[0] == "resident"      # ... here it would need a second round
     pyitd_b200.clear_plan_cache()
 
 
