@@ -106,16 +106,41 @@ __global__ void __launch_bounds__(kSplThreads, 4) spline_level_kernel(const Spli
     const double y_last = __dmul_rn(__dadd_rn(xn1, __dsub_rn(__dmul_rn(2.0, xn1), xn2)), 0.5);
     constexpr int M = kSplSlots + 4;
 
+    constexpr int kPre = (M + kSplThreads - 1) / kSplThreads;      // knot-list entries per thread and window
+    int tpre[kPre];
+    bool have_pre = false;
+#pragma unroll
+    for (int i = 0; i < kPre; ++i) tpre[i] = 0;
     for (int win = part; win * kSplUseful < K; win += p.parts) {
         // PCR slot q holds unknown (interior knot) i = base + q = knot entry m = q + 2; rows outside [1, K] are
         // identity rows
         const int base = 1 + win * kSplUseful - kSplHalo;
         __syncthreads();                                   // previous window's readers are done
-        for (int m = tid; m < M; m += kSplThreads) {
-            const int k = base - 2 + m;
-            const bool in = (k >= 0 && k <= K + 1);
-            sm.ts[m] = in ? __ldg(tau + k) : 0;
-            sm.xs[m] = in ? (double)__ldg(xk + k) : 0.0;
+#pragma unroll
+        for (int i = 0; i < kPre; ++i) {
+            const int m = tid + i * kSplThreads;
+            if (m < M) {
+                const int k = base - 2 + m;
+                const bool in = (k >= 0 && k <= K + 1);
+                sm.ts[m] = have_pre ? tpre[i] : (in ? __ldg(tau + k) : 0);
+                sm.xs[m] = in ? (double)__ldg(xk + k) : 0.0;
+            }
+        }
+        {
+            // the NEXT window's slice of the knot list while this window is solved and evaluated: tau into registers, X_k
+            // towards L2.  The first use of the two loads above was the largest single stall of the kernel (a fifth of its warp
+            // samples on the first level, ncu source page).
+            const int kn = base - 2 + p.parts * kSplUseful;            // first entry of this CTA's next window
+            have_pre = (win + p.parts) * kSplUseful < K;
+            if (have_pre) {
+#pragma unroll
+                for (int i = 0; i < kPre; ++i) {
+                    const int k = kn + tid + i * kSplThreads;
+                    tpre[i] = (tid + i * kSplThreads < M && k >= 0 && k <= K + 1) ? __ldg(tau + k) : 0;
+                }
+                const int kq = kn + tid * 16;
+                if (tid < 80 && kq >= 0 && kq <= K + 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(xk + kq));
+            }
         }
         __syncthreads();
         for (int m = tid; m < M; m += kSplThreads) {
