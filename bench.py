@@ -106,6 +106,17 @@ CPU_SAMPLE_CHANNELS = 1024          # both CPU legs (cpu_baseline and --impl ref
 # timed here is ~8x faster per core, i.e. a conservative baseline.
 NUMBA_REFERENCE_PER_CORE = {"value": 1.2e6, "unit": UNIT, "source": "SURVEY.md section 6 / BASELINE.md: ITD.py (numba) "
                             "on one core of the survey container, 52-57 ms per 65 536-sample signal; not measured on this box"}
+try:
+    # measured by tests/golden/time_reference_numba.py (imports /root/reference/ITD.py unmodified) in the build container
+    _nt = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_numba_timing.json")))
+    NUMBA_REFERENCE_PER_CORE = {
+        "value": _nt["config2_channels_65536"]["samples_per_s_per_core"], "unit": UNIT,
+        "config1_ms": _nt["config1_chirp_65536"]["ms_median"],
+        "source": "the unmodified reference ITD().itd (Python + numba), one core, JIT excluded, on 8 channels of this workload's "
+                  "generator; measured in the BUILD CONTAINER (%s), not on this box: tests/golden/time_reference_numba.py"
+                  % _nt["host"]["cpu"]}
+except Exception:
+    pass
 
 
 def cpu_port_throughput(n_samples: int, budget_s: float = 12.0, max_channels: int = CPU_SAMPLE_CHANNELS):
